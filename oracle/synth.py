@@ -1,0 +1,138 @@
+"""Portable synthetic weights / inputs for parity tests (TEST INFRASTRUCTURE, see
+grafp_oracle.py header).
+
+torch's CPU RNG streams are build- and ISA-dependent, so golden vectors are not keyed
+on ``torch.manual_seed``.  Instead every tensor is derived from numpy's PCG64 *integer*
+stream mapped to floats by exact arithmetic -- bit-identical on every machine -- and
+loaded into the reference / the oracle / the CUDA modules through ``state_dict``.
+
+``state_spec`` restates the reference's ``state_dict`` layout (names, shapes, order):
+encoder/graph_encoder.py:151-179 (stem, backbone, proj), encoder/gcn_lib/torch_vertex.py:
+146-172 (Grapher: relative_pos, fc1, graph_conv.gconv.nn, fc2), encoder/graph_encoder.py:
+38-89 (Downsample, FFN), simclr/simclr.py:13-28 + peak_extractor.py:14-23 (wrapper).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+from .grafp_oracle import SIZES, backbone_layout
+
+Spec = List[Tuple[str, Tuple[int, ...], str]]   # (name, shape, role)
+
+
+def _bn(prefix: str, c: int) -> Spec:
+    return [(prefix + ".weight", (c,), "bn_w"), (prefix + ".bias", (c,), "bn_b"),
+            (prefix + ".running_mean", (c,), "bn_rm"), (prefix + ".running_var", (c,), "bn_rv"),
+            (prefix + ".num_batches_tracked", (), "count")]
+
+
+def encoder_state_spec(size: str = "t", in_channels: int = 8, emb_dims: int = 1024,
+                       n_nodes: int = 256) -> Spec:
+    """Ordered (name, shape, role) list of GraphEncoder.state_dict()."""
+    _, channels = SIZES.get(size, SIZES["b"])
+    spec: Spec = [("stem.0.weight", (channels[0], in_channels, 1, 1), "w")]
+    spec += _bn("stem.1", channels[0])
+    n_rel = n_nodes
+    for i, (kind, cin, cout) in enumerate(backbone_layout(size)):
+        pre = "backbone.%d" % i
+        if kind == "down":
+            n_rel = n_rel // 4                                   # graph_encoder.py:166
+            spec += [(pre + ".conv.0.weight", (cout, cin, 3, 3), "w"),
+                     (pre + ".conv.0.bias", (cout,), "b")]
+            spec += _bn(pre + ".conv.1", cout)
+            continue
+        c = cin
+        g = pre + ".0"
+        spec += [(g + ".relative_pos", (1, n_rel, n_rel), "relpos"),
+                 (g + ".fc1.0.weight", (c, c, 1, 1), "w"), (g + ".fc1.0.bias", (c,), "b")]
+        spec += _bn(g + ".fc1.1", c)
+        spec += [(g + ".graph_conv.gconv.nn.0.weight", (2 * c, (2 * c) // 4, 1, 1), "w"),
+                 (g + ".graph_conv.gconv.nn.0.bias", (2 * c,), "b")]
+        spec += _bn(g + ".graph_conv.gconv.nn.1", 2 * c)
+        spec += [(g + ".fc2.0.weight", (c, 2 * c, 1, 1), "w"), (g + ".fc2.0.bias", (c,), "b")]
+        spec += _bn(g + ".fc2.1", c)
+        f = pre + ".1"
+        spec += [(f + ".fc1.0.weight", (4 * c, c, 1, 1), "w")]
+        spec += _bn(f + ".fc1.1", 4 * c)
+        spec += [(f + ".fc2.0.weight", (c, 4 * c, 1, 1), "w")]
+        spec += _bn(f + ".fc2.1", c)
+    spec += [("proj.weight", (emb_dims, channels[-1], 1, 1), "w"), ("proj.bias", (emb_dims,), "b")]
+    return spec
+
+
+def simclr_state_spec(cfg: dict, size: str = "t") -> Spec:
+    """Ordered spec of SimCLR(cfg, GraphEncoder(...)).state_dict() for arch 'grafp'.
+    Module registration order in simclr/simclr.py:8-28: encoder, peak_extractor, projector."""
+    n_nodes = cfg["n_mels"] * cfg["n_frames"] // (cfg["patch_bins"] * cfg["patch_frames"])
+    enc = [("encoder." + n, s, r) for n, s, r in
+           encoder_state_spec(size, cfg["n_filters"], cfg["h"], n_nodes)]
+    pk = [("peak_extractor.convs.0.weight",
+           (cfg["n_filters"], 3, cfg["patch_bins"], cfg["patch_frames"]), "w"),
+          ("peak_extractor.convs.0.bias", (cfg["n_filters"],), "b")]
+    du = cfg["d"] * cfg["u"]
+    pr = [("projector.0.weight", (du, cfg["h"]), "w"), ("projector.0.bias", (du,), "b"),
+          ("projector.2.weight", (cfg["d"], du), "w"), ("projector.2.bias", (cfg["d"],), "b")]
+    return enc + pk + pr
+
+
+def _uniform(rng: np.random.Generator, shape, lo: float, hi: float) -> np.ndarray:
+    """Exact-arithmetic uniform floats: 24-bit integers / 2^24 in float64, affine, -> fp32."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    u = rng.integers(0, 1 << 24, size=n, dtype=np.int64).astype(np.float64) / float(1 << 24)
+    return (lo + (hi - lo) * u).astype(np.float32).reshape(shape)
+
+
+def synth_state(spec: Spec, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """Deterministic, portable state_dict for ``spec``.  BN statistics / affine terms and
+    biases are non-trivial so that BN folding and bias paths are really exercised."""
+    out: Dict[str, torch.Tensor] = {}
+    for i, (name, shape, role) in enumerate(spec):
+        rng = np.random.Generator(np.random.PCG64([seed, i]))
+        if role == "w":
+            fan_in = int(np.prod(shape[1:]))
+            b = float(np.sqrt(3.0 / fan_in))              # unit-gain: var = 1/fan_in
+            a = _uniform(rng, shape, -b, b)
+        elif role == "b":
+            a = _uniform(rng, shape, -0.1, 0.1)
+        elif role == "bn_w":
+            a = _uniform(rng, shape, 0.6, 1.2)
+        elif role == "bn_b":
+            a = _uniform(rng, shape, -0.2, 0.2)
+        elif role == "bn_rm":
+            a = _uniform(rng, shape, -0.3, 0.3)
+        elif role == "bn_rv":
+            a = _uniform(rng, shape, 0.5, 1.5)
+        elif role == "count":
+            out[name] = torch.zeros((), dtype=torch.int64)
+            continue
+        elif role == "relpos":
+            a = np.zeros(shape, dtype=np.float32)         # never read on the hot path (Q7)
+        else:
+            raise ValueError(role)
+        out[name] = torch.from_numpy(a.copy())
+    return out
+
+
+def synth_uniform(shape, seed: int, lo: float = 0.0, hi: float = 1.0) -> torch.Tensor:
+    rng = np.random.Generator(np.random.PCG64([seed, 0xC0FFEE]))
+    return torch.from_numpy(_uniform(rng, tuple(shape), lo, hi).copy())
+
+
+def synth_normal(shape, seed: int) -> torch.Tensor:
+    """Portable ~N(0,1): sum of 12 exact uniforms - 6 (Irwin-Hall), float64 -> fp32."""
+    rng = np.random.Generator(np.random.PCG64([seed, 0xBEEF]))
+    n = int(np.prod(shape))
+    u = rng.integers(0, 1 << 24, size=(12, n), dtype=np.int64).astype(np.float64) / float(1 << 24)
+    return torch.from_numpy((u.sum(0) - 6.0).astype(np.float32).reshape(tuple(shape)).copy())
+
+
+def state_sha256(sd: Dict[str, torch.Tensor]) -> str:
+    h = hashlib.sha256()
+    for name in sd:
+        h.update(name.encode())
+        h.update(sd[name].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()

@@ -1,0 +1,187 @@
+"""Pins the CPU oracle (oracle/grafp_oracle.py) to outputs of the reference itself.
+
+* against the committed fixtures in tests/golden/ (made by make_golden.py from the live
+  reference) -- runs everywhere;
+* against the live reference on every intermediate tensor -- only where /root/reference
+  exists (this container), skipped on the GPU box.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grafp_oracle as O
+from oracle import synth
+from refimport import reference_available, import_reference
+
+torch.set_num_threads(1)
+CFG = dict(n_mels=64, n_frames=128, patch_bins=4, patch_frames=8, n_filters=8, tau=0.05,
+           d=128, h=1024, u=32, dim=2048, arch="grafp", bsz_train=256, lr=8.0e-5)
+
+
+def _enc_state():
+    return synth.synth_state(synth.encoder_state_spec("t", 8, 1024, 256), 1234)
+
+
+@pytest.mark.parametrize("fname,k", [("encoder_t_k3.npz", 3), ("encoder_t_k5.npz", 5)])
+def test_encoder_matches_golden(golden_dir, fname, k):
+    g = np.load(os.path.join(golden_dir, fname))
+    sd = _enc_state()
+    assert synth.state_sha256(sd) == str(g["weights_sha256"])
+    taps = []
+    with torch.no_grad():
+        emb = O.encoder_forward(sd, torch.from_numpy(g["x"]), k=k, taps=taps)
+    # same ATen ops, same order, single thread: the CPU oracle reproduces the reference to fp32
+    # round-off; demand 1e-5 relative (bit-exact in this container).
+    np.testing.assert_allclose(emb.numpy(), g["emb"], rtol=1e-5, atol=1e-5)
+    for i, t in enumerate(taps[1:]):
+        if t["kind"] != "block":
+            continue
+        ref_idx = g["idx_%d" % i].astype(np.int64)
+        tie = O.knn_tie_rows(t["dist"], k, 1e-6).numpy()
+        bad = (t["idx"].numpy() != ref_idx).any(-1) & ~tie
+        assert not bad.any(), "layer %d: %d rows differ off-tie" % (i, bad.sum())
+        if "knn_in_%d" % i in g.files and g["knn_in_%d" % i].shape[0]:
+            np.testing.assert_allclose(t["knn_in"][:1, :, :, 0].numpy(), g["knn_in_%d" % i],
+                                       rtol=1e-5, atol=1e-6)
+        if "out_%d_sample" % i in g.files:
+            flat = t["out"].reshape(t["out"].shape[0], -1)
+            np.testing.assert_allclose(flat[:, ::61].numpy(), g["out_%d_sample" % i], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("fname,k,d", [("dygraph_k9_d2.npz", 9, 2), ("dygraph_k4_d3_n96.npz", 4, 3)])
+def test_dygraph_dilated_matches_golden(golden_dir, fname, k, d):
+    g = np.load(os.path.join(golden_dir, fname))
+    spec = [("gconv.nn.0.weight", (128, 32, 1, 1), "w"), ("gconv.nn.0.bias", (128,), "b")] + \
+        synth._bn("gconv.nn.1", 128)
+    sd = synth.synth_state(spec, 1235)
+    p = {"gc." + n: t for n, t in sd.items()}
+    taps = {}
+    with torch.no_grad():
+        y = O.dy_graph_conv(p, "gc", torch.from_numpy(g["x"]), k, d, "mr", "relu", False, None, taps)
+    tie = O.knn_tie_rows(taps["dist"], k * d, 1e-6).numpy()
+    bad = (taps["idx"].numpy() != g["idx"].astype(np.int64)).any(-1) & ~tie
+    assert not bad.any()
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-5, atol=1e-5)
+
+
+def test_ntxent_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ntxent_b16.npz"))
+    zi = torch.from_numpy(g["z_i"]).requires_grad_(True)
+    zj = torch.from_numpy(g["z_j"]).requires_grad_(True)
+    loss = O.ntxent(zi, zj, float(g["tau"]))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-6)
+    np.testing.assert_allclose(zi.grad.numpy(), g["g_i"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(zj.grad.numpy(), g["g_j"], rtol=1e-4, atol=1e-6)
+    with torch.no_grad():
+        loop = O.ntxent_loop(torch.from_numpy(g["z_i"]), torch.from_numpy(g["z_j"]), 0.05)
+    np.testing.assert_allclose(loop.item(), g["loss"], rtol=1e-6)
+
+
+def test_simclr_eval_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "simclr_eval_b4.npz"))
+    sd = synth.synth_state(synth.simclr_state_spec(CFG, "t"), 1236)
+    assert synth.state_sha256(sd) == str(g["weights_sha256"])
+    s_i = synth.synth_normal((4, 64, 128), 21)
+    s_j = s_i + 0.1 * synth.synth_normal((4, 64, 128), 22)
+    with torch.no_grad():
+        h_i, h_j, z_i, z_j = O.simclr_forward(sd, s_i, s_j, k=3)
+    np.testing.assert_allclose(h_i.numpy(), g["h_i"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(z_i.numpy(), g["z_i"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(z_j.numpy(), g["z_j"], rtol=1e-5, atol=1e-6)
+
+
+def test_simclr_train_step_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "simclr_train_b8.npz"))
+    sd = synth.synth_state(synth.simclr_state_spec(CFG, "t"), 1236)
+    names = [str(n) for n in g["grad_names"]]
+    params = {n: (t.clone().requires_grad_(True) if n in names else t.clone()) for n, t in sd.items()}
+    s_i = synth.synth_normal((8, 64, 128), 21)
+    s_j = s_i + 0.1 * synth.synth_normal((8, 64, 128), 22)
+    stats = {}
+    h_i, h_j, z_i, z_j = O.simclr_forward(params, s_i, s_j, k=5, training=True, stats=stats)
+    loss = O.ntxent(z_i, z_j, CFG["tau"])
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+    np.testing.assert_allclose(z_i.detach().numpy(), g["z_i"], rtol=1e-4, atol=1e-6)
+    norms = np.array([float(params[n].grad.double().norm()) for n in names])
+    # biases in front of a train-mode BN have mathematically zero gradient (~1e-6 noise)
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=5e-6)
+    total = float(np.sqrt((norms ** 2).sum()))
+    np.testing.assert_allclose(total, g["grad_total"], rtol=1e-4)
+    # clip + Adam restatement against the reference's torch.optim step
+    grads = [params[n].grad for n in names]
+    O.clip_grad_norm_(grads, 1.0)
+    post = {}
+    for n in names:
+        p_ = params[n].detach().clone()
+        O.adam_step(p_, params[n].grad, torch.zeros_like(p_), torch.zeros_like(p_), 1, CFG["lr"])
+        post[n] = p_
+    got = np.concatenate([post[n].reshape(-1)[:: max(1, post[n].numel() // 16)][:16].numpy()
+                          for n in ("encoder.stem.0.weight", "encoder.backbone.0.0.fc1.0.weight",
+                                    "encoder.backbone.7.1.fc2.0.weight", "encoder.proj.weight",
+                                    "projector.2.weight", "peak_extractor.convs.0.weight")])
+    np.testing.assert_allclose(got, g["post_step_sample"], rtol=1e-5, atol=1e-7)
+
+
+def test_state_spec_counts():
+    spec = synth.encoder_state_spec("t", 8, 1024, 256)
+    assert len(spec) == 437
+    n = sum(int(np.prod(s)) if len(s) else 1 for _, s, _ in spec)
+    assert n == 13839072
+    full = synth.simclr_state_spec(CFG, "t")
+    assert len(full) == 443
+
+
+# ----------------------------------------------------------------------------------- #
+# live reference (this container only)
+# ----------------------------------------------------------------------------------- #
+needs_ref = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+
+
+@needs_ref
+@pytest.mark.reference
+def test_oracle_vs_live_reference_encoder():
+    ref = import_reference()
+    torch.manual_seed(0)
+    enc = ref.GraphEncoder(cfg=ref.cfg, in_channels=8, k=3).eval()
+    x = torch.rand(3, 8, 256)
+    with torch.no_grad():
+        a = enc(x)
+        b = O.encoder_forward(enc.state_dict(), x, k=3)
+    assert torch.equal(a, b)
+
+
+@needs_ref
+@pytest.mark.reference
+def test_oracle_vs_live_reference_grapher_train_mode():
+    ref = import_reference()
+    torch.manual_seed(1)
+    m = ref.Grapher(64, 9, 2, "mr", "relu", "batch", True, False, 0.2, 1, n=64, relative_pos=False).train()
+    sd = {"g." + n: t.clone() for n, t in m.state_dict().items()}
+    x = torch.randn(2, 64, 64, 1)
+    a = m(x)
+    stats = {}
+    b = O.grapher(sd, "g", x, 9, 2, "mr", "relu", True, stats)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+    new = m.state_dict()
+    for n, t in stats.items():
+        assert torch.allclose(new[n[2:]], t, rtol=1e-6, atol=1e-7), n
+
+
+@needs_ref
+@pytest.mark.reference
+def test_oracle_vs_live_reference_edgeconv_and_select():
+    ref = import_reference()
+    torch.manual_seed(2)
+    m = ref.DyGraphConv2d(32, 64, 4, 1, "edge", "gelu", "batch", True).eval()
+    sd = {"gc." + n: t for n, t in m.state_dict().items()}
+    x = torch.randn(2, 32, 40, 1)
+    with torch.no_grad():
+        a = m(x)
+        b = O.dy_graph_conv(sd, "gc", x, 4, 1, "edge", "gelu", False, None)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+    idx = torch.randint(0, 40, (2, 40, 5))
+    assert torch.equal(ref.batched_index_select(x, idx), O.gather_nodes(x, idx))
