@@ -1,0 +1,146 @@
+/*
+ * grafp.h -- C ABI of libgrafp_sm100a.so: the B200 (sm_100a) kernels behind the
+ * NeuralSampleID GraphEncoder hot path.
+ *
+ * The reference (chymaera96/NeuralSampleID) has no FFI / operator registry for this
+ * path: every stage is a PyTorch ATen call made from Python nn.Modules.  Each entry
+ * point below therefore replaces a *call site* of the reference (cited per function,
+ * paths relative to the reference root) and is what a ctypes / cffi binding added to
+ * the reference would bind.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, explicit sizes, a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, non-zero on failure;
+ *     grafp_last_error() returns a thread-local message for the last failure.
+ *   - functions never allocate, free or synchronise: outputs and workspaces are
+ *     caller-owned device buffers; work is enqueued on `stream`.
+ *   - activations are NODE-MAJOR fp32: a batch of B graphs with N nodes and C channels
+ *     is a dense (B*N, C) row-major matrix ("rows" = nodes); the reference's NCHW
+ *     (B, C, N, 1) tensors are converted once at the module boundary with
+ *     grafp_nchw_to_nodes / grafp_nodes_to_nchw.
+ *   - neighbour lists are int32 (B, N, k), ascending distance, lowest index first on
+ *     exact ties; the centre index (edge_index[1] in the reference) is implicit.
+ */
+#ifndef GRAFP_H_
+#define GRAFP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRAFP_ABI_VERSION 1
+
+/* activation codes (reference: act_layer, encoder/gcn_lib/torch_nn.py:9-25; ELU for the
+ * projector, simclr/simclr.py:26) */
+enum { GRAFP_ACT_NONE = 0, GRAFP_ACT_RELU = 1, GRAFP_ACT_LEAKY = 2, GRAFP_ACT_GELU = 3,
+       GRAFP_ACT_ELU = 4 };
+
+/* GEMM engines */
+enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 3xTF32 where the shape allows, else SIMT */
+       GRAFP_ENGINE_SIMT = 1,      /* fp32 FFMA tiles                                   */
+       GRAFP_ENGINE_TC_3XTF32 = 2, /* tcgen05 kind::tf32, hi/lo split, fp32-accurate    */
+       GRAFP_ENGINE_TC_TF32 = 3    /* tcgen05 kind::tf32 single pass                    */ };
+
+int grafp_abi_version(void);
+const char* grafp_last_error(void);
+/* number of kernels launched by this library in the calling process (bench bookkeeping) */
+int64_t grafp_launch_count(void);
+
+/* ---- layout -------------------------------------------------------------------------
+ * x.unsqueeze(-1) / the implicit NCHW layout of every reference module
+ * (encoder/graph_encoder.py:201).  src (B, C, N) -> dst (B*N, C) and back. */
+int grafp_nchw_to_nodes(const float* src, float* dst, int B, int C, int N, void* stream);
+int grafp_nodes_to_nchw(const float* src, float* dst, int B, int C, int N, void* stream);
+
+/* ---- dense dilated kNN graph ----------------------------------------------------------
+ * Replaces DenseDilatedKnnGraph.forward (encoder/gcn_lib/torch_edge.py:270-284):
+ * F.normalize(x, p=2, dim=1) (:281, eps 1e-12), dense_knn_matrix (:70-103) with
+ * pairwise_distance (:7-18, association order (sq_i + (-2 x_i.x_j)) + sq_j),
+ * topk(-dist, k*dilation) (:100) and DenseDilated's [::dilation] stride (:245-255).
+ *   x        (B*N, C) node-major features (un-normalised when `normalize` != 0)
+ *   idx_out  (B, N, k) int32: ranks 0, d, 2d, ... of the ascending-distance list
+ *   dist_out optional (B, N, k) fp32 distances of the selected ranks (may be NULL)
+ * Limits: k*dilation <= 128, k*dilation <= N, C % 4 == 0, N <= 4096. */
+int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dilation, int normalize,
+                  int32_t* idx_out, float* dist_out, void* stream);
+
+/* ---- neighbour gather + max-relative aggregation ---------------------------------------
+ * Replaces the two batched_index_select calls (encoder/gcn_lib/torch_nn.py:79-98) and
+ * max(x_j - x_i) of MRConv2d.forward (encoder/gcn_lib/torch_vertex.py:21-29).
+ *   x (B*N, C), idx (B, N, k) int32 -> m (B*N, C), m[n,c] = max_k (x[idx[n,k],c] - x[n,c]).
+ *   arg_out optional (B*N, C) uint8: winning rank (first maximum), used by the backward. */
+int grafp_mr_aggregate_fwd(const float* x, const int32_t* idx, int B, int N, int C, int k,
+                           float* m, uint8_t* arg_out, void* stream);
+/* dx (B*N, C) += scatter of dm through the arg-max neighbour, minus dm at the centre.
+ * dx must be initialised by the caller (it accumulates). */
+int grafp_mr_aggregate_bwd(const float* dm, const int32_t* idx, const uint8_t* arg, int B,
+                           int N, int C, int k, float* dx, void* stream);
+/* plain batched_index_select (torch_nn.py:79-98): out (B, C, N, k) from x (B*N, C). */
+int grafp_index_select(const float* x, const int32_t* idx, int B, int N, int C, int k,
+                       float* out_bcnk, void* stream);
+
+/* ---- 1x1-conv family as GEMM with fused epilogue -----------------------------------------
+ * y[m, n] = act( scale[n] * sum_k A[m, k] * W[n, k] + shift[n] ) + residual[m, n]
+ * Replaces Conv2d(1x1)+BatchNorm2d(+activation)(+shortcut) at: stem
+ * (encoder/graph_encoder.py:151-153), Grapher.fc1/fc2 (encoder/gcn_lib/torch_vertex.py:
+ * 152-162,186,193-194), BasicConv groups=4 (encoder/gcn_lib/torch_nn.py:52-64), FFN
+ * (encoder/graph_encoder.py:67-89), Downsample (:38-50, tap3 mode), proj (:179,210) and
+ * the projector Linears (simclr/simclr.py:25-28).
+ *   A is the concatenation along k of two sources a1 (M, k1) and a2 (M, k2) (a2 may be
+ *   NULL, k2 = 0) -- the MRConv interleave (torch_vertex.py:32) is expressed as a column
+ *   permutation of W done once on the host.  With groups > 1, group g reads columns
+ *   [g*k1, (g+1)*k1) of a1 and [g*k2, (g+1)*k2) of a2, rows [g*n, (g+1)*n) of W, and
+ *   writes columns [g*n, (g+1)*n) of y; k1, k2, n are PER-GROUP sizes.
+ *   tap3_nodes > 0 selects the Downsample form: a1 is (B*2*tap3_nodes, k1/3) node-major,
+ *   output row m = (b, j) reads input nodes 2j-1, 2j, 2j+1 of graph b (zero for node -1),
+ *   i.e. Conv2d(3x3, stride 2, pad 1) on an (N,1) image restricted to its centre column. */
+typedef struct {
+  const float* a1; int64_t lda1; int32_t k1;
+  const float* a2; int64_t lda2; int32_t k2;
+  const float* w;  int64_t ldw;            /* (groups*n, k1+k2) row-major               */
+  const float* scale;                       /* (groups*n) or NULL (= 1)                   */
+  const float* shift;                       /* (groups*n) or NULL (= 0)                   */
+  const float* residual; int64_t ldr;       /* (M, groups*n) or NULL                      */
+  float* y; int64_t ldy;                    /* (M, groups*n)                              */
+  int64_t m; int32_t n; int32_t groups;
+  int32_t act; float act_param;
+  int32_t tap3_nodes;
+  int32_t engine;
+} grafp_gemm_args;
+int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream);
+
+/* mean over the nodes of each graph: x (B*N, C) -> out (B, C)   (graph_encoder.py:211) */
+int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream);
+
+/* ---- wrapper stages either side of the encoder ------------------------------------------
+ * GPUPeakExtractorv2.forward (peak_extractor.py:45-69): per-segment min-max normalise,
+ * stack (t-ramp, f-ramp, spec), Conv2d(3, F, (pb, pf), stride (pb, pf)) + ReLU, emitted
+ * node-major (B*N, F) with N = (n_mels/pb)*(n_frames/pf).
+ *   spec (B, n_mels, n_frames); w (F, 3, pb, pf); bias (F). */
+int grafp_peak_extract_fwd(const float* spec, const float* w, const float* bias, int B,
+                           int n_mels, int n_frames, int F, int pb, int pf, float* out,
+                           void* stream);
+/* F.normalize(z, p=2, dim=1, eps) rows of (M, D)   (simclr/simclr.py:38,44) */
+int grafp_l2_normalize_rows(const float* z, int64_t M, int D, float eps, float* out,
+                            void* stream);
+
+/* ---- NT-Xent ------------------------------------------------------------------------------
+ * ntxent_loss (simclr/ntxent.py:5-30).  z (n, D) holds the INTERLEAVED rows
+ * (z_i[0], z_j[0], z_i[1], ...) of the whole (global) batch; rows [row0, row0+rows) are
+ * the calling rank's.  Fused similarity GEMM + masked row log-sum-exp + positive pick:
+ *   lse_out (rows)      logsumexp_{j != i} z_i.z_j / tau
+ *   loss_out (1)        atomically accumulates  -(1/n) * sum_{i in rows} (a[i,i^1] - lse_i)
+ *                       (caller zeroes it)
+ * Backward (gradient of the GLOBAL mean loss w.r.t. this rank's rows; needs lse of all n
+ * rows):  dz_i = (g/(n*tau)) * sum_{j != i} [exp(a_ij-lse_i) + exp(a_ij-lse_j) - 2*[j==i^1]] z_j */
+int grafp_ntxent_fwd(const float* z, int n, int D, float tau, int row0, int rows,
+                     float* lse_out, float* loss_out, void* stream);
+int grafp_ntxent_bwd(const float* z, const float* lse_all, int n, int D, float tau, int row0,
+                     int rows, const float* grad_loss, float* dz, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAFP_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of libgrafp_sm100a.so (the C ABI declared in include/grafp.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing the import of any
+product module fails with an explicit error (run ``python -m neuralsampleid_b200.build`` or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgrafp_sm100a.so")
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_ELU = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32 = 0, 1, 2, 3
+ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "3xtf32": ENGINE_TC_3XTF32,
+           "tf32": ENGINE_TC_TF32}
+
+
+class GrafpError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a1", C.c_void_p), ("lda1", C.c_int64), ("k1", C.c_int32),
+                ("a2", C.c_void_p), ("lda2", C.c_int64), ("k2", C.c_int32),
+                ("w", C.c_void_p), ("ldw", C.c_int64),
+                ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("residual", C.c_void_p), ("ldr", C.c_int64),
+                ("y", C.c_void_p), ("ldy", C.c_int64),
+                ("m", C.c_int64), ("n", C.c_int32), ("groups", C.c_int32),
+                ("act", C.c_int32), ("act_param", C.c_float),
+                ("tap3_nodes", C.c_int32), ("engine", C.c_int32)]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+# name -> argtypes (every function returns int except the three noted below)
+SIGNATURES = {
+    "grafp_nchw_to_nodes": [_P, _P, _I, _I, _I, _P],
+    "grafp_nodes_to_nchw": [_P, _P, _I, _I, _I, _P],
+    "grafp_knn_fwd": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "grafp_mr_aggregate_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "grafp_mr_aggregate_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "grafp_index_select": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "grafp_gemm_fwd": [C.POINTER(GemmArgs), _P],
+    "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
+    "grafp_peak_extract_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "grafp_l2_normalize_rows": [_P, _L, _I, _F, _P, _P],
+    "grafp_ntxent_fwd": [_P, _I, _I, _F, _I, _I, _P, _P, _P],
+    "grafp_ntxent_bwd": [_P, _P, _I, _I, _F, _I, _I, _P, _P, _P],
+}
+SPECIAL = {"grafp_abi_version": ([], C.c_int), "grafp_last_error": ([], C.c_char_p),
+           "grafp_launch_count": ([], C.c_int64)}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once).  Raises GrafpError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GrafpError(
+            "libgrafp_sm100a.so is not built (%s). There is no CPU/PyTorch fallback: run "
+            "`python -m neuralsampleid_b200.build`." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name, (argtypes, restype) in SPECIAL.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(SIGNATURES) + list(SPECIAL)
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().grafp_last_error()
+        raise GrafpError("%s failed: %s" % (what, msg.decode() if msg else "unknown error"))
+
+
+def launch_count() -> int:
+    return int(load().grafp_launch_count())

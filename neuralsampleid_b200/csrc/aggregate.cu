@@ -1,0 +1,228 @@
+// Neighbour gather + max-relative aggregation (the HBM-bound stage of the path).
+//
+// Node-major layout makes one graph a single contiguous N*C*4-byte span, so the staged kernel
+// is a persistent CTA per SM that pulls whole graphs into shared memory with 1-D bulk async
+// copies (TMA engine, mbarrier completion) through a multi-stage ring, gathers neighbours out
+// of shared memory with conflict-free 128-bit loads, and streams the result back with
+// coalesced 128-bit stores: every byte of x crosses HBM once, every byte of m once.
+// Algorithmic bytes per graph-layer: 2*N*C*4 + 4*N*k.
+#include "common.cuh"
+
+namespace grafp {
+
+constexpr int AGG_THREADS = 512;
+constexpr int AGG_MAX_STAGES = 4;
+
+__device__ __forceinline__ void mr_item(const float* __restrict__ sx, const int32_t* __restrict__ nb,
+                                        int k, int C, int node, int c4, float4& out,
+                                        uint32_t& arg) {
+  const float4 xi = *reinterpret_cast<const float4*>(sx + (size_t)node * C + c4 * 4);
+  float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  uint32_t ax = 0, ay = 0, az = 0, aw = 0;
+  for (int t = 0; t < k; ++t) {
+    const int j = __ldg(nb + t);
+    const float4 xj = *reinterpret_cast<const float4*>(sx + (size_t)j * C + c4 * 4);
+    const float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z, dw = xj.w - xi.w;
+    if (dx > best.x) { best.x = dx; ax = t; }
+    if (dy > best.y) { best.y = dy; ay = t; }
+    if (dz > best.z) { best.z = dz; az = t; }
+    if (dw > best.w) { best.w = dw; aw = t; }
+  }
+  out = best;
+  arg = ax | (ay << 8) | (az << 16) | (aw << 24);
+}
+
+__global__ void __launch_bounds__(AGG_THREADS, 1)
+mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int B,
+                           int N, int C, int k, int stages, float* __restrict__ m,
+                           uint32_t* __restrict__ arg_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[AGG_MAX_STAGES];
+  float* sx = reinterpret_cast<float*>(smem_raw);
+  const uint32_t graph_floats = (uint32_t)N * C;
+  const uint32_t graph_bytes = graph_floats * 4u;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int first = blockIdx.x, step = gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const int g = first + s * step;
+      if (g < B) {
+        mbar_arrive_expect_tx(&full[s], graph_bytes);
+        bulk_g2s(sx + (size_t)s * graph_floats, x + (size_t)g * graph_floats, graph_bytes, &full[s]);
+      }
+    }
+  }
+
+  const int c4n = C >> 2;
+  const int items = N * c4n;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int g = first; g < B; g += step) {
+    mbar_wait(&full[s], phase);
+    const float* gx = sx + (size_t)s * graph_floats;
+    const int32_t* gidx = idx + (size_t)g * N * k;
+    float4* gm = reinterpret_cast<float4*>(m + (size_t)g * graph_floats);
+    uint32_t* ga = arg_out ? arg_out + (size_t)g * items : nullptr;
+    for (int it = tid; it < items; it += AGG_THREADS) {
+      const int node = it / c4n, c4 = it - node * c4n;
+      float4 v; uint32_t a;
+      mr_item(gx, gidx + (size_t)node * k, k, C, node, c4, v, a);
+      stg_stream(gm + it, v);
+      if (ga) ga[it] = a;
+    }
+    __syncthreads();                      // every warp is done reading stage s
+    if (tid == 0) {
+      const int gn = g + stages * step;
+      if (gn < B) {
+        mbar_arrive_expect_tx(&full[s], graph_bytes);
+        bulk_g2s(sx + (size_t)s * graph_floats, x + (size_t)gn * graph_floats, graph_bytes, &full[s]);
+      }
+    }
+    if (++s == stages) { s = 0; phase ^= 1u; }
+  }
+}
+
+// Direct (un-staged) form for graphs that do not fit a shared-memory stage: neighbours are
+// gathered straight from global memory (L2-resident: a graph was just written by fc1).
+__global__ void __launch_bounds__(256)
+mr_aggregate_direct_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int N,
+                           int C, int k, float* __restrict__ m, uint32_t* __restrict__ arg_out) {
+  const int g = blockIdx.y;
+  const int c4n = C >> 2;
+  const int items = N * c4n;
+  const float* gx = x + (size_t)g * N * C;
+  const int32_t* gidx = idx + (size_t)g * N * k;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    const int node = it / c4n, c4 = it - node * c4n;
+    float4 v; uint32_t a;
+    mr_item(gx, gidx + (size_t)node * k, k, C, node, c4, v, a);
+    reinterpret_cast<float4*>(m + (size_t)g * N * C)[it] = v;
+    if (arg_out) arg_out[(size_t)g * items + it] = a;
+  }
+}
+
+// batched_index_select: out (B, C, N, k) <- x (B*N, C)[idx]
+__global__ void index_select_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                    int N, int C, int k, float* __restrict__ out) {
+  const int g = blockIdx.y;
+  const size_t total = (size_t)C * N * k;
+  const float* gx = x + (size_t)g * N * C;
+  const int32_t* gidx = idx + (size_t)g * N * k;
+  float* go = out + (size_t)g * total;
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(o % k);
+    const int n = (int)((o / k) % N);
+    const int c = (int)(o / ((size_t)k * N));
+    go[o] = gx[(size_t)gidx[(size_t)n * k + t] * C + c];
+  }
+}
+
+// backward: dx[j*] += dm, dx[n] -= dm, accumulated per graph in shared memory when it fits.
+__global__ void __launch_bounds__(256)
+mr_aggregate_bwd_kernel(const float* __restrict__ dm, const int32_t* __restrict__ idx,
+                        const uint8_t* __restrict__ arg, int N, int C, int k, int use_smem,
+                        float* __restrict__ dx) {
+  extern __shared__ __align__(16) float acc[];
+  const int g = blockIdx.x;
+  const size_t gbase = (size_t)g * N * C;
+  const int total = N * C;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) acc[i] = 0.0f;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int n = i / C, c = i - n * C;
+    const float gval = dm[gbase + i];
+    const int j = idx[((size_t)g * N + n) * k + arg[gbase + i]];
+    if (use_smem) {
+      atomicAdd(&acc[j * C + c], gval);
+      atomicAdd(&acc[i], -gval);
+    } else {
+      atomicAdd(&dx[gbase + (size_t)j * C + c], gval);
+      atomicAdd(&dx[gbase + i], -gval);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dx[gbase + i] += acc[i];
+  }
+}
+
+}  // namespace grafp
+
+using namespace grafp;
+
+extern "C" {
+
+int grafp_mr_aggregate_fwd(const float* x, const int32_t* idx, int B, int N, int C, int k,
+                           float* m, uint8_t* arg_out, void* stream) {
+  GRAFP_REQUIRE(x && idx && m, "mr_aggregate: null pointer");
+  GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0 && k <= 255, "mr_aggregate: bad sizes");
+  GRAFP_REQUIRE(C % 4 == 0, "mr_aggregate: C=%d must be a multiple of 4", C);
+  if (B == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const size_t graph_bytes = (size_t)N * C * 4;
+  const size_t budget = 200 * 1024;
+  if (graph_bytes <= budget / 2 && graph_bytes % 16 == 0) {
+    int stages = (int)(budget / graph_bytes);
+    if (stages > AGG_MAX_STAGES) stages = AGG_MAX_STAGES;
+    int grid = sm_count();
+    if (grid > B) grid = B;
+    const size_t smem = (size_t)stages * graph_bytes;
+    cudaFuncSetAttribute(mr_aggregate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    mr_aggregate_staged_kernel<<<grid, AGG_THREADS, smem, st>>>(
+        x, idx, B, N, C, k, stages, m, reinterpret_cast<uint32_t*>(arg_out));
+    return check_launch("mr_aggregate_staged");
+  }
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    const int items = N * (C / 4);
+    dim3 grid((items + 255) / 256 > 64 ? 64 : (items + 255) / 256, nb);
+    mr_aggregate_direct_kernel<<<grid, 256, 0, st>>>(
+        x + (size_t)b0 * N * C, idx + (size_t)b0 * N * k, N, C, k, m + (size_t)b0 * N * C,
+        arg_out ? reinterpret_cast<uint32_t*>(arg_out) + (size_t)b0 * items : nullptr);
+    if (int rc = check_launch("mr_aggregate_direct")) return rc;
+  }
+  return 0;
+}
+
+int grafp_mr_aggregate_bwd(const float* dm, const int32_t* idx, const uint8_t* arg, int B, int N,
+                           int C, int k, float* dx, void* stream) {
+  GRAFP_REQUIRE(dm && idx && arg && dx, "mr_aggregate_bwd: null pointer");
+  GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0, "mr_aggregate_bwd: bad sizes");
+  if (B == 0) return 0;
+  const size_t bytes = (size_t)N * C * 4;
+  const int use_smem = bytes <= 200 * 1024;
+  cudaFuncSetAttribute(mr_aggregate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       200 * 1024);
+  mr_aggregate_bwd_kernel<<<B, 256, use_smem ? bytes : 0, as_stream(stream)>>>(dm, idx, arg, N, C,
+                                                                               k, use_smem, dx);
+  return check_launch("mr_aggregate_bwd");
+}
+
+int grafp_index_select(const float* x, const int32_t* idx, int B, int N, int C, int k,
+                       float* out_bcnk, void* stream) {
+  GRAFP_REQUIRE(x && idx && out_bcnk, "index_select: null pointer");
+  GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0, "index_select: bad sizes");
+  if (B == 0) return 0;
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    const size_t total = (size_t)C * N * k;
+    dim3 grid((unsigned)((total + 255) / 256 > 256 ? 256 : (total + 255) / 256), nb);
+    index_select_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+        x + (size_t)b0 * N * C, idx + (size_t)b0 * N * k, N, C, k, out_bcnk + (size_t)b0 * total);
+    if (int rc = check_launch("index_select")) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// grafp_gemm_fwd: argument validation and engine dispatch.
+#include "common.cuh"
+
+namespace grafp {
+int gemm_simt_launch(const grafp_gemm_args& a, cudaStream_t st);
+int gemm_tc_supported(const grafp_gemm_args& a);
+int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st);
+}  // namespace grafp
+
+using namespace grafp;
+
+extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
+  GRAFP_REQUIRE(args, "gemm: null args");
+  const grafp_gemm_args& a = *args;
+  GRAFP_REQUIRE(a.a1 && a.w && a.y, "gemm: null pointer");
+  GRAFP_REQUIRE(a.m >= 0 && a.n > 0 && a.groups > 0 && a.k1 > 0 && a.k2 >= 0, "gemm: bad sizes");
+  GRAFP_REQUIRE((a.k2 == 0) == (a.a2 == nullptr), "gemm: a2/k2 mismatch");
+  GRAFP_REQUIRE(a.k1 % 4 == 0 && a.k2 % 4 == 0, "gemm: k1=%d, k2=%d must be multiples of 4", a.k1,
+                a.k2);
+  GRAFP_REQUIRE(a.k2 == 0 || a.k1 % 16 == 0, "gemm: dual-source needs k1 %% 16 == 0 (k1=%d)", a.k1);
+  GRAFP_REQUIRE(a.lda1 % 4 == 0 && a.lda2 % 4 == 0 && a.ldw % 4 == 0, "gemm: strides must be multiples of 4");
+  GRAFP_REQUIRE((reinterpret_cast<uintptr_t>(a.a1) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(a.a2) & 15) == 0, "gemm: operands must be 16-byte aligned");
+  if (a.tap3_nodes > 0) {
+    GRAFP_REQUIRE(a.groups == 1 && a.k2 == 0 && a.k1 % 12 == 0, "gemm: tap3 needs groups=1, k2=0, k1=3*Cin");
+    GRAFP_REQUIRE(a.m % a.tap3_nodes == 0, "gemm: tap3 m must be a multiple of tap3_nodes");
+  }
+  GRAFP_REQUIRE(a.act >= GRAFP_ACT_NONE && a.act <= GRAFP_ACT_ELU, "gemm: unknown activation %d", a.act);
+  if (a.m == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  switch (a.engine) {
+    case GRAFP_ENGINE_SIMT:
+      return gemm_simt_launch(a, st);
+    case GRAFP_ENGINE_TC_3XTF32:
+    case GRAFP_ENGINE_TC_TF32:
+      GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
+      return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_3XTF32 ? 3 : 1, st);
+    case GRAFP_ENGINE_AUTO:
+      if (gemm_tc_supported(a)) return gemm_tc_launch(a, 3, st);
+      return gemm_simt_launch(a, st);
+    default:
+      return fail("gemm: unknown engine %d", a.engine);
+  }
+}

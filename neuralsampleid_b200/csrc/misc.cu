@@ -1,0 +1,222 @@
+// Error plumbing + the small layout / reduction / wrapper-stage kernels.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace grafp {
+
+thread_local char g_err[512] = {0};
+std::atomic<int64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+// ---------------------------------------------------------------------------------------
+// (B, C, N) <-> (B*N, C): 32x32 smem-tiled transpose, coalesced on both sides.
+// ---------------------------------------------------------------------------------------
+__global__ void transpose_batched_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                         int R, int S) {
+  // src: (B, R, S) -> dst: (B, S, R)
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* s = src + (size_t)b * R * S;
+  float* d = dst + (size_t)b * R * S;
+  const int r0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = s0 + threadIdx.x;
+    if (r < R && c < S) tile[i][threadIdx.x] = s[(size_t)r * S + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = s0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < S) d[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+static int transpose_batched(const float* src, float* dst, int B, int R, int S, cudaStream_t st) {
+  if (B == 0 || R == 0 || S == 0) return 0;
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    int nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((S + 31) / 32, (R + 31) / 32, nb), block(32, 8);
+    transpose_batched_kernel<<<grid, block, 0, st>>>(src + (size_t)b0 * R * S,
+                                                    dst + (size_t)b0 * R * S, R, S);
+    if (int rc = check_launch("transpose")) return rc;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// mean over nodes: (B*N, C) -> (B, C)
+// ---------------------------------------------------------------------------------------
+__global__ void node_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int N,
+                                 int C) {
+  const int b = blockIdx.x;
+  const float* xb = x + (size_t)b * N * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.0f;
+    for (int n = 0; n < N; ++n) s += xb[(size_t)n * C + c];
+    out[(size_t)b * C + c] = s / (float)N;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// row-wise L2 normalise (F.normalize): v / max(||v||, eps)
+// ---------------------------------------------------------------------------------------
+__global__ void l2norm_rows_kernel(const float* __restrict__ z, float* __restrict__ out,
+                                   int64_t M, int D, float eps) {
+  const int warps = blockDim.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* zr = z + row * D;
+  float s = 0.0f;
+  for (int c = lane; c < D; c += 32) s = fmaf(zr[c], zr[c], s);
+  s = warp_sum(s);
+  const float den = fmaxf(sqrtf(s), eps);
+  for (int c = lane; c < D; c += 32) out[row * D + c] = __fdiv_rn(zr[c], den);
+}
+
+// ---------------------------------------------------------------------------------------
+// peak extractor: one CTA per segment.  min/max reduce, then the (pb x pf)/stride patch conv
+// over the 3-plane (t-ramp, f-ramp, normalised spec) image, ReLU, node-major output.
+// ---------------------------------------------------------------------------------------
+__global__ void peak_extract_kernel(const float* __restrict__ spec, const float* __restrict__ w,
+                                    const float* __restrict__ bias, int n_mels, int n_frames,
+                                    int F, int pb, int pf, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* s_spec = sm;                                   // n_mels * n_frames
+  float* s_w = s_spec + n_mels * n_frames;              // F * 3 * pb * pf
+  __shared__ float s_red[64];
+  __shared__ float s_mn, s_mx;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int hw = n_mels * n_frames;
+  const float* sp = spec + (size_t)b * hw;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = tid; i < hw; i += nt) {
+    float v = sp[i];
+    s_spec[i] = v;
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  for (int i = tid; i < F * 3 * pb * pf; i += nt) s_w[i] = w[i];
+  mn = -warp_max(-mn);
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) { s_red[tid >> 5] = mn; s_red[32 + (tid >> 5)] = mx; }
+  __syncthreads();
+  if (tid == 0) {
+    float a = s_red[0], c = s_red[32];
+    for (int i = 1; i < (nt >> 5); ++i) { a = fminf(a, s_red[i]); c = fmaxf(c, s_red[32 + i]); }
+    s_mn = a; s_mx = c;
+  }
+  __syncthreads();
+  const float lo = s_mn, den = s_mx - s_mn;
+  const int gh = n_mels / pb, gw = n_frames / pf, nodes = gh * gw;
+  const float tstep = n_frames > 1 ? 1.0f / (float)(n_frames - 1) : 0.0f;
+  const float fstep = n_mels > 1 ? 1.0f / (float)(n_mels - 1) : 0.0f;
+  const int pp = pb * pf;
+  for (int o = tid; o < nodes * F; o += nt) {
+    const int node = o / F, f = o - node * F;
+    const int gy = node / gw, gx = node - gy * gw;
+    const float* wf = s_w + f * 3 * pp;
+    float acc = 0.0f;
+    for (int ch = 0; ch < 3; ++ch) {
+      for (int i = 0; i < pb; ++i) {
+        const int y = gy * pb + i;
+        for (int j = 0; j < pf; ++j) {
+          const int xx = gx * pf + j;
+          // torch.linspace(0,1,steps): symmetric evaluation, start + i*step for the first half,
+          // end - (steps-1-i)*step for the second (ATen RangeFactories)
+          float v;
+          if (ch == 0) v = (xx < n_frames / 2) ? xx * tstep : 1.0f - (n_frames - 1 - xx) * tstep;
+          else if (ch == 1) v = (y < n_mels / 2) ? y * fstep : 1.0f - (n_mels - 1 - y) * fstep;
+          else v = __fdiv_rn(s_spec[y * n_frames + xx] - lo, den);
+          acc = fmaf(v, wf[ch * pp + i * pf + j], acc);
+        }
+      }
+    }
+    acc += bias[f];
+    out[((size_t)b * nodes + node) * F + f] = fmaxf(acc, 0.0f);
+  }
+}
+
+}  // namespace grafp
+
+using namespace grafp;
+
+extern "C" {
+
+int grafp_abi_version(void) { return GRAFP_ABI_VERSION; }
+const char* grafp_last_error(void) { return g_err; }
+int64_t grafp_launch_count(void) { return g_launches.load(); }
+
+int grafp_nchw_to_nodes(const float* src, float* dst, int B, int C, int N, void* stream) {
+  GRAFP_REQUIRE(src && dst && B >= 0 && C > 0 && N > 0, "nchw_to_nodes: bad arguments");
+  return transpose_batched(src, dst, B, C, N, as_stream(stream));
+}
+int grafp_nodes_to_nchw(const float* src, float* dst, int B, int C, int N, void* stream) {
+  GRAFP_REQUIRE(src && dst && B >= 0 && C > 0 && N > 0, "nodes_to_nchw: bad arguments");
+  return transpose_batched(src, dst, B, N, C, as_stream(stream));
+}
+
+int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream) {
+  GRAFP_REQUIRE(x && out && B >= 0 && N > 0 && C > 0, "node_mean: bad arguments");
+  if (B == 0) return 0;
+  node_mean_kernel<<<B, C < 256 ? ((C + 31) / 32) * 32 : 256, 0, as_stream(stream)>>>(x, out, N, C);
+  return check_launch("node_mean");
+}
+
+int grafp_l2_normalize_rows(const float* z, int64_t M, int D, float eps, float* out,
+                            void* stream) {
+  GRAFP_REQUIRE(z && out && M >= 0 && D > 0, "l2_normalize_rows: bad arguments");
+  if (M == 0) return 0;
+  const int warps = 8;
+  l2norm_rows_kernel<<<(unsigned)((M + warps - 1) / warps), warps * 32, 0, as_stream(stream)>>>(
+      z, out, M, D, eps);
+  return check_launch("l2_normalize_rows");
+}
+
+int grafp_peak_extract_fwd(const float* spec, const float* w, const float* bias, int B,
+                           int n_mels, int n_frames, int F, int pb, int pf, float* out,
+                           void* stream) {
+  GRAFP_REQUIRE(spec && w && bias && out, "peak_extract: null pointer");
+  GRAFP_REQUIRE(pb > 0 && pf > 0 && n_mels % pb == 0 && n_frames % pf == 0,
+                "peak_extract: patch (%d,%d) must tile (%d,%d)", pb, pf, n_mels, n_frames);
+  if (B == 0) return 0;
+  size_t smem = ((size_t)n_mels * n_frames + (size_t)F * 3 * pb * pf) * sizeof(float);
+  GRAFP_REQUIRE(smem <= 200 * 1024, "peak_extract: segment too large for shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(peak_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         200 * 1024);
+    attr_set = true;
+  }
+  peak_extract_kernel<<<B, 256, smem, as_stream(stream)>>>(spec, w, bias, n_mels, n_frames, F, pb,
+                                                          pf, out);
+  return check_launch("peak_extract");
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+"""B200 counterparts of the reference's encoder/gcn_lib/torch_vertex.py: ``MRConv2d`` (:11-34),
+``GraphConv2d`` (:92-111), ``DyGraphConv2d`` (:114-139) and ``Grapher`` (:142-195), with the
+constructor / forward signatures and state_dict keys of the reference.  Every ``forward`` takes
+the reference's NCHW tensors; ``forward_nodes`` is the node-major form GraphEncoder chains
+without layout round trips."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ... import ops
+from ..._prep import fold_conv_bn, sig
+from .pos_embed import get_2d_relative_pos_embed
+from .torch_edge import DenseDilatedKnnGraph
+from .torch_nn import BasicConv
+
+
+class MRConv2d(nn.Module):
+    """Max-relative graph convolution: nn([x, max_j(x_j - x_i)] interleaved)."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.nn = BasicConv([in_channels * 2, out_channels], act, norm, bias)
+
+    def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int) -> torch.Tensor:
+        m = ops.mr_aggregate(x, nn_idx, B, N)
+        return self.nn.forward_nodes(x, m)
+
+    def forward(self, x, edge_index, y=None):
+        if y is not None:
+            raise NotImplementedError("r > 1 (pooled y) graphs are not reached by GraphEncoder (r=1)")
+        B, C, N = x.shape[:3]
+        nodes = ops.nchw_to_nodes(x.reshape(B, C, N))
+        out = self.forward_nodes(nodes, edge_index[0].to(torch.int32), B, N)
+        return ops.nodes_to_nchw(out, B, N).unsqueeze(-1)
+
+
+class GraphConv2d(nn.Module):
+    """Static graph convolution dispatch.  GraphEncoder hard-codes conv='mr' (SURVEY Q2); the other
+    reference variants (edge / sage / gin) are outside the accelerated path."""
+
+    def __init__(self, in_channels, out_channels, conv="edge", act="relu", norm=None, bias=True):
+        super().__init__()
+        if conv == "mr":
+            self.gconv = MRConv2d(in_channels, out_channels, act, norm, bias)
+        elif conv in ("edge", "sage", "gin"):
+            raise NotImplementedError("conv:{} has no sm_100a kernel (GraphEncoder uses 'mr')".format(conv))
+        else:
+            raise NotImplementedError("conv:{} is not supported".format(conv))
+
+    def forward(self, x, edge_index, y=None):
+        return self.gconv(x, edge_index, y)
+
+
+class DyGraphConv2d(GraphConv2d):
+    """Dynamic graph convolution: builds the dilated kNN graph of its input on every call."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, dilation=1, conv="edge", act="relu",
+                 norm=None, bias=True, stochastic=False, epsilon=0.0, r=1):
+        super().__init__(in_channels, out_channels, conv, act, norm, bias)
+        if r != 1:
+            raise NotImplementedError("r > 1 is never used by GraphEncoder (graph_encoder.py:171)")
+        self.k, self.d, self.r = kernel_size, dilation, r
+        self.dilated_knn_graph = DenseDilatedKnnGraph(kernel_size, dilation, stochastic, epsilon)
+
+    def forward_nodes(self, x: torch.Tensor, B: int, N: int, nn_idx: torch.Tensor = None) -> torch.Tensor:
+        if nn_idx is None:
+            nn_idx = self.dilated_knn_graph.knn_nodes(x, B, N)
+        return self.gconv.forward_nodes(x, nn_idx, B, N)
+
+    def forward(self, x, relative_pos=None):
+        if relative_pos is not None:
+            raise NotImplementedError("relative_pos is never passed on the GraphEncoder path")
+        B, C, H, W = x.shape
+        nodes = ops.nchw_to_nodes(x.reshape(B, C, H * W))
+        out = self.forward_nodes(nodes, B, H * W)
+        return ops.nodes_to_nchw(out, B, H * W).reshape(B, -1, H, W)
+
+
+class Grapher(nn.Module):
+    """x + BN(fc2(graph_conv(BN(fc1(x)))))."""
+
+    def __init__(self, in_channels, kernel_size=9, dilation=1, conv="edge", act="relu", norm=None,
+                 bias=True, stochastic=False, epsilon=0.0, r=1, n=196, drop_path=0.0, relative_pos=False):
+        super().__init__()
+        self.channels, self.n, self.r = in_channels, n, r
+        self.fc1 = nn.Sequential(nn.Conv2d(in_channels, in_channels, 1, stride=1, padding=0),
+                                 nn.BatchNorm2d(in_channels))
+        self.graph_conv = DyGraphConv2d(in_channels, in_channels * 2, kernel_size, dilation, conv, act,
+                                        norm, bias, stochastic, epsilon, r)
+        self.fc2 = nn.Sequential(nn.Conv2d(in_channels * 2, in_channels, 1, stride=1, padding=0),
+                                 nn.BatchNorm2d(in_channels))
+        if drop_path > 0.0:
+            raise NotImplementedError("DropPath is never instantiated by GraphEncoder (SURVEY Q1)")
+        self.drop_path = nn.Identity()
+        self.relative_pos = None
+        if relative_pos:
+            # stored for state_dict compatibility only; never read in forward
+            table = torch.from_numpy(np.float32(get_2d_relative_pos_embed(in_channels, int(n ** 0.5))))
+            table = F.interpolate(table[None, None], size=(n, n // (r * r)), mode="bicubic",
+                                  align_corners=False)
+            self.relative_pos = nn.Parameter(-table.squeeze(1), requires_grad=False)
+        self._cache = {}
+
+    def _folded(self, name: str):
+        seq = getattr(self, name)
+        conv, bn = seq[0], seq[1]
+        key = sig(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        hit = self._cache.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, fold_conv_bn(conv.weight, conv.bias, bn))
+            self._cache[name] = hit
+        return hit[1]
+
+    def forward_nodes(self, x: torch.Tensor, B: int, N: int, nn_idx: torch.Tensor = None,
+                      taps: dict = None) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError("Grapher.forward_nodes is the eval path; training goes through "
+                               "neuralsampleid_b200.autograd")
+        w1, s1, t1 = self._folded("fc1")
+        y = ops.gemm(x, w1, s1, t1)
+        if taps is not None:
+            taps["fc1"] = y
+            if nn_idx is None:
+                nn_idx = self.graph_conv.dilated_knn_graph.knn_nodes(y, B, N)
+            taps["idx"] = nn_idx
+        g = self.graph_conv.forward_nodes(y, B, N, nn_idx)
+        w2, s2, t2 = self._folded("fc2")
+        return ops.gemm(g, w2, s2, t2, residual=x)
+
+    def forward(self, x):
+        B, C, N = x.shape[:3]
+        nodes = ops.nchw_to_nodes(x.reshape(B, C, -1))
+        N = nodes.shape[0] // B
+        out = self.forward_nodes(nodes, B, N)
+        return ops.nodes_to_nchw(out, B, N).reshape(x.shape)

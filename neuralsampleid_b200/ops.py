@@ -1,0 +1,232 @@
+"""Thin functional layer over the C ABI: torch tensors in (device memory + stream plumbing only),
+raw pointers out.  All activations here are NODE-MAJOR fp32: (B*N, C) row-major.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_ELU, ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ENGINES, GemmArgs,
+                   GrafpError, check)
+
+_ACTS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leakyrelu": ACT_LEAKY,
+         "gelu": ACT_GELU, "elu": ACT_ELU}
+
+_engine = ENGINES[os.environ.get("GRAFP_ENGINE", "auto").lower()]
+
+
+def set_engine(name: str) -> None:
+    """Selects the GEMM engine: 'auto' (tcgen05 3xTF32 where shapes allow, else fp32 SIMT),
+    'simt', '3xtf32', 'tf32'."""
+    global _engine
+    _engine = ENGINES[name.lower()]
+
+
+def get_engine() -> int:
+    return _engine
+
+
+def act_code(name) -> int:
+    key = name.lower() if isinstance(name, str) else name
+    if key not in _ACTS:
+        raise NotImplementedError("activation layer [%s] is not found" % name)
+    return _ACTS[key]
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32, name="tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise GrafpError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise GrafpError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def nchw_to_nodes(x: torch.Tensor) -> torch.Tensor:
+    """(B, C, N[,1]) -> (B*N, C)."""
+    x = _chk(x, name="x")
+    B, Cc, N = x.shape[0], x.shape[1], x.shape[2]
+    out = torch.empty((B * N, Cc), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_nchw_to_nodes(_ptr(x), _ptr(out), B, Cc, N, _stream(x)), "nchw_to_nodes")
+    return out
+
+
+def nodes_to_nchw(x: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    """(B*N, C) -> (B, C, N)."""
+    x = _chk(x, name="x")
+    Cc = x.shape[1]
+    out = torch.empty((B, Cc, N), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_nodes_to_nchw(_ptr(x), _ptr(out), B, Cc, N, _stream(x)), "nodes_to_nchw")
+    return out
+
+
+def knn(x: torch.Tensor, B: int, N: int, k: int, dilation: int = 1, normalize: bool = True,
+        return_dist: bool = False):
+    """Dense dilated kNN over node-major features -> int32 (B, N, k) [, fp32 (B, N, k)]."""
+    x = _chk(x, name="x")
+    Cc = x.shape[1]
+    idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
+    dist = torch.empty((B, N, k), device=x.device, dtype=torch.float32) if return_dist else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_knn_fwd(_ptr(x), B, N, Cc, k, dilation, int(normalize), _ptr(idx),
+                                        _ptr(dist), _stream(x)), "knn_fwd")
+    return (idx, dist) if return_dist else idx
+
+
+def mr_aggregate(x: torch.Tensor, idx: torch.Tensor, B: int, N: int, want_arg: bool = False):
+    """m[n, c] = max_k (x[idx[n, k], c] - x[n, c]);  optional uint8 arg-max ranks."""
+    x = _chk(x, name="x")
+    idx = _chk(idx, torch.int32, "idx")
+    Cc, k = x.shape[1], idx.shape[-1]
+    m = torch.empty_like(x)
+    arg = torch.empty((B * N, Cc), device=x.device, dtype=torch.uint8) if want_arg else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_mr_aggregate_fwd(_ptr(x), _ptr(idx), B, N, Cc, k, _ptr(m), _ptr(arg),
+                                                 _stream(x)), "mr_aggregate_fwd")
+    return (m, arg) if want_arg else m
+
+
+def mr_aggregate_bwd(dm: torch.Tensor, idx: torch.Tensor, arg: torch.Tensor, B: int, N: int,
+                     dx: torch.Tensor) -> torch.Tensor:
+    """Accumulates the aggregation gradient into dx (in place)."""
+    dm = _chk(dm, name="dm")
+    Cc, k = dm.shape[1], idx.shape[-1]
+    with torch.cuda.device(dm.device):
+        check(_lib.load().grafp_mr_aggregate_bwd(_ptr(dm), _ptr(idx), _ptr(arg), B, N, Cc, k, _ptr(dx),
+                                                 _stream(dm)), "mr_aggregate_bwd")
+    return dx
+
+
+def index_select(x: torch.Tensor, idx: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    """batched_index_select: (B*N, C) + (B, N', k) -> (B, C, N', k)."""
+    x = _chk(x, name="x")
+    idx = _chk(idx, torch.int32, "idx")
+    Cc, k = x.shape[1], idx.shape[-1]
+    if idx.shape[1] != N:
+        raise GrafpError("index_select: idx must list every node of the graph")
+    out = torch.empty((B, Cc, N, k), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_index_select(_ptr(x), _ptr(idx), B, N, Cc, k, _ptr(out), _stream(x)),
+              "index_select")
+    return out
+
+
+def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
+         shift: Optional[torch.Tensor] = None, act=None, act_param: float = 0.0,
+         residual: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
+         groups: int = 1, tap3_nodes: int = 0, engine: Optional[int] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(scale * [a1 | a2] @ w.T + shift) + residual  (per-group, see include/grafp.h).
+
+    a1: (M, groups*k1) (or the (2M', Cin) node matrix in tap3 mode), a2: (M, groups*k2) or None,
+    w: (groups*n, k1+k2)."""
+    a1 = _chk(a1, name="a1")
+    w = _chk(w, name="w")
+    n_total, ktot = w.shape
+    n = n_total // groups
+    if tap3_nodes > 0:
+        cin = a1.shape[1]
+        k1, k2 = 3 * cin, 0
+        M = a1.shape[0] // 2
+    else:
+        k1 = a1.shape[1] // groups
+        k2 = 0
+        M = a1.shape[0]
+        if a2 is not None:
+            a2 = _chk(a2, name="a2")
+            k2 = a2.shape[1] // groups
+    if k1 + k2 != ktot:
+        raise GrafpError("gemm: weight has %d columns, operands give %d" % (ktot, k1 + k2))
+    if out is None:
+        out = torch.empty((M, n_total), device=a1.device, dtype=torch.float32)
+    args = GemmArgs()
+    args.a1, args.lda1, args.k1 = a1.data_ptr(), a1.stride(0), k1
+    args.a2, args.lda2, args.k2 = (a2.data_ptr() if a2 is not None else None), \
+        (a2.stride(0) if a2 is not None else 0), k2
+    args.w, args.ldw = w.data_ptr(), w.stride(0)
+    args.scale = scale.data_ptr() if scale is not None else None
+    args.shift = shift.data_ptr() if shift is not None else None
+    if residual is not None:
+        residual = _chk(residual, name="residual")
+        args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
+    else:
+        args.residual, args.ldr = None, 0
+    args.y, args.ldy = out.data_ptr(), out.stride(0)
+    args.m, args.n, args.groups = M, n, groups
+    args.act, args.act_param = act_code(act) if not isinstance(act, int) else act, act_param
+    args.tap3_nodes = tap3_nodes
+    args.engine = _engine if engine is None else engine
+    with torch.cuda.device(a1.device):
+        check(_lib.load().grafp_gemm_fwd(C.byref(args), _stream(a1)), "gemm_fwd")
+    return out
+
+
+def node_mean(x: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    x = _chk(x, name="x")
+    out = torch.empty((B, x.shape[1]), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_node_mean(_ptr(x), B, N, x.shape[1], _ptr(out), _stream(x)), "node_mean")
+    return out
+
+
+def peak_extract(spec: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """(B, n_mels, n_frames) -> node-major (B*N, F)."""
+    spec = _chk(spec, name="spec")
+    w = _chk(w, name="w")
+    bias = _chk(bias, name="bias")
+    B, n_mels, n_frames = spec.shape
+    F, _, pb, pf = w.shape
+    nodes = (n_mels // pb) * (n_frames // pf)
+    out = torch.empty((B * nodes, F), device=spec.device, dtype=torch.float32)
+    with torch.cuda.device(spec.device):
+        check(_lib.load().grafp_peak_extract_fwd(_ptr(spec), _ptr(w), _ptr(bias), B, n_mels, n_frames,
+                                                 F, pb, pf, _ptr(out), _stream(spec)), "peak_extract")
+    return out
+
+
+def l2_normalize_rows(z: torch.Tensor, eps: float) -> torch.Tensor:
+    z = _chk(z, name="z")
+    out = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        check(_lib.load().grafp_l2_normalize_rows(_ptr(z), z.shape[0], z.shape[1], eps, _ptr(out),
+                                                  _stream(z)), "l2_normalize_rows")
+    return out
+
+
+def ntxent_fwd(z: torch.Tensor, tau: float, row0: int = 0, rows: Optional[int] = None):
+    """z: (n, D) interleaved rows of the global batch -> (loss_part (1,), lse (rows,))."""
+    z = _chk(z, name="z")
+    n, D = z.shape
+    rows = n if rows is None else rows
+    lse = torch.empty((rows,), device=z.device, dtype=torch.float32)
+    loss = torch.zeros((1,), device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        check(_lib.load().grafp_ntxent_fwd(_ptr(z), n, D, tau, row0, rows, _ptr(lse), _ptr(loss),
+                                           _stream(z)), "ntxent_fwd")
+    return loss, lse
+
+
+def ntxent_bwd(z: torch.Tensor, lse_all: torch.Tensor, tau: float, grad_loss: torch.Tensor,
+               row0: int = 0, rows: Optional[int] = None) -> torch.Tensor:
+    z = _chk(z, name="z")
+    n, D = z.shape
+    rows = n if rows is None else rows
+    dz = torch.empty((rows, D), device=z.device, dtype=torch.float32)
+    grad_loss = _chk(grad_loss.reshape(1), name="grad_loss")
+    with torch.cuda.device(z.device):
+        check(_lib.load().grafp_ntxent_bwd(_ptr(z), _ptr(lse_all), n, D, tau, row0, rows,
+                                           _ptr(grad_loss), _ptr(dz), _stream(z)), "ntxent_bwd")
+    return dz

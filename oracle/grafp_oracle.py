@@ -361,6 +361,36 @@ def knn_tie_rows(dist: Tensor, kk: int, tol: float) -> Tensor:
     return (gaps <= tol).any(dim=-1)
 
 
+class CascadeTracker:
+    """Tie-aware comparison of two runs of the encoder (this is how "bit-exact except on
+    documented distance ties" is checked end to end).
+
+    The graph of block l is built from the features of block l-1, so one legitimately flipped
+    near-tie neighbour changes everything downstream of it *for that segment*.  Walking the blocks
+    in order, a segment stays ``alive`` while every neighbour list so far is identical; at the
+    first block where a segment differs, all differing rows must be documented ties (adjacent
+    reference distances within ``tol`` among the k*d+1 smallest), after which the segment is
+    marked diverged and excluded from later checks.  ``bad`` counts off-tie mismatches."""
+
+    def __init__(self, n_segments: int):
+        self.alive = torch.ones(n_segments, dtype=torch.bool)
+        self.bad = 0
+        self.tie_flips = 0
+        self.log = []
+
+    def update(self, layer: int, idx_test: Tensor, idx_ref: Tensor, dist_ref: Tensor, kk: int,
+               tol: float) -> None:
+        diff = (idx_test.long() != idx_ref.long()).any(-1)            # (B, N)
+        tie = knn_tie_rows(dist_ref, kk, tol)
+        off = diff & ~tie & self.alive[:, None]
+        self.bad += int(off.sum())
+        flipped = (diff & self.alive[:, None]).any(-1)
+        self.tie_flips += int((diff & tie & self.alive[:, None]).sum())
+        if flipped.any():
+            self.log.append((layer, [int(i) for i in torch.nonzero(flipped).flatten()], int(off.sum())))
+        self.alive &= ~flipped
+
+
 def clip_grad_norm_(grads: List[Tensor], max_norm: float) -> Tensor:
     """torch.nn.utils.clip_grad_norm_ semantics used at train.py:73 (L2, eps 1e-6)."""
     total = torch.sqrt(sum((g.detach().double() ** 2).sum() for g in grads)).float()
