@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- GraphEncoder fingerprint-generation throughput (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One "step" = one pass of the hot path (GraphEncoder forward, eval, random-init size-'t'
+architecture, k=3) over a synthetic batch of 4096 spectral-peak graphs per GPU.  Weak scaling:
+every rank owns its own contiguous range of 4096 segments (no data-path collective; segments are
+independent in eval mode).  Prints ONE JSON line (rank 0).
+
+  value     segments/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       the same metric through the public module call with HOST buffers: pinned-host input ->
+            H2D copy -> forward -> D2H of the (B, 1024) embeddings, all inside the timed region
+  roofline  the dominant kernel of the step (by device time, measured live with CUDA events)
+  stage_rooflines  kNN and gather+max-relative aggregate achieved HBM GB/s (the second half of
+            BASELINE.json's metric)
+  cpu_baseline  the oracle port of the reference's PyTorch CPU path timed on this box's host cores
+            (rank 0, N=1 only) on a bounded sample
+
+--impl reference times that CPU path alone (the reference is pure Python/PyTorch and cannot travel
+to the GPU box; the oracle port restates it op for op, see oracle/grafp_oracle.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(n_mels=64, n_frames=128, patch_bins=4, patch_frames=8, n_filters=8, tau=0.05,
+           d=128, h=1024, u=32, dim=2048, arch="grafp", bsz_train=256)
+K_NEIGHBOURS = 3
+STAGES = [(256, 64, 2), (128, 128, 2), (64, 256, 6), (32, 512, 2)]   # (N, C, blocks) of size 't'
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4)
+                          if r[4 + i].lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic bytes / flops
+# ------------------------------------------------------------------------------------------
+def aggregate_bytes(B, N, C, k):
+    return B * (2 * N * C * 4 + 4 * N * k)
+
+
+def knn_bytes(B, N, C, k):
+    return B * (N * C * 4 + 4 * N * k)
+
+
+def encoder_flops_per_segment():
+    f = 2 * 256 * 8 * 64
+    for N, C, nb in STAGES:
+        f += nb * (24 * N * C * C + 2 * N * N * C)
+    f += 2 * (128 * 192 * 128 + 64 * 384 * 256 + 32 * 768 * 512)
+    f += 2 * 512 * 1024
+    return f
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's PyTorch path)
+# ------------------------------------------------------------------------------------------
+def cpu_forward_rate(batch: int, budget_s: float, warmup: int = 2, steps: int = None):
+    from oracle import grafp_oracle as O
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synth_state(synth.encoder_state_spec("t", 8, 1024, 256), 1234)
+    x = synth.synth_uniform((batch, 8, 256), 0)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.encoder_forward(sd, x, k=K_NEIGHBOURS)
+        times = []
+        t_end = time.perf_counter() + budget_s
+        while (steps is None and time.perf_counter() < t_end and len(times) < 200) or \
+                (steps is not None and len(times) < steps):
+            t0 = time.perf_counter()
+            O.encoder_forward(sd, x, k=K_NEIGHBOURS)
+            times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 32
+    times, threads = cpu_forward_rate(batch, 0.0, warmup=max(1, args.warmup), steps=max(1, args.steps))
+    total = sum(times)
+    value = batch * len(times) / total
+    sample = "%d steps x %d segments, oracle port of encoder/graph_encoder.py on host cores" % (len(times), batch)
+    line = {
+        "impl": "reference", "metric": "GraphEncoder forward segments/s", "value": value,
+        "unit": "segments/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GraphEncoder forward (size t, k=3, eval), CPU sample of %d segments/step "
+                               "of the 4096-segment fingerprint-generation batch" % batch,
+                   "segments_per_step": batch},
+        "cpu_baseline": {"value": value, "unit": "segments/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Per-C-ABI-call CUDA-event timing on the launching stream (one instrumented step)."""
+
+    def __init__(self):
+        self.records = []
+
+    def __call__(self, name, fn, args):
+        if not name.endswith(("_fwd", "_bwd", "_nodes", "_nchw", "_mean", "_rows", "_select", "_tf32")):
+            return fn(*args)
+        info = name
+        if name == "grafp_gemm_fwd":
+            a = args[0]._obj
+            info = "gemm m=%d k=%d+%d n=%d g=%d%s" % (a.m, a.k1, a.k2, a.n, a.groups, " tap3" if a.tap3_nodes else "")
+            self.last_gemm = (a.m, a.k1 + a.k2, a.n * a.groups, a.groups)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        extra = None
+        if name == "grafp_gemm_fwd":
+            m, k, n, g = self.last_gemm
+            extra = 2.0 * m * k * n / g
+        elif name in ("grafp_knn_fwd", "grafp_mr_aggregate_fwd"):
+            extra = tuple(int(v) if isinstance(v, int) else v for v in args[1:5])
+        self.records.append((info, name, s, e, extra))
+        return rc
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for info, name, s, e, extra in self.records:
+            d = out.setdefault(info, {"name": name, "ms": 0.0, "calls": 0, "flops": 0.0, "shapes": []})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            if isinstance(extra, float):
+                d["flops"] += extra
+            elif extra is not None:
+                d["shapes"].append(extra)
+        return out
+
+
+def run_native(args):
+    import torch.distributed as dist
+    from neuralsampleid_b200 import _lib, ops
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    from neuralsampleid_b200.parallel import shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.engine:
+        ops.set_engine(args.engine)
+
+    B = args.batch
+    lo, hi = shard_range(B * world, rank, world)
+    torch.manual_seed(0)                      # random-init weights of the grafp.yaml architecture
+    enc = GraphEncoder(cfg=CFG, in_channels=CFG["n_filters"], k=K_NEIGHBOURS)
+    with torch.no_grad():                     # non-trivial BN statistics so the folded epilogues do real work
+        for m in enc.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.3, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.6, 1.2)
+                m.bias.uniform_(-0.2, 0.2)
+    enc = enc.to(dev).eval()
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = torch.rand((hi - lo, 8, 256), generator=g).pin_memory()
+    out_host = torch.empty((hi - lo, 1024), dtype=torch.float32).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            enc(x_dev)
+        # ---- device-resident timing ----
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        l0 = _lib.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(args.steps):
+            enc(x_dev)
+        ev[1].record()
+        barrier()
+        launches = _lib.launch_count() - l0
+        ms_total = max_over_ranks(ev[0].elapsed_time(ev[1]))
+        # ---- end-to-end timing: pinned host -> device -> forward -> pinned host ----
+        for _ in range(2):
+            out_host.copy_(enc(x_host.to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        e2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        t0 = time.perf_counter()
+        e2[0].record()
+        for _ in range(args.steps):
+            xd = x_host.to(dev, non_blocking=True)
+            out_host.copy_(enc(xd), non_blocking=True)
+        e2[1].record()
+        barrier()
+        wall_e2e = time.perf_counter() - t0
+        ms_e2e = max_over_ranks(max(e2[0].elapsed_time(e2[1]), 1e3 * wall_e2e))
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- one instrumented step: per-kernel device times ----
+        timer = KernelTimer()
+        _lib.set_profiler(timer)
+        enc(x_dev)
+        _lib.set_profiler(None)
+        per_kernel = timer.summary()
+
+    seg_per_step = B * world
+    value = seg_per_step * args.steps / (ms_total * 1e-3)
+    e2e_value = seg_per_step * args.steps / (ms_e2e * 1e-3)
+    pk = peaks()
+
+    # dominant kernel class (by C-ABI entry point) and its roofline
+    by_entry = {}
+    for info, d in per_kernel.items():
+        e = by_entry.setdefault(d["name"], {"ms": 0.0, "flops": 0.0, "calls": 0})
+        e["ms"] += d["ms"]; e["flops"] += d["flops"]; e["calls"] += d["calls"]
+    step_ms_instr = sum(e["ms"] for e in by_entry.values())
+    dominant = max(by_entry, key=lambda n: by_entry[n]["ms"])
+    top_gemm = max((d for d in per_kernel.values() if d["name"] == "grafp_gemm_fwd"), key=lambda d: d["ms"])
+    top_gemm_name = [k for k, d in per_kernel.items() if d is top_gemm][0]
+    agg = by_entry.get("grafp_mr_aggregate_fwd", {"ms": 0.0})
+    knn = by_entry.get("grafp_knn_fwd", {"ms": 0.0})
+    Bl = hi - lo
+    agg_b = sum(nb * aggregate_bytes(Bl, N, C, K_NEIGHBOURS) for N, C, nb in STAGES)
+    knn_b = sum(nb * knn_bytes(Bl, N, C, K_NEIGHBOURS) for N, C, nb in STAGES)
+    stage_rooflines = {
+        "aggregate": {"bound": "hbm", "achieved": agg_b / (agg["ms"] * 1e-3) / 1e9 if agg["ms"] else None,
+                      "peak": pk["hbm_gbs"], "unit": "GB/s", "ms_per_step": agg["ms"],
+                      "algorithmic_bytes_per_step": agg_b},
+        "knn": {"bound": "hbm", "achieved": knn_b / (knn["ms"] * 1e-3) / 1e9 if knn["ms"] else None,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "ms_per_step": knn["ms"],
+                "algorithmic_bytes_per_step": knn_b},
+    }
+    for v in stage_rooflines.values():
+        v["frac"] = v["achieved"] / v["peak"] if v["achieved"] else None
+    if dominant == "grafp_gemm_fwd":
+        g_all = by_entry["grafp_gemm_fwd"]
+        achieved = g_all["flops"] / (g_all["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": "gemm_tc_kernel / gemm_simt_kernel (all 1x1-conv GEMMs of the step)",
+                    "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                    "peak_source": pk["source"] + " dense bf16 (cuBLAS, sustained)",
+                    "note": "fp32-parity engine = 3 kind::tf32 MMAs per k-step; tf32 runs at half the bf16 "
+                            "rate, so this engine's ceiling is peak/6; achieved counts useful 2*M*N*K flops",
+                    "share_of_step": g_all["ms"] / step_ms_instr,
+                    "top_gemm": {"shape": top_gemm_name, "ms": top_gemm["ms"],
+                                 "tflops": top_gemm["flops"] / (top_gemm["ms"] * 1e-3) / 1e12}}
+    else:
+        key = "aggregate" if dominant == "grafp_mr_aggregate_fwd" else "knn"
+        r = stage_rooflines[key]
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": r["achieved"], "peak": r["peak"],
+                    "unit": "GB/s", "frac": r["frac"], "traffic": None,
+                    "peak_source": pk["source"], "share_of_step": by_entry[dominant]["ms"] / step_ms_instr}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        times, threads = cpu_forward_rate(32, args.cpu_budget)
+        best = min(times)
+        cpu = {"value": 32 / best, "unit": "segments/s", "cores": threads, "kind": "port",
+               "sample": "B=32 segments (BASELINE configs[0]), best of %d runs in %.0f s, oracle port of the "
+                         "reference's PyTorch CPU path" % (len(times), args.cpu_budget),
+               "mean_value": 32 * len(times) / sum(times)}
+
+    line = {
+        "metric": "GraphEncoder forward segments/s", "value": value, "unit": "segments/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GraphEncoder forward fingerprint generation (generate.py path), size t, k=3, "
+                               "eval, %d segments per GPU (BASELINE configs[1])" % B,
+                   "segments_per_gpu": B, "global_segments": seg_per_step, "engine": args.engine or "auto",
+                   "l2": "inputs resident; each layer's activations (268 MB) exceed the 126 MB L2, so every "
+                         "step streams from HBM"},
+        "e2e": {"value": e2e_value, "unit": "segments/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(x_host.numel() * 4 * world),
+                "d2h_bytes_per_step": int(out_host.numel() * 4 * world)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "stage_rooflines": stage_rooflines,
+        "kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])},
+        "encoder_tflops": encoder_flops_per_segment() * value / 1e12,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="segments per GPU")
+    ap.add_argument("--engine", default=None, choices=[None, "auto", "simt", "3xtf32", "tf32"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the native arm has no CPU fallback; use --impl reference)")
+    run_native(args)
+
+
+if __name__ == "__main__":
+    main()

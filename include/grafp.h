@@ -38,7 +38,7 @@ enum { GRAFP_ACT_NONE = 0, GRAFP_ACT_RELU = 1, GRAFP_ACT_LEAKY = 2, GRAFP_ACT_GE
        GRAFP_ACT_ELU = 4 };
 
 /* GEMM engines */
-enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 3xTF32 where the shape allows, else SIMT */
+enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 3xTF32 where shape + w_split allow, else SIMT */
        GRAFP_ENGINE_SIMT = 1,      /* fp32 FFMA tiles                                   */
        GRAFP_ENGINE_TC_3XTF32 = 2, /* tcgen05 kind::tf32, hi/lo split, fp32-accurate    */
        GRAFP_ENGINE_TC_TF32 = 3    /* tcgen05 kind::tf32 single pass                    */ };
@@ -100,6 +100,9 @@ typedef struct {
   const float* a1; int64_t lda1; int32_t k1;
   const float* a2; int64_t lda2; int32_t k2;
   const float* w;  int64_t ldw;            /* (groups*n, k1+k2) row-major               */
+  const float* w_split;                     /* optional (2*groups*n, k1+k2), same ldw: the
+                                               [tf32 hi ; tf32 lo] split of w made by
+                                               grafp_split_tf32 (needed by TC_3XTF32)     */
   const float* scale;                       /* (groups*n) or NULL (= 1)                   */
   const float* shift;                       /* (groups*n) or NULL (= 0)                   */
   const float* residual; int64_t ldr;       /* (M, groups*n) or NULL                      */
@@ -110,6 +113,11 @@ typedef struct {
   int32_t engine;
 } grafp_gemm_args;
 int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream);
+/* 1 if the tcgen05 engine takes this problem (k1, k2 multiples of 32, n multiple of 16, no tap3) */
+int grafp_gemm_tc_supported(const grafp_gemm_args* args);
+/* error-compensated operand split for TC_3XTF32: out[0:count] = tf32(w), out[count:2*count] =
+ * tf32(w - tf32(w)) (round-to-nearest).  Done once per weight version. */
+int grafp_split_tf32(const float* w, int64_t count, float* out_hi_lo, void* stream);
 
 /* mean over the nodes of each graph: x (B*N, C) -> out (B, C)   (graph_encoder.py:211) */
 int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream);

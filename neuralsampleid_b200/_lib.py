@@ -25,7 +25,7 @@ class GrafpError(RuntimeError):
 class GemmArgs(C.Structure):
     _fields_ = [("a1", C.c_void_p), ("lda1", C.c_int64), ("k1", C.c_int32),
                 ("a2", C.c_void_p), ("lda2", C.c_int64), ("k2", C.c_int32),
-                ("w", C.c_void_p), ("ldw", C.c_int64),
+                ("w", C.c_void_p), ("ldw", C.c_int64), ("w_split", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("y", C.c_void_p), ("ldy", C.c_int64),
@@ -44,6 +44,8 @@ SIGNATURES = {
     "grafp_mr_aggregate_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "grafp_index_select": [_P, _P, _I, _I, _I, _I, _P, _P],
     "grafp_gemm_fwd": [C.POINTER(GemmArgs), _P],
+    "grafp_gemm_tc_supported": [C.POINTER(GemmArgs)],
+    "grafp_split_tf32": [_P, _L, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
     "grafp_peak_extract_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "grafp_l2_normalize_rows": [_P, _L, _I, _F, _P, _P],
@@ -54,6 +56,28 @@ SPECIAL = {"grafp_abi_version": ([], C.c_int), "grafp_last_error": ([], C.c_char
            "grafp_launch_count": ([], C.c_int64)}
 
 _lib = None
+_cdll = None
+_profiler = None      # optional callable(name, fn, args) -> rc, installed by bench.py / tests
+
+
+def set_profiler(cb) -> None:
+    """Installs (or clears, with None) a hook that wraps every C-ABI call: cb(name, fn, args) must
+    call fn(*args) and return its result.  Used only for per-kernel timing in bench.py."""
+    global _profiler
+    _profiler = cb
+
+
+class _Proxy:
+    """Attribute access returns the ctypes function, routed through the profiler hook if set."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if _profiler is None:
+            return fn
+        return lambda *args: _profiler(name, fn, args)
 
 
 def load():
@@ -74,8 +98,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
-    _lib = lib
-    return lib
+    _lib = _Proxy(lib)
+    return _lib
 
 
 def exported_symbols():

@@ -35,3 +35,38 @@ def tap3_weight(weight: torch.Tensor) -> torch.Tensor:
     """(Cout, Cin, 3, 3) stride-2 conv on an (N, 1) image only ever sees its centre column
     (SURVEY Q8): returns (Cout, 3*Cin) with column t*Cin + ci = weight[co, ci, t, 1]."""
     return weight.detach()[:, :, :, 1].permute(0, 2, 1).reshape(weight.shape[0], -1).float().contiguous()
+
+
+class Linear:
+    """Prepared operands of one fused GEMM layer: weight (groups*n, k), optional stacked tf32
+    [hi ; lo] split for the tcgen05 3xTF32 engine, per-channel scale / shift."""
+    __slots__ = ("w", "w_split", "scale", "shift", "groups")
+
+    def __init__(self, w, scale, shift, groups=1, w_split=None):
+        self.w, self.scale, self.shift, self.groups, self.w_split = w, scale, shift, groups, w_split
+
+
+@torch.no_grad()
+def make_linear(w: torch.Tensor, scale, shift, groups: int = 1, dual: bool = False) -> Linear:
+    """Builds the device operands for ops.gemm.  ``dual``: the k axis of each group is fed from two
+    sources of k/2 columns each.  A grouped layer whose per-source k extent is not a multiple of
+    32 (the tcgen05 k-block) is densified into one block-diagonal group so it can still run on the
+    tensor cores (at most the 2C x 2C first-stage MRConv: +1% of the encoder's flops)."""
+    from . import ops
+    w = w.float().contiguous()
+    n_total, k = w.shape
+    parts = 2 if dual else 1
+    if groups > 1 and (k // parts) % 32 != 0 and ((k // parts) * groups) % 32 == 0:
+        n = n_total // groups
+        kp = k // parts
+        dense = torch.zeros((n_total, k * groups), device=w.device, dtype=torch.float32)
+        for g in range(groups):
+            for q in range(parts):
+                dense[g * n:(g + 1) * n, q * kp * groups + g * kp: q * kp * groups + (g + 1) * kp] = \
+                    w[g * n:(g + 1) * n, q * kp:(q + 1) * kp]
+        w, groups = dense, 1
+        n_total, k = w.shape
+    lin = Linear(w, scale, shift, groups)
+    if w.is_cuda and (k // parts) % 32 == 0 and (n_total // groups) % 16 == 0:
+        lin.w_split = ops.split_tf32(w)
+    return lin

@@ -32,13 +32,20 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
     case GRAFP_ENGINE_SIMT:
       return gemm_simt_launch(a, st);
     case GRAFP_ENGINE_TC_3XTF32:
+      GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
+      GRAFP_REQUIRE(a.w_split, "gemm: TC_3XTF32 needs w_split (grafp_split_tf32)");
+      return gemm_tc_launch(a, 3, st);
     case GRAFP_ENGINE_TC_TF32:
       GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
-      return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_3XTF32 ? 3 : 1, st);
+      return gemm_tc_launch(a, 1, st);
     case GRAFP_ENGINE_AUTO:
-      if (gemm_tc_supported(a)) return gemm_tc_launch(a, 3, st);
+      if (a.w_split && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, st);
       return gemm_simt_launch(a, st);
     default:
       return fail("gemm: unknown engine %d", a.engine);
   }
+}
+
+extern "C" int grafp_gemm_tc_supported(const grafp_gemm_args* args) {
+  return args ? gemm_tc_supported(*args) : 0;
 }

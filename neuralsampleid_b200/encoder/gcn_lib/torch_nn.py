@@ -8,7 +8,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ..._prep import fold_conv_bn, sig
+from ..._prep import fold_conv_bn, make_linear, sig
 
 _SUPPORTED_ACTS = ("relu", "leakyrelu", "gelu")
 
@@ -84,7 +84,7 @@ class BasicConv(nn.Sequential):
 
     # -- node-major implementation ------------------------------------------------------
     def layer_params(self, i: int, interleaved_sources: bool):
-        """Folded (W, scale, shift, act, slope) of layer i (eval mode).  With
+        """Prepared (Linear, act, slope) of layer i (eval mode).  With
         ``interleaved_sources`` the columns of each group are regrouped [even | odd] so the layer
         reads two separate node matrices instead of the reference's channel-interleaved cat."""
         e = self._plan[i]
@@ -92,15 +92,15 @@ class BasicConv(nn.Sequential):
         bn = self[e["bn"]] if e["bn"] is not None else None
         key = (i, interleaved_sources) + sig(conv.weight, conv.bias) + \
             (sig(bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else ())
-        hit = self._cache.get(i)
+        hit = self._cache.get((i, interleaved_sources))
         if hit is None or hit[0] != key:
             w, scale, shift = fold_conv_bn(conv.weight, conv.bias, bn)
             if interleaved_sources:
                 w = torch.cat([w[:, 0::2], w[:, 1::2]], dim=1).contiguous()
-            hit = (key, (w, scale, shift))
-            self._cache[i] = hit
+            hit = (key, make_linear(w, scale, shift, self.GROUPS, dual=interleaved_sources))
+            self._cache[(i, interleaved_sources)] = hit
         act = self[e["act"]] if e["act"] is not None else None
-        return hit[1] + ((act.name, act.neg_slope) if act is not None else (None, 0.0))
+        return (hit[1],) + ((act.name, act.neg_slope) if act is not None else (None, 0.0))
 
     def forward_nodes(self, x: torch.Tensor, x2: torch.Tensor = None) -> torch.Tensor:
         """x: (M, C) node-major.  If ``x2`` is given, the first layer consumes the virtual
@@ -109,8 +109,8 @@ class BasicConv(nn.Sequential):
             raise RuntimeError("BasicConv.forward_nodes is the eval path; training goes through "
                                "neuralsampleid_b200.autograd")
         for i in range(len(self._plan)):
-            w, scale, shift, act, slope = self.layer_params(i, interleaved_sources=(i == 0 and x2 is not None))
-            x = ops.gemm(x, w, scale, shift, act, slope, a2=x2 if i == 0 else None, groups=self.GROUPS)
+            lin, act, slope = self.layer_params(i, interleaved_sources=(i == 0 and x2 is not None))
+            x = ops.linear(x, lin, act, slope, a2=x2 if i == 0 else None)
         return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ... import ops
-from ..._prep import fold_conv_bn, sig
+from ..._prep import fold_conv_bn, make_linear, sig
 from .pos_embed import get_2d_relative_pos_embed
 from .torch_edge import DenseDilatedKnnGraph
 from .torch_nn import BasicConv
@@ -110,7 +110,7 @@ class Grapher(nn.Module):
         key = sig(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
         hit = self._cache.get(name)
         if hit is None or hit[0] != key:
-            hit = (key, fold_conv_bn(conv.weight, conv.bias, bn))
+            hit = (key, make_linear(*fold_conv_bn(conv.weight, conv.bias, bn)))
             self._cache[name] = hit
         return hit[1]
 
@@ -119,16 +119,14 @@ class Grapher(nn.Module):
         if self.training:
             raise RuntimeError("Grapher.forward_nodes is the eval path; training goes through "
                                "neuralsampleid_b200.autograd")
-        w1, s1, t1 = self._folded("fc1")
-        y = ops.gemm(x, w1, s1, t1)
+        y = ops.linear(x, self._folded("fc1"))
         if taps is not None:
             taps["fc1"] = y
             if nn_idx is None:
                 nn_idx = self.graph_conv.dilated_knn_graph.knn_nodes(y, B, N)
             taps["idx"] = nn_idx
         g = self.graph_conv.forward_nodes(y, B, N, nn_idx)
-        w2, s2, t2 = self._folded("fc2")
-        return ops.gemm(g, w2, s2, t2, residual=x)
+        return ops.linear(g, self._folded("fc2"), residual=x)
 
     def forward(self, x):
         B, C, N = x.shape[:3]

@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .._prep import fold_conv_bn, sig, tap3_weight
+from .._prep import fold_conv_bn, make_linear, sig, tap3_weight
 from .gcn_lib.torch_nn import act_layer
 from .gcn_lib.torch_vertex import Grapher
 
@@ -54,9 +54,9 @@ class Downsample(_Cached):
 
         def make():
             _, s, t = fold_conv_bn(conv.weight[:, :, :1, 1], conv.bias, bn)
-            return tap3_weight(conv.weight), s, t
-        w, s, t = self._memo("conv", (conv.weight, conv.bias) + _bn_tensors(bn), make)
-        return ops.gemm(x, w, s, t, tap3_nodes=N // 2)
+            return make_linear(tap3_weight(conv.weight), s, t)
+        lin = self._memo("conv", (conv.weight, conv.bias) + _bn_tensors(bn), make)
+        return ops.linear(x, lin, tap3_nodes=N // 2)
 
     def forward(self, x):
         B, C, N, W = x.shape
@@ -85,16 +85,14 @@ class FFN(_Cached):
     def _folded(self, name):
         conv, bn = getattr(self, name)[0], getattr(self, name)[1]
         return self._memo(name, (conv.weight, conv.bias) + _bn_tensors(bn),
-                          lambda: fold_conv_bn(conv.weight, conv.bias, bn))
+                          lambda: make_linear(*fold_conv_bn(conv.weight, conv.bias, bn)))
 
     def forward_nodes(self, x: torch.Tensor) -> torch.Tensor:
         if self.training:
             raise RuntimeError("FFN.forward_nodes is the eval path; training goes through "
                                "neuralsampleid_b200.autograd")
-        w1, s1, t1 = self._folded("fc1")
-        w2, s2, t2 = self._folded("fc2")
-        h = ops.gemm(x, w1, s1, t1, self.act.name, self.act.neg_slope)
-        return ops.gemm(h, w2, s2, t2, residual=x)
+        h = ops.linear(x, self._folded("fc1"), self.act.name, self.act.neg_slope)
+        return ops.linear(h, self._folded("fc2"), residual=x)
 
     def forward(self, x):
         B, C, N = x.shape[:3]
@@ -143,14 +141,15 @@ class GraphEncoder(_Cached):
     # ------------------------------------------------------------------------------------
     def _stem_nodes(self, x_nodes):
         conv, bn = self.stem[0], self.stem[1]
-        w, s, t = self._memo("stem", (conv.weight,) + _bn_tensors(bn),
-                             lambda: fold_conv_bn(conv.weight, None, bn))
-        return ops.gemm(x_nodes, w, s, t, "leakyrelu", self.stem[2].negative_slope)
+        lin = self._memo("stem", (conv.weight,) + _bn_tensors(bn),
+                         lambda: make_linear(*fold_conv_bn(conv.weight, None, bn)))
+        return ops.linear(x_nodes, lin, "leakyrelu", self.stem[2].negative_slope)
 
     def _proj(self, mean):
-        w, _, b = self._memo("proj", (self.proj.weight, self.proj.bias),
-                             lambda: fold_conv_bn(self.proj.weight, self.proj.bias, None))
-        return ops.gemm(mean, w, None, b)
+        def make():
+            w, _, b = fold_conv_bn(self.proj.weight, self.proj.bias, None)
+            return make_linear(w, None, b)
+        return ops.linear(mean, self._memo("proj", (self.proj.weight, self.proj.bias), make))
 
     def forward(self, x, return_pre_proj=False, forced_idx=None, taps=None):
         """x: (B, in_channels, N) -> (B, emb_dims).

@@ -124,11 +124,27 @@ def index_select(x: torch.Tensor, idx: torch.Tensor, B: int, N: int) -> torch.Te
     return out
 
 
+def split_tf32(w: torch.Tensor) -> torch.Tensor:
+    """(n, k) fp32 -> (2n, k) stacked [tf32(w) ; tf32(w - tf32(w))] for the 3xTF32 engine."""
+    w = _chk(w, name="w")
+    out = torch.empty((2 * w.shape[0], w.shape[1]), device=w.device, dtype=torch.float32)
+    with torch.cuda.device(w.device):
+        check(_lib.load().grafp_split_tf32(_ptr(w), w.numel(), _ptr(out), _stream(w)), "split_tf32")
+    return out
+
+
+def linear(a1: torch.Tensor, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
+           tap3_nodes: int = 0, engine: Optional[int] = None) -> torch.Tensor:
+    """ops.gemm over a prepared ``_prep.Linear``."""
+    return gemm(a1, lin.w, lin.scale, lin.shift, act, act_param, residual, a2, lin.groups, tap3_nodes,
+                engine, None, lin.w_split)
+
+
 def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
          shift: Optional[torch.Tensor] = None, act=None, act_param: float = 0.0,
          residual: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          groups: int = 1, tap3_nodes: int = 0, engine: Optional[int] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, w_split: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = act(scale * [a1 | a2] @ w.T + shift) + residual  (per-group, see include/grafp.h).
 
     a1: (M, groups*k1) (or the (2M', Cin) node matrix in tap3 mode), a2: (M, groups*k2) or None,
@@ -157,6 +173,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     args.a2, args.lda2, args.k2 = (a2.data_ptr() if a2 is not None else None), \
         (a2.stride(0) if a2 is not None else 0), k2
     args.w, args.ldw = w.data_ptr(), w.stride(0)
+    args.w_split = w_split.data_ptr() if w_split is not None else None
     args.scale = scale.data_ptr() if scale is not None else None
     args.shift = shift.data_ptr() if shift is not None else None
     if residual is not None:

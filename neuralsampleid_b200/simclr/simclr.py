@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .._prep import sig
+from .._prep import make_linear, sig
 from ..encoder.graph_encoder import GraphEncoder
 from ..peak_extractor import GPUPeakExtractorv2
 
@@ -29,15 +29,14 @@ class SimCLR(nn.Module):
         key = sig(l1.weight, l1.bias, l2.weight, l2.bias)
         hit = self._cache.get("p")
         if hit is None or hit[0] != key:
-            hit = (key, (l1.weight.detach().float().contiguous(), l1.bias.detach().float().contiguous(),
-                         l2.weight.detach().float().contiguous(), l2.bias.detach().float().contiguous()))
+            hit = (key, (make_linear(l1.weight.detach(), None, l1.bias.detach().float().contiguous()),
+                         make_linear(l2.weight.detach(), None, l2.bias.detach().float().contiguous())))
             self._cache["p"] = hit
         return hit[1]
 
     def _project(self, h: torch.Tensor) -> torch.Tensor:
-        w1, b1, w2, b2 = self._proj_weights()
-        z = ops.gemm(h, w1, None, b1, "elu")
-        z = ops.gemm(z, w2, None, b2)
+        l1, l2 = self._proj_weights()
+        z = ops.linear(ops.linear(h, l1, "elu"), l2)
         return ops.l2_normalize_rows(z, 1e-10)
 
     def _one_view(self, x):

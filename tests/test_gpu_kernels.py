@@ -1,0 +1,351 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle / a plain fp32 torch
+restatement on the same seeded inputs.  Bit-exact for index work and the max-relative aggregate;
+stated fp32 tolerances for the floating-point kernels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grafp_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _ops():
+    from neuralsampleid_b200 import ops
+    return ops
+
+
+def _nodes(x_bcn1: torch.Tensor) -> torch.Tensor:
+    """(B, C, N, 1) -> node-major (B*N, C) on the CPU (test-side layout helper)."""
+    B, C, N = x_bcn1.shape[:3]
+    return x_bcn1.reshape(B, C, N).transpose(1, 2).reshape(B * N, C).contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,N", [(3, 8, 256), (2, 64, 96), (1, 5, 33)])
+def test_layout_roundtrip(B, C, N):
+    ops = _ops()
+    x = synth.synth_normal((B, C, N), 3)
+    nodes = ops.nchw_to_nodes(x.to(DEV))
+    assert torch.equal(nodes.cpu(), x.transpose(1, 2).reshape(B * N, C))
+    assert torch.equal(ops.nodes_to_nchw(nodes, B, N).cpu(), x)
+
+
+# ------------------------------------------------------------------------------------------
+# kNN
+# ------------------------------------------------------------------------------------------
+def _knn_check(x, k, d, tol=4e-6, normalize=True):
+    """x: (B, C, N, 1) cpu.  Compares the kernel's ordered neighbour lists with the oracle's,
+    except on rows the oracle's own distances mark as ties at `tol`."""
+    ops = _ops()
+    B, C, N = x.shape[:3]
+    if normalize:
+        edge, dist = O.dilated_knn_graph(x, k, d)
+        ref = edge[0]
+    else:
+        nn_idx, dist = O.dense_knn(x, k * d)
+        ref = nn_idx[:, :, ::d]
+    got, gd = ops.knn(_nodes(x).to(DEV), B, N, k, d, normalize=normalize, return_dist=True)
+    got = got.cpu().long()
+    assert got.shape == ref.shape
+    assert int(got.min()) >= 0 and int(got.max()) < N
+    tie = O.knn_tie_rows(dist, k * d, tol)
+    diff = (got != ref).any(-1)
+    assert not (diff & ~tie).any(), "%d off-tie rows differ" % int((diff & ~tie).sum())
+    # distances of the selected ranks agree with the reference matrix to fp32 round-off
+    want = torch.gather(dist, 2, ref)
+    ok = ~diff
+    assert torch.allclose(gd.cpu()[ok], want[ok], rtol=0, atol=4e-6)
+    return float(diff.float().mean()), float(tie.float().mean())
+
+
+@pytest.mark.parametrize("B,C,N,k,d", [
+    (4, 64, 256, 3, 1), (4, 128, 128, 3, 1), (4, 256, 64, 3, 1), (4, 512, 32, 3, 1),   # size-'t' stages
+    (4, 64, 256, 5, 1), (2, 64, 256, 9, 2), (2, 64, 96, 4, 3),                           # train k, dilation
+    (2, 64, 512, 16, 2), (1, 64, 1024, 32, 2), (1, 64, 2048, 9, 3), (1, 64, 2048, 32, 2),  # stress sweep corners
+    (3, 32, 40, 4, 1), (2, 8, 16, 16, 1), (1, 64, 200, 9, 2),                            # ragged sizes, k*d == N
+])
+def test_knn_matches_oracle(B, C, N, k, d):
+    x = synth.synth_normal((B, C, N, 1), 100 + N + k)
+    _knn_check(x, k, d)
+
+
+def test_knn_post_relu_features_and_duplicates():
+    # post-ReLU style features with exact duplicates and all-zero nodes: the reference has exact
+    # ties here; every differing row must be a documented tie and indices must stay valid
+    x = torch.relu(synth.synth_normal((2, 64, 128, 1), 7))
+    x[:, :, 5] = x[:, :, 9]
+    x[:, :, 17] = 0.0
+    x[:, :, 18] = 0.0
+    _knn_check(x, 5, 1)
+
+
+def test_knn_unnormalised_entry_point():
+    x = torch.nn.functional.normalize(synth.synth_normal((2, 32, 64, 1), 8), dim=1)
+    _knn_check(x, 6, 1, normalize=False)
+
+
+def test_knn_golden_dygraph_inputs(golden_dir):
+    for fname, k, d in (("dygraph_k9_d2.npz", 9, 2), ("dygraph_k4_d3_n96.npz", 4, 3)):
+        g = np.load(os.path.join(golden_dir, fname))
+        x = torch.from_numpy(g["x"])
+        ops = _ops()
+        B, C, N = x.shape[:3]
+        got = ops.knn(_nodes(x).to(DEV), B, N, k, d).cpu().long()
+        _, dist = O.dilated_knn_graph(x, k, d)
+        tie = O.knn_tie_rows(dist, k * d, 4e-6)
+        diff = (got != torch.from_numpy(g["idx"].astype(np.int64))).any(-1)
+        assert not (diff & ~tie).any()
+
+
+def test_knn_rejects_bad_arguments():
+    ops = _ops()
+    from neuralsampleid_b200._lib import GrafpError
+    x = torch.zeros((2 * 16, 8), device=DEV)
+    with pytest.raises(GrafpError):
+        ops.knn(x, 2, 16, 9, 2)            # k*d > N
+    with pytest.raises(GrafpError):
+        ops.knn(torch.zeros((16, 6), device=DEV), 1, 16, 3, 1)   # C % 4
+    assert ops.knn(torch.zeros((0, 8), device=DEV), 0, 16, 3, 1).shape == (0, 16, 3)   # empty batch
+
+
+# ------------------------------------------------------------------------------------------
+# gather + max-relative (bit-exact)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,N,k", [(5, 64, 256, 3), (300, 64, 256, 3), (4, 128, 128, 5), (3, 256, 64, 9),
+                                     (2, 512, 32, 3), (2, 64, 2048, 16), (3, 32, 40, 4), (1, 8, 16, 16)])
+def test_mr_aggregate_bit_exact(B, C, N, k):
+    ops = _ops()
+    x = synth.synth_normal((B, C, N, 1), 11 + B)
+    rng = np.random.Generator(np.random.PCG64(5))
+    idx = torch.from_numpy(rng.integers(0, N, size=(B, N, k), dtype=np.int64))
+    idx[:, :, 0] = torch.arange(N)                      # self at rank 0, as the kNN produces
+    center = torch.arange(N).view(1, N, 1).expand(B, N, k)
+    want = O.max_relative(x, torch.stack((idx, center)))           # (B, C, N, 1)
+    m, arg = ops.mr_aggregate(_nodes(x).to(DEV), idx.int().to(DEV), B, N, want_arg=True)
+    assert torch.equal(m.cpu(), _nodes(want))
+    # arg-max ranks reproduce m exactly
+    xn = _nodes(x).view(B, N, C)
+    a = arg.cpu().view(B, N, C).long()
+    assert int(a.max()) < k
+    nb = torch.gather(idx.unsqueeze(-1).expand(B, N, k, C), 2, a.unsqueeze(2)).squeeze(2)   # (B,N,C)
+    vals = xn[torch.arange(B).view(B, 1, 1), nb, torch.arange(C).view(1, 1, C)] - xn
+    assert torch.equal(vals.reshape(B * N, C), m.cpu())
+
+
+def test_index_select_matches_oracle():
+    ops = _ops()
+    x = synth.synth_normal((3, 16, 40, 1), 12)
+    rng = np.random.Generator(np.random.PCG64(6))
+    idx = torch.from_numpy(rng.integers(0, 40, size=(3, 40, 5), dtype=np.int64))
+    got = ops.index_select(_nodes(x).to(DEV), idx.int().to(DEV), 3, 40)
+    assert torch.equal(got.cpu(), O.gather_nodes(x, idx))
+
+
+def test_mr_aggregate_bwd_matches_autograd():
+    ops = _ops()
+    B, C, N, k = 3, 32, 48, 4
+    x = synth.synth_normal((B, C, N, 1), 13).requires_grad_(True)
+    rng = np.random.Generator(np.random.PCG64(7))
+    idx = torch.from_numpy(rng.integers(0, N, size=(B, N, k), dtype=np.int64))
+    center = torch.arange(N).view(1, N, 1).expand(B, N, k)
+    m = O.max_relative(x, torch.stack((idx, center)))
+    gm = synth.synth_normal(tuple(m.shape), 14)
+    m.backward(gm)
+    xm, arg = ops.mr_aggregate(_nodes(x.detach()).to(DEV), idx.int().to(DEV), B, N, want_arg=True)
+    dx = torch.zeros((B * N, C), device=DEV)
+    ops.mr_aggregate_bwd(_nodes(gm).to(DEV), idx.int().to(DEV), arg, B, N, dx)
+    assert torch.allclose(dx.cpu(), _nodes(x.grad), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM family (every engine) against fp64-accumulated torch
+# ------------------------------------------------------------------------------------------
+def _gemm_ref(a1, w, scale, shift, act, slope, residual, a2, groups, tap3_nodes):
+    a1, w = a1.double(), w.double()
+    if tap3_nodes:
+        cin = a1.shape[1]
+        xb = a1.view(-1, 2 * tap3_nodes, cin)
+        pad = torch.cat([torch.zeros_like(xb[:, :1]), xb], dim=1)            # node -1 = 0
+        A = torch.cat([pad[:, 0:-1:2], pad[:, 1::2], pad[:, 2::2]], dim=2).reshape(-1, 3 * cin)
+        y = A @ w.T
+    else:
+        n = w.shape[0] // groups
+        outs = []
+        for g in range(groups):
+            k1 = a1.shape[1] // groups
+            A = a1[:, g * k1:(g + 1) * k1]
+            if a2 is not None:
+                k2 = a2.shape[1] // groups
+                A = torch.cat([A, a2.double()[:, g * k2:(g + 1) * k2]], dim=1)
+            outs.append(A @ w[g * n:(g + 1) * n].T)
+        y = torch.cat(outs, dim=1)
+    if scale is not None:
+        y = y * scale.double()
+    if shift is not None:
+        y = y + shift.double()
+    if act == "relu":
+        y = torch.relu(y)
+    elif act == "leakyrelu":
+        y = torch.nn.functional.leaky_relu(y, slope)
+    elif act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif act == "elu":
+        y = torch.nn.functional.elu(y)
+    if residual is not None:
+        y = y + residual.double()
+    return y
+
+
+GEMM_CASES = [
+    # M, k1, k2, n, groups, act, residual, tap3
+    (1000, 8, 0, 64, 1, "leakyrelu", False, 0),        # stem
+    (777, 64, 0, 64, 1, None, False, 0),               # Grapher.fc1
+    (1024, 16, 16, 32, 4, "relu", False, 0),           # MRConv stage 1 (grouped, dual source)
+    (512, 32, 32, 64, 4, "relu", False, 0),            # MRConv stage 2
+    (300, 128, 0, 64, 1, None, True, 0),               # Grapher.fc2 + residual
+    (640, 64, 0, 256, 1, "relu", False, 0),            # FFN.fc1
+    (640, 256, 0, 64, 1, None, True, 0),               # FFN.fc2 + shortcut
+    (256, 512, 0, 2048, 1, "gelu", False, 0),          # stage-4 FFN.fc1
+    (130, 2048, 0, 512, 1, None, True, 0),             # stage-4 FFN.fc2, ragged M
+    (3 * 64, 3 * 64, 0, 128, 1, None, False, 64),      # Downsample 64 -> 128, 128 -> 64 nodes
+    (5 * 16, 3 * 256, 0, 512, 1, None, False, 16),     # Downsample 256 -> 512
+    (33, 512, 0, 1024, 1, None, False, 0),             # proj
+    (33, 1024, 0, 4096, 1, "elu", False, 0),           # projector.0
+    (33, 4096, 0, 128, 1, None, False, 0),             # projector.2
+    (50, 12, 0, 20, 1, "relu", True, 0),               # odd small shape (SIMT only)
+]
+
+
+@pytest.mark.parametrize("engine", ["simt", "3xtf32", "tf32", "auto"])
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: "m%d_k%d+%d_n%d_g%d_%s%s%s" % (
+    c[0], c[1], c[2], c[3], c[4], c[5], "_res" if c[6] else "", "_tap3" if c[7] else ""))
+def test_gemm_engines(case, engine):
+    ops = _ops()
+    from neuralsampleid_b200 import _lib, _prep
+    M, k1, k2, n, groups, act, use_res, tap3 = case
+    if tap3:
+        cin = k1 // 3
+        a1 = synth.synth_normal((2 * M, cin), 20)
+    else:
+        a1 = synth.synth_normal((M, groups * k1), 20)
+    a2 = synth.synth_normal((M, groups * k2), 21) if k2 else None
+    w = synth.synth_normal((groups * n, k1 + k2), 22) / float(np.sqrt(k1 + k2))
+    scale = synth.synth_uniform((groups * n,), 23, 0.5, 1.5)
+    shift = synth.synth_uniform((groups * n,), 24, -0.5, 0.5)
+    res = synth.synth_normal((M, groups * n), 25) if use_res else None
+    want = _gemm_ref(a1, w, scale, shift, act, 0.2, res, a2, groups, tap3)
+    lin = _prep.make_linear(w.to(DEV), scale.to(DEV), shift.to(DEV), groups, dual=k2 > 0)
+    eng = _lib.ENGINES[engine]
+    tc_ok = lin.w_split is not None and not tap3
+    if engine in ("3xtf32", "tf32") and not tc_ok:
+        with pytest.raises(_lib.GrafpError):
+            ops.linear(a1.to(DEV), lin, act, 0.2, res.to(DEV) if use_res else None,
+                       a2.to(DEV) if k2 else None, tap3, eng)
+        return
+    got = ops.linear(a1.to(DEV), lin, act, 0.2, res.to(DEV) if use_res else None,
+                     a2.to(DEV) if k2 else None, tap3, eng).cpu().double()
+    assert got.shape == want.shape
+    err = float((got - want).abs().max() / want.abs().max())
+    # fp32-class engines: 1e-5 of the output scale; single-pass TF32: 2e-3
+    tol = 2e-3 if (engine == "tf32") else 1e-5
+    assert err < tol, "engine %s rel err %.3g" % (engine, err)
+
+
+def test_gemm_empty_and_errors():
+    ops = _ops()
+    from neuralsampleid_b200._lib import GrafpError
+    w = torch.zeros((16, 8), device=DEV)
+    assert ops.gemm(torch.zeros((0, 8), device=DEV), w).shape == (0, 16)
+    with pytest.raises(GrafpError):
+        ops.gemm(torch.zeros((4, 6), device=DEV), torch.zeros((16, 6), device=DEV))      # k % 4
+    with pytest.raises(NotImplementedError):
+        ops.gemm(torch.zeros((4, 8), device=DEV), w, act="prelu")
+    with pytest.raises(GrafpError):
+        ops.gemm(torch.zeros((4, 8)), w)                                                  # CPU tensor
+
+
+# ------------------------------------------------------------------------------------------
+# small stages
+# ------------------------------------------------------------------------------------------
+def test_node_mean_and_l2_normalize():
+    ops = _ops()
+    x = synth.synth_normal((6 * 32, 512), 30)
+    got = ops.node_mean(x.to(DEV), 6, 32).cpu()
+    assert torch.allclose(got, x.view(6, 32, 512).mean(1), rtol=1e-6, atol=1e-6)
+    z = synth.synth_normal((9, 128), 31)
+    z[3] = 0.0
+    got = ops.l2_normalize_rows(z.to(DEV), 1e-10).cpu()
+    assert torch.allclose(got, torch.nn.functional.normalize(z, p=2, eps=1e-10), rtol=1e-6, atol=1e-7)
+
+
+def test_peak_extractor_matches_oracle():
+    ops = _ops()
+    cfg = dict(n_filters=8, patch_bins=4, patch_frames=8)
+    spec = [("peak_extractor.convs.0.weight", (8, 3, 4, 8), "w"), ("peak_extractor.convs.0.bias", (8,), "b")]
+    sd = synth.synth_state(spec, 40)
+    s = synth.synth_normal((5, 64, 128), 41)
+    want = O.peak_extractor(sd, s)                                   # (B, 8, 256)
+    got = ops.peak_extract(s.to(DEV), sd["peak_extractor.convs.0.weight"].to(DEV),
+                           sd["peak_extractor.convs.0.bias"].to(DEV)).cpu()
+    want_nodes = want.transpose(1, 2).reshape(5 * 256, 8)
+    assert torch.allclose(got, want_nodes, rtol=1e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# NT-Xent
+# ------------------------------------------------------------------------------------------
+def test_ntxent_matches_golden(golden_dir):
+    from neuralsampleid_b200.simclr.ntxent import ntxent_loss
+    g = np.load(os.path.join(golden_dir, "ntxent_b16.npz"))
+    zi = torch.from_numpy(g["z_i"]).to(DEV).requires_grad_(True)
+    zj = torch.from_numpy(g["z_j"]).to(DEV).requires_grad_(True)
+    loss = ntxent_loss(zi, zj, {"tau": float(g["tau"])})
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+    np.testing.assert_allclose(zi.grad.cpu().numpy(), g["g_i"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(zj.grad.cpu().numpy(), g["g_j"], rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("B", [1, 7, 256, 1000])
+def test_ntxent_matches_oracle_sizes(B):
+    from neuralsampleid_b200.simclr.ntxent import ntxent_loss
+    z_i = torch.nn.functional.normalize(synth.synth_normal((B, 128), 50), dim=1)
+    z_j = torch.nn.functional.normalize(z_i + 0.3 * synth.synth_normal((B, 128), 51), dim=1)
+    a = z_i.clone().requires_grad_(True)
+    b = z_j.clone().requires_grad_(True)
+    want = O.ntxent(a, b, 0.05)
+    want.backward()
+    zi = z_i.to(DEV).requires_grad_(True)
+    zj = z_j.to(DEV).requires_grad_(True)
+    loss = ntxent_loss(zi, zj, {"tau": 0.05})
+    (2.0 * loss).backward()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=2e-5)
+    scale = float(a.grad.abs().max())
+    assert float((zi.grad.cpu() - 2 * a.grad).abs().max()) < 2e-4 * 2 * scale + 1e-7
+    assert float((zj.grad.cpu() - 2 * b.grad).abs().max()) < 2e-4 * 2 * scale + 1e-7
+
+
+def test_ntxent_sharded_rows_equal_global():
+    """The data-parallel form: two ranks' row ranges sum to the global loss and the local slices of
+    the gradient concatenate to the global gradient (no collective needed to check the kernel)."""
+    ops = _ops()
+    B = 24
+    z = torch.nn.functional.normalize(synth.synth_normal((2 * B, 128), 52), dim=1).to(DEV)
+    loss, lse = ops.ntxent_fwd(z, 0.05)
+    l0, lse0 = ops.ntxent_fwd(z, 0.05, 0, 20)
+    l1, lse1 = ops.ntxent_fwd(z, 0.05, 20, 2 * B - 20)
+    assert torch.allclose(l0 + l1, loss, rtol=1e-6)
+    assert torch.equal(torch.cat([lse0, lse1]), lse)
+    one = torch.ones(1, device=DEV)
+    dz = ops.ntxent_bwd(z, lse, 0.05, one)
+    d0 = ops.ntxent_bwd(z, lse, 0.05, one, 0, 20)
+    d1 = ops.ntxent_bwd(z, lse, 0.05, one, 20, 2 * B - 20)
+    assert torch.equal(torch.cat([d0, d1]), dz)

@@ -1,0 +1,213 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol declared in
+include/grafp.h, prepared-weight folding, state_dict compatibility, loud failure without CUDA,
+and the world_size-2 (gloo) logic of the data-parallel NT-Xent / segment sharding."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grafp_oracle as O
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = dict(n_mels=64, n_frames=128, patch_bins=4, patch_frames=8, n_filters=8, tau=0.05,
+           d=128, h=1024, u=32, dim=2048, arch="grafp", bsz_train=256, lr=8.0e-5)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from neuralsampleid_b200 import build, _lib
+    build.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "grafp.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(grafp_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    handle = lib.load()
+    for name in sorted(declared):
+        assert hasattr(handle, name), "library does not export %s" % name
+    assert declared == set(lib.exported_symbols()), declared ^ set(lib.exported_symbols())
+    assert handle.grafp_abi_version() == 1
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(lib):
+    sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_product_fails_loudly_without_cuda(lib):
+    from neuralsampleid_b200 import ops
+    with pytest.raises(lib.GrafpError):
+        ops.knn(torch.zeros((16, 8)), 1, 16, 3)
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    enc = GraphEncoder(cfg=CFG, in_channels=8, k=3).eval()
+    with pytest.raises(lib.GrafpError):
+        enc(torch.zeros((1, 8, 256)))
+    # the product never imports the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "neuralsampleid_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_state_dict_layout_matches_reference_spec():
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    from neuralsampleid_b200.simclr.simclr import SimCLR
+    model = SimCLR(CFG, encoder=GraphEncoder(cfg=CFG, in_channels=8, k=3))
+    sd = model.state_dict()
+    spec = synth.simclr_state_spec(CFG, "t")
+    assert [n for n, _, _ in spec] == list(sd.keys())
+    for n, shape, _ in spec:
+        assert tuple(sd[n].shape) == tuple(shape), n
+    assert len(sd) == 443
+    model.load_state_dict(synth.synth_state(spec, 1236))
+    model.load_state_dict({"module." + k: v for k, v in sd.items()}, strict=False)   # DataParallel-style keys are ignored
+
+
+def test_fold_conv_bn_matches_oracle_layers():
+    from neuralsampleid_b200 import _prep
+    sd = synth.synth_state(synth.encoder_state_spec("t", 8, 1024, 256), 1234)
+    x = synth.synth_normal((2, 64, 256, 1), 5)
+    bn = torch.nn.BatchNorm2d(64)
+    bn.load_state_dict({k[len("backbone.0.0.fc1.1."):]: v for k, v in sd.items() if k.startswith("backbone.0.0.fc1.1.")})
+    w, s, t = _prep.fold_conv_bn(sd["backbone.0.0.fc1.0.weight"], sd["backbone.0.0.fc1.0.bias"], bn.eval())
+    want = O._bn(sd, "backbone.0.0.fc1.1",
+                 torch.nn.functional.conv2d(x, sd["backbone.0.0.fc1.0.weight"], sd["backbone.0.0.fc1.0.bias"]),
+                 False, None)
+    nodes = x.reshape(2, 64, 256).transpose(1, 2).reshape(512, 64)
+    got = (nodes @ w.T) * s + t
+    assert torch.allclose(got, want.reshape(2, 64, 256).transpose(1, 2).reshape(512, 64), rtol=1e-5, atol=1e-5)
+    # Downsample: centre column of the 3x3 kernel as a 3-tap stride-2 conv over nodes
+    wd = sd["backbone.2.conv.0.weight"]
+    w3 = _prep.tap3_weight(wd)
+    xin = synth.synth_normal((2, 64, 256, 1), 6)
+    want = torch.nn.functional.conv2d(xin, wd, None, stride=2, padding=1)              # (2,128,128,1)
+    xn = xin.reshape(2, 64, 256).transpose(1, 2)                                       # (2,256,64)
+    pad = torch.cat([torch.zeros(2, 1, 64), xn], dim=1)
+    A = torch.cat([pad[:, 0:-1:2], pad[:, 1::2], pad[:, 2::2]], dim=2)                 # (2,128,192)
+    got = A @ w3.T
+    assert torch.allclose(got, want.reshape(2, 128, 128).transpose(1, 2), rtol=1e-4, atol=1e-5)
+
+
+def test_mrconv_weight_regrouping_matches_interleave():
+    """BasicConv's [even | odd] column regrouping + dual-source groups == the reference's interleaved cat."""
+    C = 64
+    w = synth.synth_normal((2 * C, C // 2, 1, 1), 9)
+    x = synth.synth_normal((1, C, 10, 1), 10)
+    m = synth.synth_normal((1, C, 10, 1), 11)
+    want = torch.nn.functional.conv2d(O.interleave(x, m), w, None, groups=4)           # (1,2C,10,1)
+    w2 = w.reshape(2 * C, C // 2)
+    wr = torch.cat([w2[:, 0::2], w2[:, 1::2]], dim=1)
+    xn, mn = x.reshape(C, 10).T, m.reshape(C, 10).T
+    outs = []
+    kp, n = C // 4, 2 * C // 4
+    for g in range(4):
+        A = torch.cat([xn[:, g * kp:(g + 1) * kp], mn[:, g * kp:(g + 1) * kp]], dim=1)
+        outs.append(A @ wr[g * n:(g + 1) * n].T)
+    got = torch.cat(outs, dim=1)
+    assert torch.allclose(got, want.reshape(2 * C, 10).T, rtol=1e-5, atol=1e-5)
+    # and the block-diagonal densification used when k/group is not a multiple of 32
+    from neuralsampleid_b200 import _prep
+    lin = _prep.make_linear(wr, None, None, groups=4, dual=True)
+    assert lin.groups == 1 and lin.w.shape == (2 * C, 2 * C)
+    got2 = torch.cat([xn, mn], dim=1) @ lin.w.T
+    assert torch.allclose(got2, got, rtol=1e-5, atol=1e-5)
+
+
+def test_unsupported_variants_raise_like_the_reference():
+    from neuralsampleid_b200.encoder.gcn_lib.torch_nn import act_layer, norm_layer
+    from neuralsampleid_b200.encoder.gcn_lib.torch_vertex import GraphConv2d
+    with pytest.raises(NotImplementedError):
+        act_layer("swish")
+    with pytest.raises(NotImplementedError):
+        norm_layer("layer", 8)
+    with pytest.raises(NotImplementedError):
+        GraphConv2d(8, 16, conv="foo")
+
+
+# ------------------------------------------------------------------------------------------
+# world_size 2, gloo
+# ------------------------------------------------------------------------------------------
+def _cpu_ntxent_fwd(z, tau, row0=0, rows=None):
+    n = z.shape[0]
+    rows = n if rows is None else rows
+    a = (z @ z.T) / tau
+    a = a.masked_fill(torch.eye(n, dtype=torch.bool), float("-inf"))
+    lse = torch.logsumexp(a, dim=1)[row0:row0 + rows]
+    i = torch.arange(row0, row0 + rows)
+    pos = ((z[i] * z[i ^ 1]).sum(1)) / tau
+    return (-(pos - lse).sum() / n).reshape(1), lse
+
+
+def _cpu_ntxent_bwd(z, lse_all, tau, g, row0=0, rows=None):
+    n = z.shape[0]
+    rows = n if rows is None else rows
+    a = (z @ z.T) / tau
+    i = torch.arange(row0, row0 + rows)
+    coef = torch.exp(a[i] - lse_all[i, None]) + torch.exp(a[i] - lse_all[None, :])
+    coef[torch.arange(rows), i] = 0.0
+    coef[torch.arange(rows), i ^ 1] -= 2.0
+    return (coef @ z) * (g.reshape(()) / (n * tau))
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from neuralsampleid_b200 import ops
+    from neuralsampleid_b200.simclr import ntxent as nt
+    from neuralsampleid_b200.parallel import shard_range
+    ops.ntxent_fwd, ops.ntxent_bwd = _cpu_ntxent_fwd, _cpu_ntxent_bwd      # host logic under test
+    B = 6
+    z_i = torch.nn.functional.normalize(synth.synth_normal((world * B, 16), 1), dim=1)
+    z_j = torch.nn.functional.normalize(z_i + 0.2 * synth.synth_normal((world * B, 16), 2), dim=1)
+    lo, hi = shard_range(world * B, rank, world)
+    a = z_i[lo:hi].clone().requires_grad_(True)
+    b = z_j[lo:hi].clone().requires_grad_(True)
+    loss = nt.ntxent_loss_distributed(a, b, {"tau": 0.05})
+    loss.backward()
+    q.put((rank, loss.item(), a.grad.numpy(), b.grad.numpy(), (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_distributed_ntxent_equals_global_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 29611
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)])
+    for p in procs:
+        p.join(60)
+    B = 6
+    z_i = torch.nn.functional.normalize(synth.synth_normal((world * B, 16), 1), dim=1).requires_grad_(True)
+    z_j = torch.nn.functional.normalize(z_i.detach() + 0.2 * synth.synth_normal((world * B, 16), 2), dim=1).requires_grad_(True)
+    want = O.ntxent(z_i, z_j, 0.05)
+    want.backward()
+    for rank, loss, ga, gb, (lo, hi) in res:
+        assert abs(loss - want.item()) < 1e-5
+        np.testing.assert_allclose(ga, z_i.grad[lo:hi].numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(gb, z_j.grad[lo:hi].numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_shard_range_partitions_exactly():
+    from neuralsampleid_b200.parallel import shard_range
+    for n in (0, 1, 7, 4096, 1000000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
