@@ -164,7 +164,7 @@ extern "C" {
 
 int grafp_mr_aggregate_fwd(const float* x, const int32_t* idx, int B, int N, int C, int k,
                            float* m, uint8_t* arg_out, void* stream) {
-  GRAFP_REQUIRE(x && idx && m, "mr_aggregate: null pointer");
+  GRAFP_REQUIRE(B <= 0 || (x && idx && m), "mr_aggregate: null pointer");
   GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0 && k <= 255, "mr_aggregate: bad sizes");
   GRAFP_REQUIRE(C % 4 == 0, "mr_aggregate: C=%d must be a multiple of 4", C);
   if (B == 0) return 0;

@@ -12,9 +12,9 @@ using namespace grafp;
 extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
   GRAFP_REQUIRE(args, "gemm: null args");
   const grafp_gemm_args& a = *args;
-  GRAFP_REQUIRE(a.a1 && a.w && a.y, "gemm: null pointer");
   GRAFP_REQUIRE(a.m >= 0 && a.n > 0 && a.groups > 0 && a.k1 > 0 && a.k2 >= 0, "gemm: bad sizes");
-  GRAFP_REQUIRE((a.k2 == 0) == (a.a2 == nullptr), "gemm: a2/k2 mismatch");
+  GRAFP_REQUIRE(a.m == 0 || (a.a1 && a.w && a.y), "gemm: null pointer");
+  GRAFP_REQUIRE(a.m == 0 || (a.k2 == 0) == (a.a2 == nullptr), "gemm: a2/k2 mismatch");
   GRAFP_REQUIRE(a.k1 % 4 == 0 && a.k2 % 4 == 0, "gemm: k1=%d, k2=%d must be multiples of 4", a.k1,
                 a.k2);
   GRAFP_REQUIRE(a.k2 == 0 || a.k1 % 16 == 0, "gemm: dual-source needs k1 %% 16 == 0 (k1=%d)", a.k1);

@@ -187,8 +187,8 @@ using namespace grafp;
 
 extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dilation,
                              int normalize, int32_t* idx_out, float* dist_out, void* stream) {
-  GRAFP_REQUIRE(x && idx_out, "knn: null pointer");
   GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0 && dilation > 0, "knn: bad sizes");
+  GRAFP_REQUIRE(B == 0 || (x && idx_out), "knn: null pointer");
   GRAFP_REQUIRE(C % 4 == 0, "knn: C=%d must be a multiple of 4", C);
   const int kk = k * dilation;
   GRAFP_REQUIRE(kk <= N, "knn: k*dilation=%d exceeds the %d nodes of a graph", kk, N);

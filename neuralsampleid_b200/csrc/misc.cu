@@ -174,16 +174,16 @@ const char* grafp_last_error(void) { return g_err; }
 int64_t grafp_launch_count(void) { return g_launches.load(); }
 
 int grafp_nchw_to_nodes(const float* src, float* dst, int B, int C, int N, void* stream) {
-  GRAFP_REQUIRE(src && dst && B >= 0 && C > 0 && N > 0, "nchw_to_nodes: bad arguments");
+  GRAFP_REQUIRE(B >= 0 && C > 0 && N > 0 && (B == 0 || (src && dst)), "nchw_to_nodes: bad arguments");
   return transpose_batched(src, dst, B, C, N, as_stream(stream));
 }
 int grafp_nodes_to_nchw(const float* src, float* dst, int B, int C, int N, void* stream) {
-  GRAFP_REQUIRE(src && dst && B >= 0 && C > 0 && N > 0, "nodes_to_nchw: bad arguments");
+  GRAFP_REQUIRE(B >= 0 && C > 0 && N > 0 && (B == 0 || (src && dst)), "nodes_to_nchw: bad arguments");
   return transpose_batched(src, dst, B, N, C, as_stream(stream));
 }
 
 int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream) {
-  GRAFP_REQUIRE(x && out && B >= 0 && N > 0 && C > 0, "node_mean: bad arguments");
+  GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && (B == 0 || (x && out)), "node_mean: bad arguments");
   if (B == 0) return 0;
   node_mean_kernel<<<B, C < 256 ? ((C + 31) / 32) * 32 : 256, 0, as_stream(stream)>>>(x, out, N, C);
   return check_launch("node_mean");
@@ -191,7 +191,7 @@ int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* strea
 
 int grafp_l2_normalize_rows(const float* z, int64_t M, int D, float eps, float* out,
                             void* stream) {
-  GRAFP_REQUIRE(z && out && M >= 0 && D > 0, "l2_normalize_rows: bad arguments");
+  GRAFP_REQUIRE(M >= 0 && D > 0 && (M == 0 || (z && out)), "l2_normalize_rows: bad arguments");
   if (M == 0) return 0;
   const int warps = 8;
   l2norm_rows_kernel<<<(unsigned)((M + warps - 1) / warps), warps * 32, 0, as_stream(stream)>>>(
@@ -202,7 +202,7 @@ int grafp_l2_normalize_rows(const float* z, int64_t M, int D, float eps, float* 
 int grafp_peak_extract_fwd(const float* spec, const float* w, const float* bias, int B,
                            int n_mels, int n_frames, int F, int pb, int pf, float* out,
                            void* stream) {
-  GRAFP_REQUIRE(spec && w && bias && out, "peak_extract: null pointer");
+  GRAFP_REQUIRE(B == 0 || (spec && w && bias && out), "peak_extract: null pointer");
   GRAFP_REQUIRE(pb > 0 && pf > 0 && n_mels % pb == 0 && n_frames % pf == 0,
                 "peak_extract: patch (%d,%d) must tile (%d,%d)", pb, pf, n_mels, n_frames);
   if (B == 0) return 0;

@@ -117,7 +117,7 @@ def test_encoder_matches_reference_golden(golden_dir, fname, k):
     assert float(_rel(got_f.cpu(), torch.from_numpy(g["emb"])).max()) < REL_TOL
 
 
-@pytest.mark.parametrize("engine", ["simt", "3xtf32"])
+@pytest.mark.parametrize("engine", ["simt", "auto"])
 def test_encoder_engines_agree(engine):
     from neuralsampleid_b200 import ops
     enc, sd = _encoder(3)
@@ -194,10 +194,12 @@ def test_grapher_module_api_matches_oracle():
     with torch.no_grad():
         want = O.grapher(p, "g", x, 9, 2, "mr", "relu", False, None, taps)
         got = m(x.to(DEV)).cpu()
-    tie = O.knn_tie_rows(taps["dist"], 18, TIE_TOL).any(-1)            # per graph
-    ok = ~tie
-    assert ok.any()
-    assert float(_rel(got[ok], want[ok]).max()) < REL_TOL
+    # a node's output depends only on its own neighbour list: compare every off-tie node
+    ok = ~O.knn_tie_rows(taps["dist"], 18, TIE_TOL)                    # (B, N)
+    assert float(ok.float().mean()) > 0.5
+    a = got.squeeze(-1).transpose(1, 2)[ok]
+    b = want.squeeze(-1).transpose(1, 2)[ok]
+    assert float(_rel(a, b).max()) < REL_TOL
     # functional entry points keep the reference's shapes / dtypes
     idx = torch.randint(0, 128, (3, 128, 5))
     sel = batched_index_select(x.to(DEV), idx.to(DEV))

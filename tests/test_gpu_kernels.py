@@ -254,8 +254,10 @@ def test_gemm_engines(case, engine):
                      a2.to(DEV) if k2 else None, tap3, eng).cpu().double()
     assert got.shape == want.shape
     err = float((got - want).abs().max() / want.abs().max())
-    # fp32-class engines: 1e-5 of the output scale; single-pass TF32: 2e-3
-    tol = 2e-3 if (engine == "tf32") else 1e-5
+    # fp32 FFMA engine: 1e-5 of the output scale.  3xTF32: the tensor core's fp32 accumulator
+    # truncates on every MMA, a bias that grows with the number of k-steps (measured 1.3e-5 at
+    # k=2048, 3.0e-5 at k=4096) -> 5e-5.  Single-pass TF32: 2e-3.
+    tol = {"tf32": 2e-3, "simt": 1e-5}.get(engine, 5e-5)
     assert err < tol, "engine %s rel err %.3g" % (engine, err)
 
 
