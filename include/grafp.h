@@ -24,6 +24,7 @@
 #ifndef GRAFP_H_
 #define GRAFP_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -62,9 +63,16 @@ int grafp_nodes_to_nchw(const float* src, float* dst, int B, int C, int N, void*
  *   x        (B*N, C) node-major features (un-normalised when `normalize` != 0)
  *   idx_out  (B, N, k) int32: ranks 0, d, 2d, ... of the ascending-distance list
  *   dist_out optional (B, N, k) fp32 distances of the selected ranks (may be NULL)
- * Limits: k*dilation <= 128, k*dilation <= N, C % 4 == 0, N <= 4096. */
+ *   engine   GRAFP_ENGINE_AUTO: tcgen05 3xTF32 Gram tiles + thread-per-row top-k when the shape
+ *            allows (N in {16,32,64,128,256}, C % 32 == 0, k*dilation <= 16) and a workspace is
+ *            given, else the exact fp32 SIMT kernel; GRAFP_ENGINE_SIMT / GRAFP_ENGINE_TC_3XTF32
+ *            force one of them.
+ *   workspace  caller-owned scratch of grafp_knn_workspace_bytes() bytes (may be NULL -> SIMT)
+ * Limits: k*dilation <= N, C % 4 == 0, N <= 2048. */
+size_t grafp_knn_workspace_bytes(int B, int N, int C, int k, int dilation);
 int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dilation, int normalize,
-                  int32_t* idx_out, float* dist_out, void* stream);
+                  int engine, int32_t* idx_out, float* dist_out, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ---- neighbour gather + max-relative aggregation ---------------------------------------
  * Replaces the two batched_index_select calls (encoder/gcn_lib/torch_nn.py:79-98) and

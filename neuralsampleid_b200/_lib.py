@@ -39,7 +39,7 @@ _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "grafp_nchw_to_nodes": [_P, _P, _I, _I, _I, _P],
     "grafp_nodes_to_nchw": [_P, _P, _I, _I, _I, _P],
-    "grafp_knn_fwd": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "grafp_knn_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P],
     "grafp_mr_aggregate_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
     "grafp_mr_aggregate_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "grafp_index_select": [_P, _P, _I, _I, _I, _I, _P, _P],
@@ -52,7 +52,8 @@ SIGNATURES = {
     "grafp_ntxent_fwd": [_P, _I, _I, _F, _I, _I, _P, _P, _P],
     "grafp_ntxent_bwd": [_P, _P, _I, _I, _F, _I, _I, _P, _P, _P],
 }
-SPECIAL = {"grafp_abi_version": ([], C.c_int), "grafp_last_error": ([], C.c_char_p),
+SPECIAL = {"grafp_knn_workspace_bytes": ([_I, _I, _I, _I, _I], C.c_size_t),
+           "grafp_abi_version": ([], C.c_int), "grafp_last_error": ([], C.c_char_p),
            "grafp_launch_count": ([], C.c_int64)}
 
 _lib = None

@@ -185,8 +185,21 @@ static int knn_launch(const float* x, int B, int N, int C, int kk, int d, int k,
 
 using namespace grafp;
 
+namespace grafp {
+int knn_tc_supported(int B, int N, int C, int kk);
+size_t knn_tc_workspace_bytes(int B, int N);
+int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int normalize,
+                  int32_t* idx, float* dist, float* workspace, cudaStream_t st);
+}  // namespace grafp
+
+extern "C" size_t grafp_knn_workspace_bytes(int B, int N, int C, int k, int dilation) {
+  if (B <= 0 || N <= 0 || C <= 0 || k <= 0 || dilation <= 0) return 0;
+  return knn_tc_supported(B, N, C, k * dilation) ? knn_tc_workspace_bytes(B, N) : 0;
+}
+
 extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dilation,
-                             int normalize, int32_t* idx_out, float* dist_out, void* stream) {
+                             int normalize, int engine, int32_t* idx_out, float* dist_out,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0 && dilation > 0, "knn: bad sizes");
   GRAFP_REQUIRE(B == 0 || (x && idx_out), "knn: null pointer");
   GRAFP_REQUIRE(C % 4 == 0, "knn: C=%d must be a multiple of 4", C);
@@ -195,6 +208,16 @@ extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dil
   GRAFP_REQUIRE(N <= 2048, "knn: N=%d above the 2048-node limit of the dense kernel", N);
   if (B == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  const bool tc_ok = knn_tc_supported(B, N, C, kk) && workspace &&
+                     workspace_bytes >= knn_tc_workspace_bytes(B, N);
+  if (engine == GRAFP_ENGINE_TC_3XTF32) {
+    GRAFP_REQUIRE(tc_ok, "knn: tcgen05 engine needs N in {16..128 | 128, 256}, C %% 32 == 0, k*d <= 16 "
+                         "and a workspace of grafp_knn_workspace_bytes()");
+  }
+  if ((engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_TC_3XTF32) && tc_ok)
+    return knn_tc_launch(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out,
+                         static_cast<float*>(workspace), st);
+  GRAFP_REQUIRE(engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_SIMT, "knn: unknown engine %d", engine);
   if (N <= 16) return knn_launch<1>(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out, st);
   if (N <= 32) return knn_launch<2>(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out, st);
   if (N <= 512) return knn_launch<4>(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out, st);

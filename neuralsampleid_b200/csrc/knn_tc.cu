@@ -1,0 +1,304 @@
+// Dense dilated kNN graph on the tensor cores (sm_100a).
+//
+// Pairwise distance = a 3xTF32 tcgen05 Gram-tile contraction fed by TMA; the 128 x N distance
+// tile lives only in TMEM; the epilogue is a thread-per-row (TMEM lane = node) streaming top-(k*d)
+// insertion that emits every d-th rank.  The N x N matrix never reaches shared or global memory.
+//
+//   prepass   rinv[m] = 1 / max(||x_m||, 1e-12), sq[m] = sum_c (x_mc * rinv_m)^2    (one read of x)
+//   tile      rows = 128 consecutive nodes; columns = the nodes of the rows' graph (N >= 128) or
+//             the same 128 nodes (N < 128, block-diagonal mask in the epilogue)
+//   transform both operand stages are scaled by rinv (F.normalize) and split hi/lo in shared memory
+//   MMA       D = Xn_rows * Xn_cols^T, 3 kind::tf32 passes, fp32 accumulate in TMEM (double-buffered)
+//   epilogue  dist = (sq_i + (-2 * dot)) + sq_j  (reference association, torch_edge.py:16-18),
+//             ascending (distance, index) insertion, lowest index first on exact ties
+//
+// Warp roles (448 threads): warp 0 TMA, warp 1 MMA issuer + TMEM allocator, warps 2-9 transform,
+// warps 10-13 epilogue.
+#include "tc_common.cuh"
+
+namespace grafp {
+
+constexpr int KT_THREADS = 448;
+constexpr int KT_MAX_STAGES = 4;
+
+struct KnnTcParams {
+  int N, C, kk, d, k;
+  int64_t M;
+  int bn;                 // columns per tile: N (N >= 128) or 128
+  int stages;
+  const float* rinv; const float* sq;
+  int32_t* idx; float* dist;
+  uint32_t tmem_cols;
+};
+
+__global__ void knn_rownorm_kernel(const float* __restrict__ x, int64_t M, int C, int normalize,
+                                   float* __restrict__ rinv, float* __restrict__ sq) {
+  const int warps = blockDim.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * C;
+  float s = 0.0f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+  }
+  s = warp_sum(s);
+  float ri = 1.0f, q = s;
+  if (normalize) {
+    ri = __frcp_rn(fmaxf(sqrtf(s), 1e-12f));
+    float t = 0.0f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float a0 = v.x * ri, a1 = v.y * ri, a2 = v.z * ri, a3 = v.w * ri;
+      t = fmaf(a0, a0, t); t = fmaf(a1, a1, t); t = fmaf(a2, a2, t); t = fmaf(a3, a3, t);
+    }
+    q = warp_sum(t);
+  }
+  if (lane == 0) { rinv[row] = ri; sq[row] = q; }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(KT_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant__ CUtensorMap tmCols,
+              const KnnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[KT_MAX_STAGES];
+  __shared__ __align__(8) uint64_t xf_bar[KT_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[KT_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 4;
+  const uint32_t stage_bytes = 2u * (TC_A_BYTES + b_bytes);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + TC_A_BYTES; };
+  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TC_A_BYTES; };
+  auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
+
+  const int nkb = p.C / TC_BK;
+  const int64_t total_tiles = (p.M + TC_BM - 1) / TC_BM;
+  auto col_start = [&](int64_t m0) -> int64_t { return p.N >= TC_BM ? (m0 / p.N) * p.N : m0; };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmRows);
+    tma_prefetch_desc(&tmCols);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&xf_bar[s], 256);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int64_t m0 = tile * TC_BM, c0 = col_start(m0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], TC_A_BYTES + b_bytes);
+          tma_load_2d(a_hi(s), &tmRows, kb * TC_BK, (int)m0, &full_bar[s]);
+          tma_load_2d(b_hi(s), &tmCols, kb * TC_BK, (int)c0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, p.bn);
+      uint32_t it = 0, ti = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[buf], tph ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          mbar_wait(&xf_bar[s], ph);
+          tc_fence_after();
+          const uint64_t dah = umma_desc_sw128(smem_u32(a_hi(s)));
+          const uint64_t dal = umma_desc_sw128(smem_u32(a_lo(s)));
+          const uint64_t dbh = umma_desc_sw128(smem_u32(b_hi(s)));
+          const uint64_t dbl = umma_desc_sw128(smem_u32(b_lo(s)));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+            umma_tf32(tacc, dal + koff, dbh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
+            umma_tf32(tacc, dah + koff, dbh + koff, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else if (warp < 10) {
+    // ===== transform (256 threads): scale rows by rinv (F.normalize), split tf32 hi / lo =====
+    const int t = threadIdx.x - 64;
+    const int a_vec = TC_A_BYTES / 16;                  // 1024 float4
+    const int b_vec = (int)(b_bytes / 16);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int64_t m0 = tile * TC_BM, c0 = col_start(m0);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        float4* ah = reinterpret_cast<float4*>(a_hi(s));
+        float4* al = reinterpret_cast<float4*>(a_lo(s));
+        float4* bh = reinterpret_cast<float4*>(b_hi(s));
+        float4* bl = reinterpret_cast<float4*>(b_lo(s));
+        for (int q = t; q < a_vec + b_vec; q += 256) {
+          const bool is_a = q < a_vec;
+          const int qq = is_a ? q : q - a_vec;
+          const int64_t node = (is_a ? m0 : c0) + (qq >> 3);
+          const float ri = node < p.M ? __ldg(p.rinv + node) : 0.0f;
+          float4* hp = is_a ? ah + qq : bh + qq;
+          float4* lp = is_a ? al + qq : bl + qq;
+          float4 v = *hp;
+          v.x *= ri; v.y *= ri; v.z *= ri; v.w *= ri;
+          float4 h, l;
+          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y);
+          l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+          *hp = h;
+          *lp = l;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&xf_bar[s]);
+      }
+    }
+  } else {
+    // ===== epilogue (128 threads): streaming per-row top-(k*d) over the TMEM distance tile =====
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    uint32_t ti = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int64_t m0 = tile * TC_BM, c0 = col_start(m0);
+      const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+      const int64_t grow = m0 + r;
+      const bool row_ok = grow < p.M;
+      const int64_t gs = row_ok ? (grow / p.N) * p.N : 0;      // first node of this row's graph
+      const float sqi = row_ok ? __ldg(p.sq + grow) : 0.0f;
+      float bd[KMAX];
+      int bj[KMAX];
+#pragma unroll
+      for (int t = 0; t < KMAX; ++t) { bd[t] = INFINITY; bj[t] = (int)(grow - gs); }
+      mbar_wait(&tmem_full_bar[buf], tph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
+      for (int c = 0; c < p.bn; c += 16) {
+        float v[16];
+        tmem_ld16_nowait(tacc + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c + 16 >= p.bn) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[buf]);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int64_t gcol = c0 + c + q;
+          const bool ok = row_ok && gcol < p.M && gcol >= gs && gcol < gs + p.N;
+          if (ok) {
+            const float dv = __fadd_rn(__fadd_rn(sqi, -2.0f * v[q]), __ldg(p.sq + gcol));
+            if (dv < bd[KMAX - 1]) {
+              bd[KMAX - 1] = dv;
+              bj[KMAX - 1] = (int)(gcol - gs);
+#pragma unroll
+              for (int t = KMAX - 1; t > 0; --t) {
+                if (bd[t] < bd[t - 1]) {
+                  const float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td;
+                  const int tj = bj[t]; bj[t] = bj[t - 1]; bj[t - 1] = tj;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+          if (t < p.kk && (t % p.d) == 0) {
+            const int64_t o = grow * p.k + t / p.d;
+            p.idx[o] = bj[t];
+            if (p.dist) p.dist[o] = bd[t];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int knn_tc_supported(int B, int N, int C, int kk) {
+  if (kk > 16) return 0;
+  if (C % TC_BK != 0) return 0;
+  if (N > 256) return 0;
+  if (N >= TC_BM) return N % TC_BM == 0;
+  return N >= 16 && TC_BM % N == 0;
+}
+
+size_t knn_tc_workspace_bytes(int B, int N) { return (size_t)B * N * 2 * sizeof(float); }
+
+template <int KMAX>
+static int knn_tc_launch_t(const CUtensorMap& mr, const CUtensorMap& mc, const KnnTcParams& p,
+                           size_t smem, int grid, cudaStream_t st) {
+  cudaFuncSetAttribute(knn_tc_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  knn_tc_kernel<KMAX><<<grid, KT_THREADS, smem, st>>>(mr, mc, p);
+  return check_launch("knn_tc");
+}
+
+int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int normalize,
+                  int32_t* idx, float* dist, float* workspace, cudaStream_t st) {
+  const int64_t M = (int64_t)B * N;
+  float* rinv = workspace;
+  float* sq = workspace + M;
+  knn_rownorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, M, C, normalize, rinv, sq);
+  if (int rc = check_launch("knn_rownorm")) return rc;
+  KnnTcParams p;
+  p.N = N; p.C = C; p.kk = kk; p.d = d; p.k = k; p.M = M;
+  p.bn = N >= TC_BM ? N : TC_BM;
+  p.rinv = rinv; p.sq = sq; p.idx = idx; p.dist = dist;
+  uint32_t cols = 32;
+  while ((int)cols < 2 * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t stage_bytes = 2 * (TC_A_BYTES + (size_t)p.bn * TC_BK * 4);
+  int stages = (int)((224 * 1024 - 1024) / stage_bytes);
+  if (stages > KT_MAX_STAGES) stages = KT_MAX_STAGES;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = stage_bytes * stages + 1024;
+  CUtensorMap mr, mc;
+  if (int rc = tc_make_map_2d(&mr, x, M, C, C, TC_BM)) return rc;
+  if (int rc = tc_make_map_2d(&mc, x, M, C, C, p.bn)) return rc;
+  const int64_t tiles = (M + TC_BM - 1) / TC_BM;
+  int grid = sm_count();
+  if (tiles < grid) grid = (int)tiles;
+  if (kk <= 4) return knn_tc_launch_t<4>(mr, mc, p, smem, grid, st);
+  if (kk <= 8) return knn_tc_launch_t<8>(mr, mc, p, smem, grid, st);
+  return knn_tc_launch_t<16>(mr, mc, p, smem, grid, st);
+}
+
+}  // namespace grafp

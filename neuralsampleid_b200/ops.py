@@ -74,15 +74,20 @@ def nodes_to_nchw(x: torch.Tensor, B: int, N: int) -> torch.Tensor:
 
 
 def knn(x: torch.Tensor, B: int, N: int, k: int, dilation: int = 1, normalize: bool = True,
-        return_dist: bool = False):
+        return_dist: bool = False, engine: Optional[int] = None):
     """Dense dilated kNN over node-major features -> int32 (B, N, k) [, fp32 (B, N, k)]."""
     x = _chk(x, name="x")
     Cc = x.shape[1]
     idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
     dist = torch.empty((B, N, k), device=x.device, dtype=torch.float32) if return_dist else None
+    eng = _engine if engine is None else engine
+    eng = {_lib.ENGINE_TC_TF32: _lib.ENGINE_TC_3XTF32}.get(eng, eng)
+    lib = _lib.load()
+    ws_bytes = int(lib.grafp_knn_workspace_bytes(B, N, Cc, k, dilation)) if eng != _lib.ENGINE_SIMT else 0
+    ws = torch.empty((ws_bytes // 4,), device=x.device, dtype=torch.float32) if ws_bytes else None
     with torch.cuda.device(x.device):
-        check(_lib.load().grafp_knn_fwd(_ptr(x), B, N, Cc, k, dilation, int(normalize), _ptr(idx),
-                                        _ptr(dist), _stream(x)), "knn_fwd")
+        check(lib.grafp_knn_fwd(_ptr(x), B, N, Cc, k, dilation, int(normalize), eng, _ptr(idx),
+                                _ptr(dist), _ptr(ws), ws_bytes, _stream(x)), "knn_fwd")
     return (idx, dist) if return_dist else idx
 
 

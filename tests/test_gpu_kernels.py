@@ -41,7 +41,7 @@ def test_layout_roundtrip(B, C, N):
 # ------------------------------------------------------------------------------------------
 # kNN
 # ------------------------------------------------------------------------------------------
-def _knn_check(x, k, d, tol=4e-6, normalize=True):
+def _knn_check(x, k, d, tol=4e-6, normalize=True, engine=None):
     """x: (B, C, N, 1) cpu.  Compares the kernel's ordered neighbour lists with the oracle's,
     except on rows the oracle's own distances mark as ties at `tol`."""
     ops = _ops()
@@ -52,7 +52,9 @@ def _knn_check(x, k, d, tol=4e-6, normalize=True):
     else:
         nn_idx, dist = O.dense_knn(x, k * d)
         ref = nn_idx[:, :, ::d]
-    got, gd = ops.knn(_nodes(x).to(DEV), B, N, k, d, normalize=normalize, return_dist=True)
+    from neuralsampleid_b200 import _lib
+    got, gd = ops.knn(_nodes(x).to(DEV), B, N, k, d, normalize=normalize, return_dist=True,
+                      engine=None if engine is None else _lib.ENGINES[engine])
     got = got.cpu().long()
     assert got.shape == ref.shape
     assert int(got.min()) >= 0 and int(got.max()) < N
@@ -62,7 +64,7 @@ def _knn_check(x, k, d, tol=4e-6, normalize=True):
     # distances of the selected ranks agree with the reference matrix to fp32 round-off
     want = torch.gather(dist, 2, ref)
     ok = ~diff
-    assert torch.allclose(gd.cpu()[ok], want[ok], rtol=0, atol=4e-6)
+    assert torch.allclose(gd.cpu()[ok], want[ok], rtol=0, atol=max(tol, 4e-6))
     return float(diff.float().mean()), float(tie.float().mean())
 
 
@@ -75,6 +77,18 @@ def _knn_check(x, k, d, tol=4e-6, normalize=True):
 def test_knn_matches_oracle(B, C, N, k, d):
     x = synth.synth_normal((B, C, N, 1), 100 + N + k)
     _knn_check(x, k, d)
+
+
+@pytest.mark.parametrize("engine", ["simt", "3xtf32"])
+@pytest.mark.parametrize("B,C,N,k,d", [
+    (6, 64, 256, 3, 1), (6, 128, 128, 3, 1), (6, 256, 64, 3, 1), (6, 512, 32, 3, 1),   # size-'t' stages
+    (5, 64, 256, 5, 1), (3, 64, 256, 8, 2), (3, 64, 128, 4, 3), (131, 64, 16, 4, 1), (7, 32, 64, 9, 1),
+])
+def test_knn_engines(B, C, N, k, d, engine):
+    """Both engines against the oracle.  The tensor-core engine (3xTF32 Gram + x * (1/norm) instead of
+    x / norm) perturbs distances by ~1e-6, so its documented-tie tolerance is 1e-5."""
+    x = torch.relu(synth.synth_normal((B, C, N, 1), 300 + N + k)) + 0.05 * synth.synth_normal((B, C, N, 1), 301)
+    _knn_check(x, k, d, tol=4e-6 if engine == "simt" else 1e-5, engine=engine)
 
 
 def test_knn_post_relu_features_and_duplicates():
