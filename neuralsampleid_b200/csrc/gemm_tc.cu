@@ -45,6 +45,26 @@ struct TcParams {
   uint32_t tmem_cols;
 };
 
+// v = act(v * scale + shift) + residual over one 32-column chunk of a row; scale/shift are read
+// as 128-bit broadcast loads (every thread of the CTA reads the same 32 columns)
+template <int ACT>
+__device__ __forceinline__ void epi_apply(float (&v)[32], const float* __restrict__ scale,
+                                          const float* __restrict__ shift,
+                                          const float* __restrict__ res, float act_param) {
+#pragma unroll
+  for (int q = 0; q < 32; q += 4) {
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + q));
+    if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + q));
+    if (res) r4 = *reinterpret_cast<const float4*>(res + q);
+    v[q + 0] = apply_act(fmaf(v[q + 0], sc.x, sh.x), ACT, act_param) + r4.x;
+    v[q + 1] = apply_act(fmaf(v[q + 1], sc.y, sh.y), ACT, act_param) + r4.y;
+    v[q + 2] = apply_act(fmaf(v[q + 2], sc.z, sh.z), ACT, act_param) + r4.z;
+    v[q + 3] = apply_act(fmaf(v[q + 3], sc.w, sh.w), ACT, act_param) + r4.w;
+  }
+}
+
 template <int kPasses>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -225,18 +245,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           mbar_arrive(&tmem_empty_bar[buf]);
         }
         const float* res = (p.residual && row_ok) ? p.residual + row * p.ldr + col0 + c : nullptr;
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (res) r4 = *reinterpret_cast<const float4*>(res + q);
-          const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t col = col0 + c + q + j;
-            const float sc = p.scale ? __ldg(p.scale + col) : 1.0f;
-            const float sh = p.shift ? __ldg(p.shift + col) : 0.0f;
-            v[q + j] = apply_act(fmaf(v[q + j], sc, sh), p.act, p.act_param) + rr[j];
-          }
+        const float* scp = p.scale ? p.scale + col0 + c : nullptr;
+        const float* shp = p.shift ? p.shift + col0 + c : nullptr;
+        switch (p.act) {        // one specialised, branch-free instance per activation
+          case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, scp, shp, res, p.act_param); break;
+          case GRAFP_ACT_RELU:  epi_apply<GRAFP_ACT_RELU>(v, scp, shp, res, p.act_param); break;
+          case GRAFP_ACT_LEAKY: epi_apply<GRAFP_ACT_LEAKY>(v, scp, shp, res, p.act_param); break;
+          case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, scp, shp, res, p.act_param); break;
+          default:              epi_apply<GRAFP_ACT_ELU>(v, scp, shp, res, p.act_param); break;
         }
         uint8_t* sb = store_buf + (cc & 1u) * TC_STORE_BYTES;
         if (store_thread) bulk_wait_group_read<1>();     // the store that last used `sb` has read it

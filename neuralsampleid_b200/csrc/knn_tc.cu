@@ -19,7 +19,7 @@
 namespace grafp {
 
 constexpr int KT_THREADS = 448;
-constexpr int KT_MAX_STAGES = 4;
+constexpr int KT_MAX_STAGES = 6;
 
 struct KnnTcParams {
   int N, C, kk, d, k;
@@ -60,8 +60,7 @@ __global__ void knn_rownorm_kernel(const float* __restrict__ x, int64_t M, int C
 
 template <int KMAX>
 __global__ void __launch_bounds__(KT_THREADS, 1)
-knn_tc_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant__ CUtensorMap tmCols,
-              const KnnTcParams p) {
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[KT_MAX_STAGES];
   __shared__ __align__(8) uint64_t xf_bar[KT_MAX_STAGES];
@@ -73,19 +72,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 4;
-  const uint32_t stage_bytes = 2u * (TC_A_BYTES + b_bytes);
+  // The 128 rows of a tile are a subset of its column set (same graph), so one stage holds only
+  // the column operand [hi | lo]; the row operand is a 1024-aligned window into it.
+  const uint32_t stage_bytes = 2u * b_bytes;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
-  auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + TC_A_BYTES; };
-  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TC_A_BYTES; };
-  auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
+  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + b_bytes; };
 
   const int nkb = p.C / TC_BK;
   const int64_t total_tiles = (p.M + TC_BM - 1) / TC_BM;
   auto col_start = [&](int64_t m0) -> int64_t { return p.N >= TC_BM ? (m0 / p.N) * p.N : m0; };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmRows);
     tma_prefetch_desc(&tmCols);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -113,8 +111,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant_
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[s], TC_A_BYTES + b_bytes);
-          tma_load_2d(a_hi(s), &tmRows, kb * TC_BK, (int)m0, &full_bar[s]);
+          mbar_arrive_expect_tx(&full_bar[s], b_bytes);
           tma_load_2d(b_hi(s), &tmCols, kb * TC_BK, (int)c0, &full_bar[s]);
         }
       }
@@ -128,13 +125,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant_
         mbar_wait(&tmem_empty_bar[buf], tph ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn;
+        const int64_t m0 = tile * TC_BM;
+        const uint32_t row_off = (uint32_t)(m0 - col_start(m0)) * (TC_BK * 4);   // 0 or 16 KB
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(&xf_bar[s], ph);
           tc_fence_after();
-          const uint64_t dah = umma_desc_sw128(smem_u32(a_hi(s)));
-          const uint64_t dal = umma_desc_sw128(smem_u32(a_lo(s)));
+          const uint64_t dah = umma_desc_sw128(smem_u32(b_hi(s)) + row_off);
+          const uint64_t dal = umma_desc_sw128(smem_u32(b_lo(s)) + row_off);
           const uint64_t dbh = umma_desc_sw128(smem_u32(b_hi(s)));
           const uint64_t dbl = umma_desc_sw128(smem_u32(b_lo(s)));
 #pragma unroll
@@ -152,26 +151,21 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant_
   } else if (warp < 10) {
     // ===== transform (256 threads): scale rows by rinv (F.normalize), split tf32 hi / lo =====
     const int t = threadIdx.x - 64;
-    const int a_vec = TC_A_BYTES / 16;                  // 1024 float4
     const int b_vec = (int)(b_bytes / 16);
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int64_t m0 = tile * TC_BM, c0 = col_start(m0);
+      const int64_t c0 = col_start(tile * TC_BM);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1u;
         mbar_wait(&full_bar[s], ph);
-        float4* ah = reinterpret_cast<float4*>(a_hi(s));
-        float4* al = reinterpret_cast<float4*>(a_lo(s));
         float4* bh = reinterpret_cast<float4*>(b_hi(s));
         float4* bl = reinterpret_cast<float4*>(b_lo(s));
-        for (int q = t; q < a_vec + b_vec; q += 256) {
-          const bool is_a = q < a_vec;
-          const int qq = is_a ? q : q - a_vec;
-          const int64_t node = (is_a ? m0 : c0) + (qq >> 3);
+        for (int q = t; q < b_vec; q += 256) {
+          const int64_t node = c0 + (q >> 3);
           const float ri = node < p.M ? __ldg(p.rinv + node) : 0.0f;
-          float4* hp = is_a ? ah + qq : bh + qq;
-          float4* lp = is_a ? al + qq : bl + qq;
+          float4* hp = bh + q;
+          float4* lp = bl + q;
           float4 v = *hp;
           v.x *= ri; v.y *= ri; v.z *= ri; v.w *= ri;
           float4 h, l;
@@ -263,10 +257,10 @@ int knn_tc_supported(int B, int N, int C, int kk) {
 size_t knn_tc_workspace_bytes(int B, int N) { return (size_t)B * N * 2 * sizeof(float); }
 
 template <int KMAX>
-static int knn_tc_launch_t(const CUtensorMap& mr, const CUtensorMap& mc, const KnnTcParams& p,
-                           size_t smem, int grid, cudaStream_t st) {
+static int knn_tc_launch_t(const CUtensorMap& mc, const KnnTcParams& p, size_t smem, int grid,
+                           cudaStream_t st) {
   cudaFuncSetAttribute(knn_tc_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  knn_tc_kernel<KMAX><<<grid, KT_THREADS, smem, st>>>(mr, mc, p);
+  knn_tc_kernel<KMAX><<<grid, KT_THREADS, smem, st>>>(mc, p);
   return check_launch("knn_tc");
 }
 
@@ -284,21 +278,20 @@ int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int
   uint32_t cols = 32;
   while ((int)cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t stage_bytes = 2 * (TC_A_BYTES + (size_t)p.bn * TC_BK * 4);
+  const size_t stage_bytes = 2 * (size_t)p.bn * TC_BK * 4;
   int stages = (int)((224 * 1024 - 1024) / stage_bytes);
   if (stages > KT_MAX_STAGES) stages = KT_MAX_STAGES;
   if (stages < 1) stages = 1;
   p.stages = stages;
   const size_t smem = stage_bytes * stages + 1024;
-  CUtensorMap mr, mc;
-  if (int rc = tc_make_map_2d(&mr, x, M, C, C, TC_BM)) return rc;
+  CUtensorMap mc;
   if (int rc = tc_make_map_2d(&mc, x, M, C, C, p.bn)) return rc;
   const int64_t tiles = (M + TC_BM - 1) / TC_BM;
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;
-  if (kk <= 4) return knn_tc_launch_t<4>(mr, mc, p, smem, grid, st);
-  if (kk <= 8) return knn_tc_launch_t<8>(mr, mc, p, smem, grid, st);
-  return knn_tc_launch_t<16>(mr, mc, p, smem, grid, st);
+  if (kk <= 4) return knn_tc_launch_t<4>(mc, p, smem, grid, st);
+  if (kk <= 8) return knn_tc_launch_t<8>(mc, p, smem, grid, st);
+  return knn_tc_launch_t<16>(mc, p, smem, grid, st);
 }
 
 }  // namespace grafp

