@@ -156,6 +156,61 @@ int grafp_ntxent_fwd(const float* z, int n, int D, float tau, int row0, int rows
 int grafp_ntxent_bwd(const float* z, const float* lse_all, int n, int D, float tau, int row0,
                      int rows, const float* grad_loss, float* dz, void* stream);
 
+/* ---- contrastive train step (train.py:48-83) -------------------------------------------------
+ * Train-mode layers are  raw = A W^T (grafp_gemm_fwd without epilogue)  ->  batch statistics  ->
+ * fused normalise + activation + shortcut.  nn.BatchNorm2d semantics: eps added to the biased
+ * batch variance, running_var updated with the unbiased one, momentum 0.1.  The conv bias cancels
+ * inside a train-mode BatchNorm, so it only enters the running_mean update (conv_bias). */
+/* per-column sum and sum of squares over the rows of x (M, C), accumulated in fp64 (caller zeroes) */
+int grafp_col_stats(const float* x, int64_t M, int C, int64_t ld, double* sum, double* sumsq,
+                    void* stream);
+/* batch mean / var -> fused (scale, shift), saved (mean, invstd), running-stat update.
+ * gamma/beta/conv_bias/running_* may be NULL. */
+int grafp_bn_finalize(const double* sum, const double* sumsq, int64_t M, int C, const float* gamma,
+                      const float* beta, const float* conv_bias, float eps, float momentum,
+                      float* running_mean, float* running_var, float* scale, float* shift,
+                      float* mean, float* invstd, void* stream);
+/* out = act(x * scale + shift) + residual   (C % 4 == 0; scale/shift/residual may be NULL) */
+int grafp_affine_act(const float* x, int64_t M, int C, int64_t ld, const float* scale,
+                     const float* shift, int act, float act_param, const float* residual,
+                     int64_t ldr, float* out, int64_t ldo, void* stream);
+/* backward of (BatchNorm | bias) + activation, two passes:
+ *   reduce: dz = dout * act'(raw*scale+shift);  sum_dz += dz;  sum_dz_xhat += dz * (raw-mean)*invstd
+ *   apply : draw = scale * (dz - [bn] (sum_dz + xhat * sum_dz_xhat) / M)
+ *   param : dgamma += sum_dz_xhat, dbeta += sum_dz  (dbeta doubles as the bias gradient) */
+int grafp_bn_bwd_reduce(const float* dout, int64_t ldd, const float* raw, int64_t ld, int64_t M, int C,
+                        const float* scale, const float* shift, const float* mean, const float* invstd,
+                        int act, float act_param, double* sum_dz, double* sum_dz_xhat, void* stream);
+int grafp_bn_bwd_apply(const float* dout, int64_t ldd, const float* raw, int64_t ld, int64_t M, int C,
+                       const float* scale, const float* shift, const float* mean, const float* invstd,
+                       int act, float act_param, int bn, const double* sum_dz, const double* sum_dz_xhat,
+                       float* draw, int64_t ldo, void* stream);
+int grafp_bn_param_grad(const double* sum_dz, const double* sum_dz_xhat, int C, float* dgamma,
+                        float* dbeta, void* stream);
+/* weight gradient  dw[g*n + j, :] += sum_m dy[m, g*n + j] * A_g[m, :]  (A_g as in grafp_gemm_fwd:
+ * two sources, groups, tap3); dw (groups*n, k1+k2) accumulates (caller zeroes). */
+int grafp_gemm_wgrad(const float* dy, int64_t ldy, const float* a1, int64_t lda1, int k1,
+                     const float* a2, int64_t lda2, int k2, int64_t m, int n, int groups,
+                     int tap3_nodes, float* dw, int64_t ldw, void* stream);
+/* Downsample input gradient: dA (rows, 3*cin) = dRaw W -> dX (2*rows, cin) */
+int grafp_tap3_bwd_input(const float* dA, int64_t rows, int rows_per_graph, int cin, float* dX,
+                         void* stream);
+int grafp_node_mean_bwd(const float* dmean, int B, int N, int C, float* dx, void* stream);
+int grafp_l2_normalize_rows_bwd(const float* v, const float* dz, int64_t M, int D, float eps, float* dv,
+                                void* stream);
+/* peak extractor weight / bias gradient (accumulates; caller zeroes) */
+int grafp_peak_extract_bwd(const float* spec, const float* w, const float* bias, const float* dout,
+                           int B, int n_mels, int n_frames, int F, int pb, int pf, float* dw, float* db,
+                           void* stream);
+/* clip_grad_norm_(max_norm) + Adam over flat buffers (train.py:73-75):  out_accum += sum g^2;
+ * adam_clip_step scales g by min(1, max_norm / (sqrt(*sq_norm) + 1e-6)) (max_norm <= 0: no clip)
+ * and applies torch.optim.Adam's update (no weight decay / amsgrad) for step `step` (1-based). */
+int grafp_sq_norm(const float* g, int64_t n, double* out_accum, void* stream);
+int grafp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                         float beta2, float eps, int step, float max_norm, const double* sq_norm,
+                         void* stream);
+int grafp_add_inplace(float* y, const float* x, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

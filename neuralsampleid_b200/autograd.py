@@ -1,0 +1,315 @@
+"""Train-mode forward and the hand-written backward of the SimCLR(GraphEncoder) path.
+
+The reference trains through PyTorch autograd over ~40 ATen kernels per block (train.py:61-70);
+here each view is ONE autograd node: the forward runs the node-major kernel pipeline in train mode
+(raw GEMM -> batch statistics -> fused normalise/activation/shortcut) while recording a tape, and
+the backward replays the tape with the backward kernels of csrc/train.cu, returning gradients for
+every parameter.  The kNN graph carries no gradient (it is built under no_grad in the reference,
+encoder/gcn_lib/torch_edge.py:78,96); max-relative routes the gradient to the arg-max neighbour.
+
+Weight re-layouts between the reference's parameter shapes and the (n, k) GEMM operands (the MRConv
+even/odd column regrouping, the Downsample centre-column extraction, transposes for the input
+gradient) are O(parameters) index operations done with torch on the parameter side.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._prep import tap3_weight
+
+
+class _Layer:
+    """Tape entry of one  out = act(BN(A W^T [+ bias])) [+ residual]  layer."""
+    __slots__ = ("a1", "a2", "raw", "ssmi", "act", "slope", "bn", "w2d", "groups", "tap3_nodes",
+                 "weight", "bias", "kind", "k1", "k2", "has_residual")
+
+
+def _w_split(w2d: torch.Tensor, groups: int, k_parts: int):
+    n_total, k = w2d.shape
+    if (k // k_parts) % 32 == 0 and (n_total // groups) % 32 == 0:
+        return ops.split_tf32(w2d)
+    return None
+
+
+def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: torch.Tensor, kind: str,
+              bias: Optional[nn.Parameter] = None, bn: Optional[nn.BatchNorm2d] = None, act=None,
+              slope: float = 0.0, residual: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
+              groups: int = 1, tap3_nodes: int = 0) -> torch.Tensor:
+    w2d = w2d.contiguous()
+    raw = ops.gemm(a1, w2d, None, None, None, 0.0, None, a2, groups, tap3_nodes, None, None,
+                   _w_split(w2d, groups, 2 if a2 is not None else 1))
+    M, C = raw.shape
+    if bn is not None:
+        stats = ops.col_stats(raw)
+        ssmi = ops.bn_finalize(stats, M, bn.weight.detach(), bn.bias.detach(),
+                               bias.detach() if bias is not None else None, bn.eps, bn.momentum,
+                               bn.running_mean, bn.running_var)
+        bn.num_batches_tracked += 1
+    else:
+        ssmi = torch.zeros((4, C), device=raw.device, dtype=torch.float32)
+        ssmi[0].fill_(1.0)
+        ssmi[3].fill_(1.0)
+        if bias is not None:
+            ssmi[1].copy_(bias.detach())
+    out = ops.affine_act(raw, ssmi[0], ssmi[1], act, slope, residual)
+    L = _Layer()
+    L.a1, L.a2, L.raw, L.ssmi, L.act, L.slope, L.bn = a1, a2, raw, ssmi, act, slope, bn
+    L.w2d, L.groups, L.tap3_nodes, L.weight, L.bias, L.kind = w2d, groups, tap3_nodes, weight, bias, kind
+    L.k1 = (3 * a1.shape[1]) if tap3_nodes else a1.shape[1] // groups
+    L.k2 = a2.shape[1] // groups if a2 is not None else 0
+    L.has_residual = residual is not None
+    tape.append(L)
+    return out
+
+
+def _acc(grads: Dict, p, g: torch.Tensor) -> None:
+    if p is None or not p.requires_grad:
+        return
+    g = g.reshape(p.shape)
+    if p in grads:
+        ops.add_inplace(grads[p], g.contiguous())
+    else:
+        grads[p] = g.contiguous()
+
+
+def _weight_grad_to_param(L: _Layer, dw2d: torch.Tensor) -> torch.Tensor:
+    """(n, k) GEMM-operand gradient -> the reference parameter's layout."""
+    w = L.weight
+    if L.kind == "mr":            # columns were regrouped [even | odd] per group
+        half = dw2d.shape[1] // 2
+        out = torch.empty_like(dw2d)
+        out[:, 0::2] = dw2d[:, :half]
+        out[:, 1::2] = dw2d[:, half:]
+        return out.reshape(w.shape)
+    if L.kind == "tap3":          # (Cout, 3*Cin) -> centre column of the (Cout, Cin, 3, 3) kernel
+        cout, cin = w.shape[0], w.shape[1]
+        g = torch.zeros_like(w)
+        g[:, :, :, 1] = dw2d.view(cout, 3, cin).permute(0, 2, 1)
+        return g
+    return dw2d.reshape(w.shape)
+
+
+def layer_bwd(L: _Layer, dout: torch.Tensor, grads: Dict, need_input: bool = True,
+              add_to: Optional[torch.Tensor] = None):
+    """Returns (da1, da2).  The shortcut gradient of a residual layer is `dout` itself (caller's)."""
+    bn = L.bn is not None
+    draw, sums = ops.bn_act_bwd(dout, L.raw, L.ssmi, L.act, L.slope, bn)
+    if bn:
+        dg, db = ops.bn_param_grad(sums, True, True)
+        _acc(grads, L.bn.weight, dg)
+        _acc(grads, L.bn.bias, db)
+        # a conv bias in front of a train-mode BatchNorm has exactly zero gradient
+        if L.bias is not None and L.bias.requires_grad and L.bias not in grads:
+            grads[L.bias] = torch.zeros_like(L.bias)
+    elif L.bias is not None:
+        _, db = ops.bn_param_grad(sums, False, True)
+        _acc(grads, L.bias, db)
+    if L.weight.requires_grad:
+        dw = ops.gemm_wgrad(draw, L.a1, L.a2, L.w2d.shape[0], L.groups, L.tap3_nodes)
+        _acc(grads, L.weight, _weight_grad_to_param(L, dw))
+    if not need_input:
+        return None, None
+    n = L.w2d.shape[0] // L.groups
+    if L.tap3_nodes:
+        cin = L.k1 // 3
+        wT = L.w2d.t().contiguous()                                   # (3*Cin, Cout)
+        dA = ops.gemm(draw, wT, w_split=_w_split(wT, 1, 1))
+        return ops.tap3_bwd_input(dA, L.tap3_nodes, cin), None
+    wg = L.w2d.view(L.groups, n, L.k1 + L.k2)
+    wT1 = wg[:, :, :L.k1].transpose(1, 2).reshape(L.groups * L.k1, n).contiguous()
+    da1 = ops.gemm(draw, wT1, residual=add_to, groups=L.groups, w_split=_w_split(wT1, L.groups, 1))
+    da2 = None
+    if L.k2:
+        wT2 = wg[:, :, L.k1:].transpose(1, 2).reshape(L.groups * L.k2, n).contiguous()
+        da2 = ops.gemm(draw, wT2, groups=L.groups, w_split=_w_split(wT2, L.groups, 1))
+    return da1, da2
+
+
+# ------------------------------------------------------------------------------------------
+# GraphEncoder
+# ------------------------------------------------------------------------------------------
+def _conv2d_w(conv: nn.Conv2d) -> torch.Tensor:
+    return conv.weight.detach().reshape(conv.weight.shape[0], -1)
+
+
+class _EncTape:
+    __slots__ = ("layers", "blocks", "B", "N_out", "mean")
+
+
+def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int):
+    """Train-mode forward from node-major (B*N, C_in) features.  Returns (emb, nodes, tape)."""
+    from .encoder.graph_encoder import Downsample
+    tape = _EncTape()
+    tape.layers, tape.blocks, tape.B = [], [], B
+    Ls = tape.layers
+    stem = enc.stem
+    h = layer_fwd(Ls, x_nodes, stem[0].weight, _conv2d_w(stem[0]), "dense", None, stem[1], "leakyrelu",
+                  stem[2].negative_slope)
+    tape.blocks.append(("stem", 1))
+    for entry in enc.backbone:
+        if isinstance(entry, Downsample):
+            conv, bn = entry.conv[0], entry.conv[1]
+            h = layer_fwd(Ls, h, conv.weight, tap3_weight(conv.weight), "tap3", conv.bias, bn,
+                          tap3_nodes=N // 2)
+            N //= 2
+            tape.blocks.append(("down", 1))
+            continue
+        g, f = entry[0], entry[1]
+        y = layer_fwd(Ls, h, g.fc1[0].weight, _conv2d_w(g.fc1[0]), "dense", g.fc1[0].bias, g.fc1[1])
+        gc = g.graph_conv
+        idx = gc.dilated_knn_graph.knn_nodes(y, B, N)
+        m, arg = ops.mr_aggregate(y, idx, B, N, want_arg=True)
+        mr = gc.gconv.nn
+        conv, bnm = mr[0], mr[1]
+        w = _conv2d_w(conv)
+        w_mr = torch.cat([w[:, 0::2], w[:, 1::2]], dim=1)
+        act = mr[2] if len(mr) > 2 else None
+        u = layer_fwd(Ls, y, conv.weight, w_mr, "mr", conv.bias, bnm, act.name if act else None,
+                      act.neg_slope if act else 0.0, a2=m, groups=mr.GROUPS)
+        h2 = layer_fwd(Ls, u, g.fc2[0].weight, _conv2d_w(g.fc2[0]), "dense", g.fc2[0].bias, g.fc2[1], residual=h)
+        t = layer_fwd(Ls, h2, f.fc1[0].weight, _conv2d_w(f.fc1[0]), "dense", None, f.fc1[1], f.act.name,
+                      f.act.neg_slope)
+        h = layer_fwd(Ls, t, f.fc2[0].weight, _conv2d_w(f.fc2[0]), "dense", None, f.fc2[1], residual=h2)
+        tape.blocks.append(("block", (idx, arg, N)))
+    mean = ops.node_mean(h, B, N)
+    emb = layer_fwd(Ls, mean, enc.proj.weight, _conv2d_w(enc.proj), "dense", enc.proj.bias, None)
+    tape.N_out = N
+    return emb, h, tape
+
+
+def encoder_train_bwd(tape: _EncTape, demb: torch.Tensor, grads: Dict, dnodes: Optional[torch.Tensor] = None,
+                      need_input: bool = False):
+    """Backward of encoder_train_fwd.  Returns d(x_nodes) if need_input."""
+    Ls = list(tape.layers)
+    B = tape.B
+    dmean, _ = layer_bwd(Ls.pop(), demb.contiguous(), grads)
+    dh = ops.node_mean_bwd(dmean, B, tape.N_out)
+    if dnodes is not None:
+        ops.add_inplace(dh, dnodes.contiguous())
+    for kind, info in reversed(tape.blocks):
+        if kind == "block":
+            idx, arg, N = info
+            L_f2, L_f1, L_fc2, L_mr, L_fc1 = Ls.pop(), Ls.pop(), Ls.pop(), Ls.pop(), Ls.pop()
+            dt, _ = layer_bwd(L_f2, dh, grads)                       # shortcut grad to h2: dh
+            dh2, _ = layer_bwd(L_f1, dt, grads, add_to=dh)           # dh2 = dA + dh
+            du, _ = layer_bwd(L_fc2, dh2, grads)                     # shortcut grad to h: dh2
+            dy, dm = layer_bwd(L_mr, du, grads)
+            ops.mr_aggregate_bwd(dm, idx, arg, B, N, dy)             # dy += scatter(dm)
+            dh, _ = layer_bwd(L_fc1, dy, grads, add_to=dh2)
+        elif kind == "down":
+            dh, _ = layer_bwd(Ls.pop(), dh, grads)
+        else:                                                        # stem
+            dx, _ = layer_bwd(Ls.pop(), dh, grads, need_input=need_input)
+            return dx
+    return None
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc, x, return_nodes, *params):
+        B, _, N = x.shape
+        emb, nodes, tape = encoder_train_fwd(enc, ops.nchw_to_nodes(x.detach()), B, N)
+        ctx.tape, ctx.params, ctx.need_x = tape, params, x.requires_grad
+        ctx.B, ctx.N = B, N
+        if return_nodes:
+            return emb, ops.nodes_to_nchw(nodes, B, tape.N_out)
+        return emb
+
+    @staticmethod
+    def backward(ctx, demb, dnodes=None):
+        grads: Dict = {}
+        dn = None
+        if dnodes is not None:
+            dn = ops.nchw_to_nodes(dnodes.contiguous())
+        dx = encoder_train_bwd(ctx.tape, demb, grads, dn, ctx.need_x)
+        ctx.tape = None
+        gx = ops.nodes_to_nchw(dx, ctx.B, ctx.N) if (ctx.need_x and dx is not None) else None
+        return (None, gx, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+def encoder_forward_train(enc, x: torch.Tensor, return_pre_proj: bool = False):
+    params = tuple(enc.parameters())
+    out = _EncoderFn.apply(enc, x, return_pre_proj, *params)
+    if return_pre_proj:
+        emb, nodes = out
+        return nodes, emb
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# SimCLR view: peak extractor -> encoder -> projector -> normalise
+# ------------------------------------------------------------------------------------------
+class _ViewCtx:
+    __slots__ = ("tape", "ptape", "z2", "spec")
+
+
+def view_fwd(model, spec: torch.Tensor):
+    """One SimCLR view in train mode -> (h, z, ctx)."""
+    pe = model.peak_extractor.convs[0]
+    spec = spec.detach().contiguous()
+    B = spec.shape[0]
+    nodes = ops.peak_extract(spec, pe.weight.detach(), pe.bias.detach())
+    N = nodes.shape[0] // B
+    h, _, tape = encoder_train_fwd(model.encoder, nodes, B, N)
+    ptape: List[_Layer] = []
+    l0, l2 = model.projector[0], model.projector[2]
+    z1 = layer_fwd(ptape, h, l0.weight, l0.weight.detach(), "dense", l0.bias, None, "elu")
+    z2 = layer_fwd(ptape, z1, l2.weight, l2.weight.detach(), "dense", l2.bias, None)
+    z = ops.l2_normalize_rows(z2, 1e-10)
+    c = _ViewCtx()
+    c.tape, c.ptape, c.z2, c.spec = tape, ptape, z2, spec
+    return h, z, c
+
+
+def view_bwd(model, c: _ViewCtx, dh: Optional[torch.Tensor], dz: torch.Tensor, grads: Dict) -> None:
+    dz2 = ops.l2_normalize_rows_bwd(c.z2, dz.contiguous(), 1e-10)
+    dz1, _ = layer_bwd(c.ptape[1], dz2, grads)
+    dhh, _ = layer_bwd(c.ptape[0], dz1, grads, add_to=dh.contiguous() if dh is not None else None)
+    dnodes = encoder_train_bwd(c.tape, dhh, grads, None, need_input=True)
+    pe = model.peak_extractor.convs[0]
+    if pe.weight.requires_grad:
+        dw, db = ops.peak_extract_bwd(c.spec, pe.weight.detach(), pe.bias.detach(), dnodes)
+        _acc(grads, pe.weight, dw)
+        _acc(grads, pe.bias, db)
+
+
+class _ViewFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, spec, *params):
+        h, z, c = view_fwd(model, spec)
+        ctx.c, ctx.params, ctx.model = c, params, model
+        return h, z
+
+    @staticmethod
+    def backward(ctx, dh, dz):
+        grads: Dict = {}
+        view_bwd(ctx.model, ctx.c, dh, dz, grads)
+        ctx.c = None
+        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+def simclr_view_train(model, x: torch.Tensor):
+    from .encoder.graph_encoder import GraphEncoder
+    if not isinstance(model.encoder, GraphEncoder):
+        raise NotImplementedError("the train path is implemented for GraphEncoder")
+    params = tuple(model.parameters())
+    return _ViewFn.apply(model, x, *params)
+
+
+class PeakExtractFn(torch.autograd.Function):
+    """Stand-alone peak extractor with weight gradients (module-level use)."""
+
+    @staticmethod
+    def forward(ctx, spec, w, b):
+        ctx.save_for_backward(spec, w, b)
+        return ops.peak_extract(spec.detach().contiguous(), w.detach(), b.detach())
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, w, b = ctx.saved_tensors
+        dw, db = ops.peak_extract_bwd(spec.contiguous(), w.detach(), b.detach(), dout.contiguous())
+        return None, dw, db

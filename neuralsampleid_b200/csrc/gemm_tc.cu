@@ -10,13 +10,14 @@
 //                grafp_split_tf32); A is split in shared memory by the transform warps between
 //                the TMA arrival and the MMA issue, so activations cross HBM once, as plain fp32.
 //
-// One persistent CTA per SM walks the tile list (m fastest, so concurrently running CTAs share
-// the same weight tile in L2).  Warp roles (320 threads):
+// One persistent CTA per SM walks the tile list with n fastest: the CTAs running at the same time
+// share the same 128 rows of A (read from HBM once, L2 hits for the other column tiles) while the
+// weights, a few MB, stay L2-resident.  Warp roles (448 threads):
 //   warp 0      TMA producer (A from one of two sources or the 3-tap Downsample view, W hi/lo)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5   transform: in-place tf32 hi / lo split of the A stage
-//   warps 6-9   epilogue: TMEM -> registers -> scale/shift/activation/residual -> 128B-swizzled
+//   warps 2-5   epilogue: TMEM -> registers -> scale/shift/activation/residual -> 128B-swizzled
 //               staging tile -> TMA store (coalesced, clipped at the matrix edge)
+//   warps 6-13  transform: tf32 hi / lo split of the A stage (hi = top 19 bits, lo = v - hi exact)
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.  Pipelines: full[s] (TMA -> transform), xf[s] (transform -> MMA),
 // empty[s] (MMA commit -> TMA), tmem_full[b] (MMA commit -> epilogue), tmem_empty[b].
@@ -26,7 +27,8 @@
 namespace grafp {
 
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;
+constexpr int TC_XF_THREADS = 256;
 constexpr int TC_STORE_BYTES = TC_BM * 32 * 4;   // one 128 x 32 fp32 staging tile
 
 struct TcParams {
@@ -92,7 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
 
   const int nkb = (p.k1 + p.k2) / TC_BK;
-  const int tiles_m = (int)((p.m + TC_BM - 1) / TC_BM);
+  const int64_t tiles_m = (p.m + TC_BM - 1) / TC_BM;
   const int tiles_n = p.n / p.bn;
   const int64_t total_tiles = (int64_t)tiles_m * tiles_n * p.groups;
 
@@ -103,7 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmY);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&xf_bar[s], 128);
+      mbar_init(&xf_bar[s], TC_XF_THREADS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -123,9 +125,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (lane == 0) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = (int)(tile % tiles_m);
-        const int rest = (int)(tile / tiles_m);
-        const int nt = rest % tiles_n, g = rest / tiles_n;
+        const int nt = (int)(tile % tiles_n);
+        const int64_t rest = tile / tiles_n;
+        const int g = (int)(rest % p.groups), mt = (int)(rest / p.groups);
         const int m0 = mt * TC_BM, n0 = nt * p.bn;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
@@ -189,10 +191,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         umma_commit(&tmem_full_bar[buf]);       // accumulator complete
       }
     }
-  } else if (warp < 6) {
-    // ===== transform: tf32 hi / lo split of the A stage (warps 2..5) =====
+  } else if (warp >= 6) {
+    // ===== transform (warps 6..13, 256 threads): split the A stage into tf32 hi / lo =====
+    // hi = v with the 13 low mantissa bits cleared (exactly representable in tf32), lo = v - hi
+    // (exact in fp32, |lo| < 2^-10 |v|; the tensor core reads its top 19 bits)
     if (kPasses == 3) {
-      const int t = threadIdx.x - 64;
+      constexpr int PER = TC_A_BYTES / 16 / TC_XF_THREADS;
+      const int t = threadIdx.x - 192;
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -201,15 +206,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           mbar_wait(&full_bar[s], ph);
           float4* hi = reinterpret_cast<float4*>(a_hi(s));
           float4* lo = reinterpret_cast<float4*>(a_lo(s));
+          float4 v[PER];
 #pragma unroll
-          for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
-            const float4 v = hi[t + 128 * i];
+          for (int i = 0; i < PER; ++i) v[i] = hi[t + TC_XF_THREADS * i];
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
             float4 h, l;
-            h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-            l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y);
-            l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-            hi[t + 128 * i] = h;
-            lo[t + 128 * i] = l;
+            h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+            l.x = v[i].x - h.x; l.y = v[i].y - h.y; l.z = v[i].z - h.z; l.w = v[i].w - h.w;
+            hi[t + TC_XF_THREADS * i] = h;
+            lo[t + TC_XF_THREADS * i] = l;
           }
           fence_proxy_async_smem();             // generic-proxy writes -> visible to the MMA (async proxy)
           mbar_arrive(&xf_bar[s]);
@@ -217,16 +226,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else {
-    // ===== epilogue (warps 6..9, 128 threads) =====
-    const int et = threadIdx.x - 192;            // 0..127
+    // ===== epilogue (warps 2..5, 128 threads) =====
+    const int et = threadIdx.x - 64;             // 0..127
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;              // row inside the tile
     const bool store_thread = (et == 0);
     uint32_t ti = 0, cc = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      const int mt = (int)(tile % tiles_m);
-      const int rest = (int)(tile / tiles_m);
-      const int nt = rest % tiles_n, g = rest / tiles_n;
+      const int nt = (int)(tile % tiles_n);
+      const int64_t rest = tile / tiles_n;
+      const int g = (int)(rest % p.groups), mt = (int)(rest / p.groups);
       const int m0 = mt * TC_BM, n0 = nt * p.bn;
       const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
       mbar_wait(&tmem_full_bar[buf], tph);

@@ -31,31 +31,38 @@ struct KnnTcParams {
   uint32_t tmem_cols;
 };
 
-__global__ void knn_rownorm_kernel(const float* __restrict__ x, int64_t M, int C, int normalize,
-                                   float* __restrict__ rinv, float* __restrict__ sq) {
-  const int warps = blockDim.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5);
-  if (row >= M) return;
+// lanes_per_row = min(32, C/4) lanes cooperate on one node, 32/lanes_per_row nodes per warp
+__global__ void __launch_bounds__(256)
+knn_rownorm_kernel(const float* __restrict__ x, int64_t M, int C, int normalize, int lanes_per_row,
+                   float* __restrict__ rinv, float* __restrict__ sq) {
+  const int rows_per_warp = 32 / lanes_per_row;
   const int lane = threadIdx.x & 31;
-  const float* xr = x + row * C;
+  const int sub = lane / lanes_per_row, sl = lane % lanes_per_row;
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t row = warp_id * rows_per_warp + sub;
+  const bool ok = row < M;
+  const float* xr = x + (ok ? row : 0) * C;
   float s = 0.0f;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + c);
-    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
-  }
-  s = warp_sum(s);
+  if (ok)
+    for (int c = sl * 4; c < C; c += lanes_per_row * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+    }
+  for (int o = lanes_per_row >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float ri = 1.0f, q = s;
   if (normalize) {
     ri = __frcp_rn(fmaxf(sqrtf(s), 1e-12f));
     float t = 0.0f;
-    for (int c = lane * 4; c < C; c += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      const float a0 = v.x * ri, a1 = v.y * ri, a2 = v.z * ri, a3 = v.w * ri;
-      t = fmaf(a0, a0, t); t = fmaf(a1, a1, t); t = fmaf(a2, a2, t); t = fmaf(a3, a3, t);
-    }
-    q = warp_sum(t);
+    if (ok)
+      for (int c = sl * 4; c < C; c += lanes_per_row * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        const float a0 = v.x * ri, a1 = v.y * ri, a2 = v.z * ri, a3 = v.w * ri;
+        t = fmaf(a0, a0, t); t = fmaf(a1, a1, t); t = fmaf(a2, a2, t); t = fmaf(a3, a3, t);
+      }
+    for (int o = lanes_per_row >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    q = t;
   }
-  if (lane == 0) { rinv[row] = ri; sq[row] = q; }
+  if (ok && sl == 0) { rinv[row] = ri; sq[row] = q; }
 }
 
 template <int KMAX>
@@ -150,30 +157,41 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
     }
   } else if (warp < 10) {
     // ===== transform (256 threads): scale rows by rinv (F.normalize), split tf32 hi / lo =====
+    // hi = top 19 bits of v, lo = v - hi (exact); each thread owns the same rows in every k-block
     const int t = threadIdx.x - 64;
-    const int b_vec = (int)(b_bytes / 16);
+    const int per = (int)(b_bytes / 16) / 256;          // float4 per thread per stage: 4 or 8
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int64_t c0 = col_start(tile * TC_BM);
+      float ri[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t node = c0 + (t >> 3) + 32 * i;
+        ri[i] = (i < per && node < p.M) ? __ldg(p.rinv + node) : 0.0f;
+      }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1u;
         mbar_wait(&full_bar[s], ph);
         float4* bh = reinterpret_cast<float4*>(b_hi(s));
         float4* bl = reinterpret_cast<float4*>(b_lo(s));
-        for (int q = t; q < b_vec; q += 256) {
-          const int64_t node = c0 + (q >> 3);
-          const float ri = node < p.M ? __ldg(p.rinv + node) : 0.0f;
-          float4* hp = bh + q;
-          float4* lp = bl + q;
-          float4 v = *hp;
-          v.x *= ri; v.y *= ri; v.z *= ri; v.w *= ri;
-          float4 h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y);
-          l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-          *hp = h;
-          *lp = l;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < per) v[i] = bh[t + 256 * i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < per) {
+            const float x0 = v[i].x * ri[i], x1 = v[i].y * ri[i], x2 = v[i].z * ri[i], x3 = v[i].w * ri[i];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u);
+            l.x = x0 - h.x; l.y = x1 - h.y; l.z = x2 - h.z; l.w = x3 - h.w;
+            bh[t + 256 * i] = h;
+            bl[t + 256 * i] = l;
+          }
         }
         fence_proxy_async_smem();
         mbar_arrive(&xf_bar[s]);
@@ -189,8 +207,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
       const int64_t grow = m0 + r;
       const bool row_ok = grow < p.M;
-      const int64_t gs = row_ok ? (grow / p.N) * p.N : 0;      // first node of this row's graph
+      const int64_t gs = row_ok ? (grow / p.N) * p.N : c0;     // first node of this row's graph
+      const int lo_col = (int)(gs - c0);                       // its first column inside the tile
+      const unsigned ncols = row_ok ? (unsigned)p.N : 0u;      // columns [lo_col, lo_col + N) are its graph
       const float sqi = row_ok ? __ldg(p.sq + grow) : 0.0f;
+      const float4* sqv = reinterpret_cast<const float4*>(p.sq + c0);   // 16-byte aligned: c0 % 128 == 0
       float bd[KMAX];
       int bj[KMAX];
 #pragma unroll
@@ -201,6 +222,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       for (int c = 0; c < p.bn; c += 16) {
         float v[16];
         tmem_ld16_nowait(tacc + (uint32_t)c, v);
+        float sj[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                            // (workspace is padded: no bounds issue)
+          const float4 s4 = __ldg(sqv + (c >> 2) + q);
+          sj[4 * q] = s4.x; sj[4 * q + 1] = s4.y; sj[4 * q + 2] = s4.z; sj[4 * q + 3] = s4.w;
+        }
         tmem_ld_wait();
         if (c + 16 >= p.bn) {
           tc_fence_before();
@@ -208,19 +235,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
         }
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          const int64_t gcol = c0 + c + q;
-          const bool ok = row_ok && gcol < p.M && gcol >= gs && gcol < gs + p.N;
-          if (ok) {
-            const float dv = __fadd_rn(__fadd_rn(sqi, -2.0f * v[q]), __ldg(p.sq + gcol));
-            if (dv < bd[KMAX - 1]) {
-              bd[KMAX - 1] = dv;
-              bj[KMAX - 1] = (int)(gcol - gs);
+          const float dv = __fadd_rn(__fadd_rn(sqi, -2.0f * v[q]), sj[q]);
+          const int jl = c + q - lo_col;
+          if ((unsigned)jl < ncols && dv < bd[KMAX - 1]) {
+            bd[KMAX - 1] = dv;
+            bj[KMAX - 1] = jl;
 #pragma unroll
-              for (int t = KMAX - 1; t > 0; --t) {
-                if (bd[t] < bd[t - 1]) {
-                  const float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td;
-                  const int tj = bj[t]; bj[t] = bj[t - 1]; bj[t - 1] = tj;
-                }
+            for (int t = KMAX - 1; t > 0; --t) {
+              if (bd[t] < bd[t - 1]) {
+                const float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td;
+                const int tj = bj[t]; bj[t] = bj[t - 1]; bj[t - 1] = tj;
               }
             }
           }
@@ -254,7 +278,8 @@ int knn_tc_supported(int B, int N, int C, int kk) {
   return N >= 16 && TC_BM % N == 0;
 }
 
-size_t knn_tc_workspace_bytes(int B, int N) { return (size_t)B * N * 2 * sizeof(float); }
+// rinv[M] | pad | sq[M] | pad : the pads let the epilogue read sq in whole float4 groups
+size_t knn_tc_workspace_bytes(int B, int N) { return ((size_t)B * N + 128) * 2 * sizeof(float); }
 
 template <int KMAX>
 static int knn_tc_launch_t(const CUtensorMap& mc, const KnnTcParams& p, size_t smem, int grid,
@@ -268,8 +293,12 @@ int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int
                   int32_t* idx, float* dist, float* workspace, cudaStream_t st) {
   const int64_t M = (int64_t)B * N;
   float* rinv = workspace;
-  float* sq = workspace + M;
-  knn_rownorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, M, C, normalize, rinv, sq);
+  float* sq = workspace + M + 128;
+  int lpr = 32;
+  while (lpr > 1 && lpr * 4 > C) lpr >>= 1;               // power of two, <= C/4
+  const int rows_per_block = 8 * (32 / lpr);
+  knn_rownorm_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(
+      x, M, C, normalize, lpr, rinv, sq);
   if (int rc = check_launch("knn_rownorm")) return rc;
   KnnTcParams p;
   p.N = N; p.C = C; p.kk = kk; p.d = d; p.k = k; p.M = M;

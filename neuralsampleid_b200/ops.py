@@ -252,3 +252,153 @@ def ntxent_bwd(z: torch.Tensor, lse_all: torch.Tensor, tau: float, grad_loss: to
         check(_lib.load().grafp_ntxent_bwd(_ptr(z), _ptr(lse_all), n, D, tau, row0, rows,
                                            _ptr(grad_loss), _ptr(dz), _stream(z)), "ntxent_bwd")
     return dz
+
+
+# ------------------------------------------------------------------------------------------
+# train-step kernels (csrc/train.cu)
+# ------------------------------------------------------------------------------------------
+def col_stats(x: torch.Tensor) -> torch.Tensor:
+    """(M, C) -> fp64 (2, C): column sums and sums of squares."""
+    x = _chk(x, name="x")
+    M, Cc = x.shape
+    out = torch.zeros((2, Cc), device=x.device, dtype=torch.float64)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_col_stats(_ptr(x), M, Cc, x.stride(0), _ptr(out[0]), _ptr(out[1]), _stream(x)),
+              "col_stats")
+    return out
+
+
+def bn_finalize(stats: torch.Tensor, M: int, gamma, beta, conv_bias, eps: float, momentum: float,
+                running_mean, running_var):
+    """-> fp32 (4, C): scale, shift, mean, invstd; updates the running statistics in place."""
+    Cc = stats.shape[1]
+    out = torch.empty((4, Cc), device=stats.device, dtype=torch.float32)
+    with torch.cuda.device(stats.device):
+        check(_lib.load().grafp_bn_finalize(_ptr(stats[0]), _ptr(stats[1]), M, Cc, _ptr(gamma), _ptr(beta),
+                                            _ptr(conv_bias), eps, momentum, _ptr(running_mean),
+                                            _ptr(running_var), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                            _ptr(out[3]), _stream(stats)), "bn_finalize")
+    return out
+
+
+def affine_act(x: torch.Tensor, scale, shift, act=None, act_param: float = 0.0, residual=None) -> torch.Tensor:
+    x = _chk(x, name="x")
+    M, Cc = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_affine_act(_ptr(x), M, Cc, x.stride(0), _ptr(scale), _ptr(shift), act_code(act),
+                                           act_param, _ptr(residual), residual.stride(0) if residual is not None else 0,
+                                           _ptr(out), out.stride(0), _stream(x)), "affine_act")
+    return out
+
+
+def bn_act_bwd(dout: torch.Tensor, raw: torch.Tensor, ssmi: torch.Tensor, act, act_param: float, bn: bool):
+    """Backward of (BatchNorm | bias) + activation.  ssmi: (4, C) scale/shift/mean/invstd.
+    Returns (draw (M, C), sums fp64 (2, C) = [sum dz, sum dz*xhat])."""
+    dout = _chk(dout, name="dout")
+    raw = _chk(raw, name="raw")
+    M, Cc = raw.shape
+    sums = torch.zeros((2, Cc), device=raw.device, dtype=torch.float64)
+    draw = torch.empty_like(raw)
+    a = act_code(act)
+    lib = _lib.load()
+    with torch.cuda.device(raw.device):
+        check(lib.grafp_bn_bwd_reduce(_ptr(dout), dout.stride(0), _ptr(raw), raw.stride(0), M, Cc, _ptr(ssmi[0]),
+                                      _ptr(ssmi[1]), _ptr(ssmi[2]), _ptr(ssmi[3]), a, act_param, _ptr(sums[0]),
+                                      _ptr(sums[1]), _stream(raw)), "bn_bwd_reduce")
+        check(lib.grafp_bn_bwd_apply(_ptr(dout), dout.stride(0), _ptr(raw), raw.stride(0), M, Cc, _ptr(ssmi[0]),
+                                     _ptr(ssmi[1]), _ptr(ssmi[2]), _ptr(ssmi[3]), a, act_param, int(bn),
+                                     _ptr(sums[0]), _ptr(sums[1]), _ptr(draw), draw.stride(0), _stream(raw)),
+              "bn_bwd_apply")
+    return draw, sums
+
+
+def bn_param_grad(sums: torch.Tensor, want_gamma: bool, want_beta: bool):
+    Cc = sums.shape[1]
+    dg = torch.zeros((Cc,), device=sums.device, dtype=torch.float32) if want_gamma else None
+    db = torch.zeros((Cc,), device=sums.device, dtype=torch.float32) if want_beta else None
+    with torch.cuda.device(sums.device):
+        check(_lib.load().grafp_bn_param_grad(_ptr(sums[0]), _ptr(sums[1]), Cc, _ptr(dg), _ptr(db), _stream(sums)),
+              "bn_param_grad")
+    return dg, db
+
+
+def gemm_wgrad(dy: torch.Tensor, a1: torch.Tensor, a2, n_total: int, groups: int = 1,
+               tap3_nodes: int = 0) -> torch.Tensor:
+    """dw (groups*n, k1+k2) = sum_m dy[m]^T A[m] (per group)."""
+    dy = _chk(dy, name="dy")
+    a1 = _chk(a1, name="a1")
+    n = n_total // groups
+    if tap3_nodes > 0:
+        k1, k2, M = 3 * a1.shape[1], 0, a1.shape[0] // 2
+    else:
+        k1, k2, M = a1.shape[1] // groups, 0, a1.shape[0]
+        if a2 is not None:
+            a2 = _chk(a2, name="a2")
+            k2 = a2.shape[1] // groups
+    dw = torch.zeros((n_total, k1 + k2), device=dy.device, dtype=torch.float32)
+    with torch.cuda.device(dy.device):
+        check(_lib.load().grafp_gemm_wgrad(_ptr(dy), dy.stride(0), _ptr(a1), a1.stride(0), k1, _ptr(a2),
+                                           a2.stride(0) if a2 is not None else 0, k2, M, n, groups, tap3_nodes,
+                                           _ptr(dw), dw.stride(0), _stream(dy)), "gemm_wgrad")
+    return dw
+
+
+def tap3_bwd_input(dA: torch.Tensor, rows_per_graph: int, cin: int) -> torch.Tensor:
+    dA = _chk(dA, name="dA")
+    rows = dA.shape[0]
+    dX = torch.empty((2 * rows, cin), device=dA.device, dtype=torch.float32)
+    with torch.cuda.device(dA.device):
+        check(_lib.load().grafp_tap3_bwd_input(_ptr(dA), rows, rows_per_graph, cin, _ptr(dX), _stream(dA)),
+              "tap3_bwd_input")
+    return dX
+
+
+def node_mean_bwd(dmean: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    dmean = _chk(dmean, name="dmean")
+    Cc = dmean.shape[1]
+    dx = torch.empty((B * N, Cc), device=dmean.device, dtype=torch.float32)
+    with torch.cuda.device(dmean.device):
+        check(_lib.load().grafp_node_mean_bwd(_ptr(dmean), B, N, Cc, _ptr(dx), _stream(dmean)), "node_mean_bwd")
+    return dx
+
+
+def l2_normalize_rows_bwd(v: torch.Tensor, dz: torch.Tensor, eps: float) -> torch.Tensor:
+    v = _chk(v, name="v")
+    dz = _chk(dz, name="dz")
+    dv = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        check(_lib.load().grafp_l2_normalize_rows_bwd(_ptr(v), _ptr(dz), v.shape[0], v.shape[1], eps, _ptr(dv),
+                                                      _stream(v)), "l2_normalize_rows_bwd")
+    return dv
+
+
+def peak_extract_bwd(spec: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, dout: torch.Tensor):
+    spec = _chk(spec, name="spec")
+    dout = _chk(dout, name="dout")
+    B, n_mels, n_frames = spec.shape
+    F, _, pb, pf = w.shape
+    dw = torch.zeros_like(w, dtype=torch.float32).contiguous()
+    db = torch.zeros((F,), device=w.device, dtype=torch.float32)
+    with torch.cuda.device(spec.device):
+        check(_lib.load().grafp_peak_extract_bwd(_ptr(spec), _ptr(_chk(w, name="w")), _ptr(_chk(bias, name="bias")),
+                                                 _ptr(dout), B, n_mels, n_frames, F, pb, pf, _ptr(dw), _ptr(db),
+                                                 _stream(spec)), "peak_extract_bwd")
+    return dw, db
+
+
+def sq_norm(g: torch.Tensor, out: torch.Tensor) -> None:
+    with torch.cuda.device(g.device):
+        check(_lib.load().grafp_sq_norm(_ptr(g), g.numel(), _ptr(out), _stream(g)), "sq_norm")
+
+
+def adam_clip_step(p, g, m, v, lr, beta1, beta2, eps, step, max_norm, sq) -> None:
+    with torch.cuda.device(p.device):
+        check(_lib.load().grafp_adam_clip_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps,
+                                               step, max_norm, _ptr(sq), _stream(p)), "adam_clip_step")
+
+
+def add_inplace(y: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    with torch.cuda.device(y.device):
+        check(_lib.load().grafp_add_inplace(_ptr(y), _ptr(x), y.numel(), _stream(y)), "add_inplace")
+    return y

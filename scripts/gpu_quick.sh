@@ -8,3 +8,4 @@ echo "== bench auto"; timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu
 echo "== bench BN=256"; GRAFP_TC_BN=256 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_bn256.json 2> $OUT/${TAG}_bench_bn256.err; echo "rc=$?"; cut -c1-200 $OUT/${TAG}_bench_bn256.json
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 40 -c 4 -o $OUT/${TAG}_prof_gemm -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_gemm.log 2>&1; echo "rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn_tc_kernel -s 2 -c 2 -o $OUT/${TAG}_prof_knn -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_knn.log 2>&1; echo "rc=$?"
+echo "== train"; timeout 1500 python -m pytest tests/test_gpu_train.py -q -m gpu -p no:cacheprovider -x > $OUT/${TAG}_t_train.log 2>&1; echo "rc=$?"; tail -25 $OUT/${TAG}_t_train.log
