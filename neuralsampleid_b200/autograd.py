@@ -140,8 +140,9 @@ class _EncTape:
     __slots__ = ("layers", "blocks", "B", "N_out", "mean")
 
 
-def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int):
-    """Train-mode forward from node-major (B*N, C_in) features.  Returns (emb, nodes, tape)."""
+def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int, forced_idx=None):
+    """Train-mode forward from node-major (B*N, C_in) features.  Returns (emb, nodes, tape).
+    ``forced_idx``: optional per-block int32 (B, N, k) neighbour lists (parity-test hook)."""
     from .encoder.graph_encoder import Downsample
     tape = _EncTape()
     tape.layers, tape.blocks, tape.B = [], [], B
@@ -161,7 +162,10 @@ def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int):
         g, f = entry[0], entry[1]
         y = layer_fwd(Ls, h, g.fc1[0].weight, _conv2d_w(g.fc1[0]), "dense", g.fc1[0].bias, g.fc1[1])
         gc = g.graph_conv
-        idx = gc.dilated_knn_graph.knn_nodes(y, B, N)
+        if forced_idx is not None:
+            idx = forced_idx[sum(1 for b in tape.blocks if b[0] == "block")]
+        else:
+            idx = gc.dilated_knn_graph.knn_nodes(y, B, N)
         m, arg = ops.mr_aggregate(y, idx, B, N, want_arg=True)
         mr = gc.gconv.nn
         conv, bnm = mr[0], mr[1]
@@ -247,14 +251,15 @@ class _ViewCtx:
     __slots__ = ("tape", "ptape", "z2", "spec")
 
 
-def view_fwd(model, spec: torch.Tensor):
-    """One SimCLR view in train mode -> (h, z, ctx)."""
+def view_fwd(model, spec: torch.Tensor, forced_idx=None):
+    """One SimCLR view in train mode -> (h, z, ctx).  ``forced_idx``: parity-test hook (per-block
+    neighbour lists to use instead of the computed graph)."""
     pe = model.peak_extractor.convs[0]
     spec = spec.detach().contiguous()
     B = spec.shape[0]
     nodes = ops.peak_extract(spec, pe.weight.detach(), pe.bias.detach())
     N = nodes.shape[0] // B
-    h, _, tape = encoder_train_fwd(model.encoder, nodes, B, N)
+    h, _, tape = encoder_train_fwd(model.encoder, nodes, B, N, forced_idx)
     ptape: List[_Layer] = []
     l0, l2 = model.projector[0], model.projector[2]
     z1 = layer_fwd(ptape, h, l0.weight, l0.weight.detach(), "dense", l0.bias, None, "elu")
@@ -279,8 +284,8 @@ def view_bwd(model, c: _ViewCtx, dh: Optional[torch.Tensor], dz: torch.Tensor, g
 
 class _ViewFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, spec, *params):
-        h, z, c = view_fwd(model, spec)
+    def forward(ctx, model, spec, forced_idx, *params):
+        h, z, c = view_fwd(model, spec, forced_idx)
         ctx.c, ctx.params, ctx.model = c, params, model
         return h, z
 
@@ -289,15 +294,15 @@ class _ViewFn(torch.autograd.Function):
         grads: Dict = {}
         view_bwd(ctx.model, ctx.c, dh, dz, grads)
         ctx.c = None
-        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
 
 
-def simclr_view_train(model, x: torch.Tensor):
+def simclr_view_train(model, x: torch.Tensor, forced_idx=None):
     from .encoder.graph_encoder import GraphEncoder
     if not isinstance(model.encoder, GraphEncoder):
         raise NotImplementedError("the train path is implemented for GraphEncoder")
     params = tuple(model.parameters())
-    return _ViewFn.apply(model, x, *params)
+    return _ViewFn.apply(model, x, forced_idx, *params)
 
 
 class PeakExtractFn(torch.autograd.Function):

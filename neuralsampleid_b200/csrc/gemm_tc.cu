@@ -67,7 +67,12 @@ __device__ __forceinline__ void epi_apply(float (&v)[32], const float* __restric
   }
 }
 
-template <int kPasses>
+// kCluster == 2: CTA pairs (thread-block cluster 2x1) work on two vertically adjacent 128-row tiles
+// of the same column tile; each CTA fetches HALF of the weight tile and TMA-multicasts it into both
+// CTAs' shared memory, halving the per-SM weight traffic out of L2 (the limiter of the 1-CTA form).
+// A stage may be refilled only when BOTH CTAs have consumed it: every MMA commit is multicast to
+// the pair's `empty` barriers (count 2).
+template <int kPasses, int kCluster>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -96,7 +101,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int nkb = (p.k1 + p.k2) / TC_BK;
   const int64_t tiles_m = (p.m + TC_BM - 1) / TC_BM;
   const int tiles_n = p.n / p.bn;
-  const int64_t total_tiles = (int64_t)tiles_m * tiles_n * p.groups;
+  // work units: (row-tile group of kCluster tiles) x column tile x group; a cluster walks units,
+  // CTA `crank` of the cluster takes row tile  unit_row * kCluster + crank
+  const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
+  const int64_t first_unit = blockIdx.x / kCluster, unit_step = gridDim.x / kCluster;
+  const int64_t total_tiles = ((tiles_m + kCluster - 1) / kCluster) * tiles_n * p.groups;   // units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -106,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&xf_bar[s], TC_XF_THREADS);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kCluster);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -116,7 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if (kCluster == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -124,11 +133,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
         const int nt = (int)(tile % tiles_n);
         const int64_t rest = tile / tiles_n;
-        const int g = (int)(rest % p.groups), mt = (int)(rest / p.groups);
-        const int m0 = mt * TC_BM, n0 = nt * p.bn;
+        const int g = (int)(rest % p.groups);
+        const int64_t mt = (rest / p.groups) * kCluster + crank;
+        const int m0 = (int)(mt * TC_BM), n0 = nt * p.bn;      // mt may be one past the last tile: all OOB
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
@@ -150,8 +160,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           } else {
             tma_load_2d(a_hi(s), &tmA2, g * p.k2 + (k - p.k1), m0, &full_bar[s]);
           }
-          tma_load_2d(b_hi(s), &tmW, k, g * p.n + n0, &full_bar[s]);
-          if (kPasses == 3) tma_load_2d(b_lo(s), &tmW, k, p.n_total + g * p.n + n0, &full_bar[s]);
+          if (kCluster == 2) {
+            // my half of the weight tile, multicast to both CTAs of the pair (tmW box = bn/2 rows)
+            const int half = p.bn / 2;
+            const uint32_t off = crank * (uint32_t)half * (TC_BK * 4);
+            tma_load_2d_mc(b_hi(s) + off, &tmW, k, g * p.n + n0 + (int)crank * half, &full_bar[s], 0x3);
+            if (kPasses == 3)
+              tma_load_2d_mc(b_lo(s) + off, &tmW, k, p.n_total + g * p.n + n0 + (int)crank * half,
+                             &full_bar[s], 0x3);
+          } else {
+            tma_load_2d(b_hi(s), &tmW, k, g * p.n + n0, &full_bar[s]);
+            if (kPasses == 3) tma_load_2d(b_lo(s), &tmW, k, p.n_total + g * p.n + n0, &full_bar[s]);
+          }
         }
       }
     }
@@ -160,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(TC_BM, p.bn);
       uint32_t it = 0, ti = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
         const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[buf], tph ^ 1u);          // epilogue drained this accumulator
         tc_fence_after();
@@ -186,7 +206,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               umma_tf32(tacc, dah + koff, dbh + koff, idesc, acc);
             }
           }
-          umma_commit(&empty_bar[s]);           // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in both CTAs of a pair)
+          if (kCluster == 2) umma_commit_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full_bar[buf]);       // accumulator complete
       }
@@ -199,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       constexpr int PER = TC_A_BYTES / 16 / TC_XF_THREADS;
       const int t = threadIdx.x - 192;
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
@@ -232,11 +253,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int r = quad * 32 + lane;              // row inside the tile
     const bool store_thread = (et == 0);
     uint32_t ti = 0, cc = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
       const int nt = (int)(tile % tiles_n);
       const int64_t rest = tile / tiles_n;
-      const int g = (int)(rest % p.groups), mt = (int)(rest / p.groups);
-      const int m0 = mt * TC_BM, n0 = nt * p.bn;
+      const int g = (int)(rest % p.groups);
+      const int64_t mt = (rest / p.groups) * kCluster + crank;
+      const int m0 = (int)(mt * TC_BM), n0 = nt * p.bn;
       const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
       mbar_wait(&tmem_full_bar[buf], tph);
       tc_fence_after();
@@ -281,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (store_thread) bulk_wait_group_all();
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCluster == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal my barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -339,7 +361,7 @@ static int pick_bn(int n) {
     forced = e ? atoi(e) : 0;
   }
   if (forced > 0 && forced <= 256 && forced % 32 == 0 && n % forced == 0) return forced;
-  for (int bn = 128; bn >= 32; bn -= 32)
+  for (int bn = 256; bn >= 32; bn -= 32)
     if (n % bn == 0) return bn;
   return 0;
 }
@@ -386,8 +408,12 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st) {
       mA2 = mA1;
     }
   }
+  const int64_t tiles_m = (a.m + TC_BM - 1) / TC_BM;
+  static int mc_env = -1;
+  if (mc_env < 0) { const char* e = getenv("GRAFP_TC_CLUSTER"); mc_env = e ? atoi(e) : 2; }
+  const int cluster = (mc_env == 2 && tiles_m >= 2 && bn % 64 == 0 && sm_count() % 2 == 0) ? 2 : 1;
   if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
-                              a.k1 + a.k2, a.ldw, bn))
+                              a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
     return rc;
   if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) return rc;
   p.k1 = a.k1; p.k2 = a.k2; p.n = a.n; p.bn = bn; p.n_total = n_total; p.groups = a.groups; p.m = a.m;
@@ -404,16 +430,27 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st) {
   p.stages = stages;
   (void)nkb;
   const size_t smem = stage_bytes * stages + 2 * TC_STORE_BYTES + 1024;
-  const int64_t tiles = ((a.m + TC_BM - 1) / TC_BM) * (a.n / bn) * a.groups;
-  int grid = sm_count();
-  if (tiles < grid) grid = (int)tiles;
-  if (passes == 3) {
-    cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(mA1, mA2, mW, mY, p);
-  } else {
-    cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(mA1, mA2, mW, mY, p);
-  }
+  const int64_t units = ((tiles_m + cluster - 1) / cluster) * (a.n / bn) * a.groups;
+  int grid = sm_count() / cluster;
+  if (units < grid) grid = (int)units;
+  grid *= cluster;
+  auto kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2> : gemm_tc_kernel<3, 1>)
+                          : (cluster == 2 ? gemm_tc_kernel<1, 2> : gemm_tc_kernel<1, 1>);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA1, mA2, mW, mY, p);
+  if (le != cudaSuccess) return fail("gemm_tc launch: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc");
 }
 

@@ -39,7 +39,7 @@ class SimCLR(nn.Module):
         z = ops.linear(ops.linear(h, l1, "elu"), l2)
         return ops.l2_normalize_rows(z, 1e-10)
 
-    def _one_view(self, x):
+    def _one_view(self, x, forced_idx=None):
         if isinstance(self.encoder, GraphEncoder) and not (self.training and torch.is_grad_enabled()):
             if self.encoder.training:
                 raise RuntimeError("call .eval() for inference (BatchNorm statistics)")
@@ -47,9 +47,10 @@ class SimCLR(nn.Module):
             h = self.encoder.forward_nodes(nodes, x.shape[0], N)
             return h, self._project(h)
         from ..autograd import simclr_view_train
-        return simclr_view_train(self, x)
+        return simclr_view_train(self, x, forced_idx)
 
     def forward(self, x_i, x_j):
-        h_i, z_i = self._one_view(x_i)
-        h_j, z_j = self._one_view(x_j)
+        forced = getattr(self, "_forced_idx", None)          # parity-test hook: (view i lists, view j lists)
+        h_i, z_i = self._one_view(x_i, forced[0] if forced else None)
+        h_j, z_j = self._one_view(x_j, forced[1] if forced else None)
         return h_i, h_j, z_i, z_j

@@ -75,7 +75,7 @@ class FusedClipAdam:
 
 
 def train_step(model, x_i: torch.Tensor, x_j: torch.Tensor, cfg, optimizer: FusedClipAdam,
-               group=None, skip_nan: bool = True):
+               group=None, skip_nan: bool = True, forced_idx=None):
     """One step of train.py::train on this rank's shard of the batch.  Returns the (global) loss
     tensor; a NaN loss skips the update like the reference (train.py:65-68)."""
     if not model.training:
@@ -85,8 +85,8 @@ def train_step(model, x_i: torch.Tensor, x_j: torch.Tensor, cfg, optimizer: Fuse
     rank = dist.get_rank(group) if world > 1 else 0
     optimizer.zero_grad()
     with torch.no_grad():
-        h_i, z_i, c_i = view_fwd(model, x_i)
-        h_j, z_j, c_j = view_fwd(model, x_j)
+        h_i, z_i, c_i = view_fwd(model, x_i, forced_idx[0] if forced_idx else None)
+        h_j, z_j, c_j = view_fwd(model, x_j, forced_idx[1] if forced_idx else None)
         z_loc = torch.stack((z_i, z_j), dim=1).reshape(2 * z_i.shape[0], z_i.shape[1]).contiguous()
         rows = z_loc.shape[0]
         if world > 1:
