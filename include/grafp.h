@@ -39,10 +39,15 @@ enum { GRAFP_ACT_NONE = 0, GRAFP_ACT_RELU = 1, GRAFP_ACT_LEAKY = 2, GRAFP_ACT_GE
        GRAFP_ACT_ELU = 4 };
 
 /* GEMM engines */
-enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 3xTF32 where shape + w_split allow, else SIMT */
-       GRAFP_ENGINE_SIMT = 1,      /* fp32 FFMA tiles                                   */
-       GRAFP_ENGINE_TC_3XTF32 = 2, /* tcgen05 kind::tf32, hi/lo split, fp32-accurate    */
-       GRAFP_ENGINE_TC_TF32 = 3    /* tcgen05 kind::tf32 single pass                    */ };
+enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 bf16x3 (else 3xTF32) where the shape and the split
+                                      weights allow, else SIMT                            */
+       GRAFP_ENGINE_SIMT = 1,      /* fp32 FFMA tiles (exact fp32)                       */
+       GRAFP_ENGINE_TC_3XTF32 = 2, /* tcgen05 kind::tf32, hi/lo split, ~2e-6 per product */
+       GRAFP_ENGINE_TC_TF32 = 3,   /* tcgen05 kind::tf32 single pass (not parity grade)  */
+       GRAFP_ENGINE_TC_BF16X3 = 4, /* tcgen05 kind::f16 bf16 hi/lo split, 3 passes at twice the
+                                      tf32 rate, <= 3*2^-18 per product: the fp32-parity engine */
+       GRAFP_ENGINE_TC_BF16 = 5    /* tcgen05 kind::f16 plain bf16 operands, fp32 accumulate
+                                      (reduced precision, reported separately)            */ };
 
 int grafp_abi_version(void);
 const char* grafp_last_error(void);
@@ -111,6 +116,9 @@ typedef struct {
   const float* w_split;                     /* optional (2*groups*n, k1+k2), same ldw: the
                                                [tf32 hi ; tf32 lo] split of w made by
                                                grafp_split_tf32 (needed by TC_3XTF32)     */
+  const void* w_split_bf16;                 /* optional bf16 (2*groups*n, k1+k2), row stride ldw
+                                               elements: [bf16(w) ; bf16(w - bf16(w))] made by
+                                               grafp_split_bf16 (needed by TC_BF16X3 / TC_BF16) */
   const float* scale;                       /* (groups*n) or NULL (= 1)                   */
   const float* shift;                       /* (groups*n) or NULL (= 0)                   */
   const float* residual; int64_t ldr;       /* (M, groups*n) or NULL                      */
@@ -126,6 +134,8 @@ int grafp_gemm_tc_supported(const grafp_gemm_args* args);
 /* error-compensated operand split for TC_3XTF32: out[0:count] = tf32(w), out[count:2*count] =
  * tf32(w - tf32(w)) (round-to-nearest).  Done once per weight version. */
 int grafp_split_tf32(const float* w, int64_t count, float* out_hi_lo, void* stream);
+/* bf16 operand split: out (bf16)[0:count] = bf16(w), out[count:2*count] = bf16(w - bf16(w)) */
+int grafp_split_bf16(const float* w, int64_t count, void* out_bf16_hi_lo, void* stream);
 
 /* mean over the nodes of each graph: x (B*N, C) -> out (B, C)   (graph_encoder.py:211) */
 int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream);

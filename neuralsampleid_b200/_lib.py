@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgrafp_sm100a.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_ELU = 0, 1, 2, 3, 4
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32 = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16X3, ENGINE_TC_BF16 = 0, 1, 2, 3, 4, 5
 ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "3xtf32": ENGINE_TC_3XTF32,
-           "tf32": ENGINE_TC_TF32}
+           "tf32": ENGINE_TC_TF32, "bf16x3": ENGINE_TC_BF16X3, "bf16": ENGINE_TC_BF16}
 
 
 class GrafpError(RuntimeError):
@@ -26,6 +26,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("a1", C.c_void_p), ("lda1", C.c_int64), ("k1", C.c_int32),
                 ("a2", C.c_void_p), ("lda2", C.c_int64), ("k2", C.c_int32),
                 ("w", C.c_void_p), ("ldw", C.c_int64), ("w_split", C.c_void_p),
+                ("w_split_bf16", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("y", C.c_void_p), ("ldy", C.c_int64),
@@ -46,6 +47,7 @@ SIGNATURES = {
     "grafp_gemm_fwd": [C.POINTER(GemmArgs), _P],
     "grafp_gemm_tc_supported": [C.POINTER(GemmArgs)],
     "grafp_split_tf32": [_P, _L, _P, _P],
+    "grafp_split_bf16": [_P, _L, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
     "grafp_peak_extract_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "grafp_l2_normalize_rows": [_P, _L, _I, _F, _P, _P],

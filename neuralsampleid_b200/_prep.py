@@ -40,10 +40,11 @@ def tap3_weight(weight: torch.Tensor) -> torch.Tensor:
 class Linear:
     """Prepared operands of one fused GEMM layer: weight (groups*n, k), optional stacked tf32
     [hi ; lo] split for the tcgen05 3xTF32 engine, per-channel scale / shift."""
-    __slots__ = ("w", "w_split", "scale", "shift", "groups")
+    __slots__ = ("w", "w_split", "w_split_bf16", "scale", "shift", "groups")
 
-    def __init__(self, w, scale, shift, groups=1, w_split=None):
-        self.w, self.scale, self.shift, self.groups, self.w_split = w, scale, shift, groups, w_split
+    def __init__(self, w, scale, shift, groups=1, w_split=None, w_split_bf16=None):
+        self.w, self.scale, self.shift, self.groups = w, scale, shift, groups
+        self.w_split, self.w_split_bf16 = w_split, w_split_bf16
 
 
 @torch.no_grad()
@@ -67,6 +68,8 @@ def make_linear(w: torch.Tensor, scale, shift, groups: int = 1, dual: bool = Fal
         w, groups = dense, 1
         n_total, k = w.shape
     lin = Linear(w, scale, shift, groups)
-    if w.is_cuda and (k // parts) % 32 == 0 and (n_total // groups) % 16 == 0:
+    if w.is_cuda and (k // parts) % 32 == 0 and (n_total // groups) % 32 == 0:
+        # both operand splits are tiny (weights): keep them so any engine can be selected later
         lin.w_split = ops.split_tf32(w)
+        lin.w_split_bf16 = ops.split_bf16(w)
     return lin

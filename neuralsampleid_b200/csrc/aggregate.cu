@@ -32,15 +32,20 @@ __device__ __forceinline__ void mr_item(const float* __restrict__ sx, const int3
   arg = ax | (ay << 8) | (az << 16) | (aw << 24);
 }
 
+// One stage = [ x of one graph : N*C floats | its neighbour lists : N*k int32 ], both fetched with
+// 1-D bulk copies on the same mbarrier.  Each thread works on AGG_UNROLL items (one item = one node x
+// 4 channels) at a time so 4 independent idx -> gather -> max chains are in flight.
+constexpr int AGG_UNROLL = 4;
+
 __global__ void __launch_bounds__(AGG_THREADS, 1)
 mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int B,
-                           int N, int C, int k, int stages, float* __restrict__ m,
-                           uint32_t* __restrict__ arg_out) {
+                           int N, int C, int k, int stages, uint32_t stage_bytes, int idx_in_smem,
+                           float* __restrict__ m, uint32_t* __restrict__ arg_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[AGG_MAX_STAGES];
-  float* sx = reinterpret_cast<float*>(smem_raw);
   const uint32_t graph_floats = (uint32_t)N * C;
   const uint32_t graph_bytes = graph_floats * 4u;
+  const uint32_t idx_bytes = (uint32_t)N * k * 4u;
   const int tid = threadIdx.x;
 
   if (tid == 0) {
@@ -49,16 +54,17 @@ mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restric
   }
   __syncthreads();
 
+  auto issue = [&](int s, int g) {
+    unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
+    mbar_arrive_expect_tx(&full[s], graph_bytes + (idx_in_smem ? idx_bytes : 0u));
+    bulk_g2s(dst, x + (size_t)g * graph_floats, graph_bytes, &full[s]);
+    if (idx_in_smem) bulk_g2s(dst + graph_bytes, idx + (size_t)g * N * k, idx_bytes, &full[s]);
+  };
+
   const int first = blockIdx.x, step = gridDim.x;
-  if (tid == 0) {
-    for (int s = 0; s < stages; ++s) {
-      const int g = first + s * step;
-      if (g < B) {
-        mbar_arrive_expect_tx(&full[s], graph_bytes);
-        bulk_g2s(sx + (size_t)s * graph_floats, x + (size_t)g * graph_floats, graph_bytes, &full[s]);
-      }
-    }
-  }
+  if (tid == 0)
+    for (int s = 0; s < stages; ++s)
+      if (first + s * step < B) issue(s, first + s * step);
 
   const int c4n = C >> 2;
   const int items = N * c4n;
@@ -66,24 +72,50 @@ mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restric
   uint32_t phase = 0;
   for (int g = first; g < B; g += step) {
     mbar_wait(&full[s], phase);
-    const float* gx = sx + (size_t)s * graph_floats;
-    const int32_t* gidx = idx + (size_t)g * N * k;
+    const float* gx = reinterpret_cast<const float*>(smem_raw + (size_t)s * stage_bytes);
+    const int32_t* gidx = idx_in_smem ? reinterpret_cast<const int32_t*>(smem_raw + (size_t)s * stage_bytes + graph_bytes)
+                                      : idx + (size_t)g * N * k;
     float4* gm = reinterpret_cast<float4*>(m + (size_t)g * graph_floats);
     uint32_t* ga = arg_out ? arg_out + (size_t)g * items : nullptr;
-    for (int it = tid; it < items; it += AGG_THREADS) {
-      const int node = it / c4n, c4 = it - node * c4n;
-      float4 v; uint32_t a;
-      mr_item(gx, gidx + (size_t)node * k, k, C, node, c4, v, a);
-      stg_stream(gm + it, v);
-      if (ga) ga[it] = a;
+    for (int it0 = tid; it0 < items; it0 += AGG_UNROLL * AGG_THREADS) {
+      int node[AGG_UNROLL], off[AGG_UNROLL];
+      float4 xi[AGG_UNROLL], best[AGG_UNROLL];
+      uint32_t arg[AGG_UNROLL];
+#pragma unroll
+      for (int u = 0; u < AGG_UNROLL; ++u) {
+        int it = it0 + u * AGG_THREADS;
+        if (it >= items) it = it0;                      // tail: recompute item it0, store masked below
+        node[u] = it / c4n;
+        off[u] = (it - node[u] * c4n) * 4;
+        xi[u] = *reinterpret_cast<const float4*>(gx + (size_t)node[u] * C + off[u]);
+        best[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        arg[u] = 0u;
+      }
+      for (int t = 0; t < k; ++t) {
+#pragma unroll
+        for (int u = 0; u < AGG_UNROLL; ++u) {
+          const int j = gidx[node[u] * k + t];
+          const float4 xj = *reinterpret_cast<const float4*>(gx + (size_t)j * C + off[u]);
+          const float dx = xj.x - xi[u].x, dy = xj.y - xi[u].y, dz = xj.z - xi[u].z, dw = xj.w - xi[u].w;
+          if (dx > best[u].x) { best[u].x = dx; arg[u] = (arg[u] & 0xFFFFFF00u) | (uint32_t)t; }
+          if (dy > best[u].y) { best[u].y = dy; arg[u] = (arg[u] & 0xFFFF00FFu) | ((uint32_t)t << 8); }
+          if (dz > best[u].z) { best[u].z = dz; arg[u] = (arg[u] & 0xFF00FFFFu) | ((uint32_t)t << 16); }
+          if (dw > best[u].w) { best[u].w = dw; arg[u] = (arg[u] & 0x00FFFFFFu) | ((uint32_t)t << 24); }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < AGG_UNROLL; ++u) {
+        const int it = it0 + u * AGG_THREADS;
+        if (it < items) {
+          __stcs(gm + it, best[u]);
+          if (ga) ga[it] = arg[u];
+        }
+      }
     }
     __syncthreads();                      // every warp is done reading stage s
     if (tid == 0) {
       const int gn = g + stages * step;
-      if (gn < B) {
-        mbar_arrive_expect_tx(&full[s], graph_bytes);
-        bulk_g2s(sx + (size_t)s * graph_floats, x + (size_t)gn * graph_floats, graph_bytes, &full[s]);
-      }
+      if (gn < B) issue(s, gn);
     }
     if (++s == stages) { s = 0; phase ^= 1u; }
   }
@@ -170,17 +202,21 @@ int grafp_mr_aggregate_fwd(const float* x, const int32_t* idx, int B, int N, int
   if (B == 0) return 0;
   cudaStream_t st = as_stream(stream);
   const size_t graph_bytes = (size_t)N * C * 4;
-  const size_t budget = 200 * 1024;
-  if (graph_bytes <= budget / 2 && graph_bytes % 16 == 0) {
-    int stages = (int)(budget / graph_bytes);
+  const size_t budget = 216 * 1024;
+  const size_t idx_bytes = (size_t)N * k * 4;
+  const int idx_in_smem = (idx_bytes % 16 == 0) ? 1 : 0;
+  const size_t stage_bytes = graph_bytes + (idx_in_smem ? idx_bytes : 0);
+  if (stage_bytes <= budget / 2 && graph_bytes % 16 == 0) {
+    int stages = (int)(budget / stage_bytes);
     if (stages > AGG_MAX_STAGES) stages = AGG_MAX_STAGES;
     int grid = sm_count();
     if (grid > B) grid = B;
-    const size_t smem = (size_t)stages * graph_bytes;
+    const size_t smem = (size_t)stages * stage_bytes;
     cudaFuncSetAttribute(mr_aggregate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     mr_aggregate_staged_kernel<<<grid, AGG_THREADS, smem, st>>>(
-        x, idx, B, N, C, k, stages, m, reinterpret_cast<uint32_t*>(arg_out));
+        x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m,
+        reinterpret_cast<uint32_t*>(arg_out));
     return check_launch("mr_aggregate_staged");
   }
   for (int b0 = 0; b0 < B; b0 += 65535) {

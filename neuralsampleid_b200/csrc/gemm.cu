@@ -4,7 +4,7 @@
 namespace grafp {
 int gemm_simt_launch(const grafp_gemm_args& a, cudaStream_t st);
 int gemm_tc_supported(const grafp_gemm_args& a);
-int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st);
+int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t st);
 }  // namespace grafp
 
 using namespace grafp;
@@ -34,12 +34,18 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
     case GRAFP_ENGINE_TC_3XTF32:
       GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
       GRAFP_REQUIRE(a.w_split, "gemm: TC_3XTF32 needs w_split (grafp_split_tf32)");
-      return gemm_tc_launch(a, 3, st);
+      return gemm_tc_launch(a, 3, 0, st);
     case GRAFP_ENGINE_TC_TF32:
       GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
-      return gemm_tc_launch(a, 1, st);
+      return gemm_tc_launch(a, 1, 0, st);
+    case GRAFP_ENGINE_TC_BF16X3:
+    case GRAFP_ENGINE_TC_BF16:
+      GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
+      GRAFP_REQUIRE(a.w_split_bf16, "gemm: the bf16 engines need w_split_bf16 (grafp_split_bf16)");
+      return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_BF16X3 ? 3 : 1, 1, st);
     case GRAFP_ENGINE_AUTO:
-      if (a.w_split && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, st);
+      if (a.w_split_bf16 && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, 1, st);
+      if (a.w_split && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, 0, st);
       return gemm_simt_launch(a, st);
     default:
       return fail("gemm: unknown engine %d", a.engine);

@@ -22,6 +22,7 @@
 // the main loop of tile i+1.  Pipelines: full[s] (TMA -> transform), xf[s] (transform -> MMA),
 // empty[s] (MMA commit -> TMA), tmem_full[b] (MMA commit -> epilogue), tmem_empty[b].
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include "tc_common.cuh"
 
 namespace grafp {
@@ -72,7 +73,14 @@ __device__ __forceinline__ void epi_apply(float (&v)[32], const float* __restric
 // CTAs' shared memory, halving the per-SM weight traffic out of L2 (the limiter of the 1-CTA form).
 // A stage may be refilled only when BOTH CTAs have consumed it: every MMA commit is multicast to
 // the pair's `empty` barriers (count 2).
-template <int kPasses, int kCluster>
+//
+// kBf16: the MMA operands are bf16 (kind::f16, twice the tf32 rate, half the operand bytes):
+//   passes = 3 : "bf16x3"  a = a1 + a2 (+ 2^-18 |a|), w = w1 + w2;  D += a2*w1 + a1*w2 + a1*w1
+//                (per-product error <= 3 * 2^-18; the fp32-parity engine under the power cap)
+//   passes = 1 : plain bf16 operands, fp32 accumulate (reduced precision, stated separately)
+// A still arrives from HBM as fp32 (TMA, 128B swizzle); the transform warps convert it into
+// 64-byte-row bf16 tiles (64B swizzle); W is pre-split on the host into stacked bf16 [w1 ; w2].
+template <int kPasses, int kCluster, bool kBf16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -87,15 +95,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 4;
-  const uint32_t stage_bytes = (kPasses == 3 ? 2u : 1u) * (TC_A_BYTES + b_bytes);
+  constexpr uint32_t kOpRow = kBf16 ? 64u : 128u;             // operand bytes per row per k-block
+  constexpr uint32_t kAop = TC_BM * kOpRow;                   // one A operand tile: 8 KB / 16 KB
+  constexpr uint32_t kNP = kPasses == 3 ? 2u : 1u;            // operand copies (hi [+ lo])
+  const uint32_t b_bytes = (uint32_t)p.bn * kOpRow;
+  const uint32_t stage_bytes = kBf16 ? TC_A_BYTES + kNP * (kAop + b_bytes) : kNP * (TC_A_BYTES + b_bytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* store_buf = smem;                                  // 2 x 16 KB staging tiles
   uint8_t* stage0 = smem + 2 * TC_STORE_BYTES;
-  // stage layout: [A_hi | A_lo (3x) | B_hi | B_lo (3x)]
-  auto a_hi = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
-  auto a_lo = [&](int s) { return stage0 + (size_t)s * stage_bytes + TC_A_BYTES; };
-  auto b_hi = [&](int s) { return stage0 + (size_t)s * stage_bytes + (kPasses == 3 ? 2 : 1) * TC_A_BYTES; };
+  // stage layout   tf32: [A raw = hi | A_lo (3x) | B_hi | B_lo (3x)]
+  //                bf16: [A raw fp32 | A_hi | A_lo (3x) | B_hi | B_lo (3x)]
+  auto a_raw = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
+  auto a_hi = [&](int s) { return a_raw(s) + (kBf16 ? TC_A_BYTES : 0); };
+  auto a_lo = [&](int s) { return a_hi(s) + kAop; };
+  auto b_hi = [&](int s) { return a_hi(s) + kNP * kAop; };
   auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
 
   const int nkb = (p.k1 + p.k2) / TC_BK;
@@ -143,7 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[s], TC_A_BYTES + (kPasses == 3 ? 2u : 1u) * b_bytes);
+          mbar_arrive_expect_tx(&full_bar[s], TC_A_BYTES + kNP * b_bytes);
           const int k = kb * TC_BK;
           if (p.tap3_rows > 0) {
             // Downsample: W columns are [tap0 | tap1 | tap2]; taps 1,2 = the (M, 2*Cin) view of
@@ -151,19 +164,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             // (3-D map, out-of-range row -1 zero-filled by TMA)
             if (k < p.tap3_cin) {
               const int b0 = m0 / p.tap3_rows, j0 = m0 % p.tap3_rows;
-              tma_load_3d(a_hi(s), &tmA2, p.tap3_cin + k, j0 - 1, b0, &full_bar[s]);
+              tma_load_3d(a_raw(s), &tmA2, p.tap3_cin + k, j0 - 1, b0, &full_bar[s]);
             } else {
-              tma_load_2d(a_hi(s), &tmA1, k - p.tap3_cin, m0, &full_bar[s]);
+              tma_load_2d(a_raw(s), &tmA1, k - p.tap3_cin, m0, &full_bar[s]);
             }
           } else if (k < p.k1) {
-            tma_load_2d(a_hi(s), &tmA1, g * p.k1 + k, m0, &full_bar[s]);
+            tma_load_2d(a_raw(s), &tmA1, g * p.k1 + k, m0, &full_bar[s]);
           } else {
-            tma_load_2d(a_hi(s), &tmA2, g * p.k2 + (k - p.k1), m0, &full_bar[s]);
+            tma_load_2d(a_raw(s), &tmA2, g * p.k2 + (k - p.k1), m0, &full_bar[s]);
           }
           if (kCluster == 2) {
             // my half of the weight tile, multicast to both CTAs of the pair (tmW box = bn/2 rows)
             const int half = p.bn / 2;
-            const uint32_t off = crank * (uint32_t)half * (TC_BK * 4);
+            const uint32_t off = crank * (uint32_t)half * kOpRow;
             tma_load_2d_mc(b_hi(s) + off, &tmW, k, g * p.n + n0 + (int)crank * half, &full_bar[s], 0x3);
             if (kPasses == 3)
               tma_load_2d_mc(b_lo(s) + off, &tmW, k, p.n_total + g * p.n + n0 + (int)crank * half,
@@ -178,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TC_BM, p.bn);
+      const uint32_t idesc = kBf16 ? umma_idesc_bf16(TC_BM, p.bn) : umma_idesc_tf32(TC_BM, p.bn);
       uint32_t it = 0, ti = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
         const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
@@ -188,22 +201,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
-          mbar_wait(kPasses == 3 ? &xf_bar[s] : &full_bar[s], ph);
+          mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph);
           tc_fence_after();
-          const uint64_t dah = umma_desc_sw128(smem_u32(a_hi(s)));
-          const uint64_t dbh = umma_desc_sw128(smem_u32(b_hi(s)));
+          if (kBf16) {
+            const uint64_t dah = umma_desc_sw64(smem_u32(a_hi(s))), dbh = umma_desc_sw64(smem_u32(b_hi(s)));
+            const uint64_t dal = umma_desc_sw64(smem_u32(a_lo(s))), dbl = umma_desc_sw64(smem_u32(b_lo(s)));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);       // 32 B per k-step
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            if (kPasses == 3) {
-              const uint64_t dal = umma_desc_sw128(smem_u32(a_lo(s)));
-              const uint64_t dbl = umma_desc_sw128(smem_u32(b_lo(s)));
-              umma_tf32(tacc, dal + koff, dbh + koff, idesc, acc);
-              umma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
-              umma_tf32(tacc, dah + koff, dbh + koff, idesc, 1u);
-            } else {
-              umma_tf32(tacc, dah + koff, dbh + koff, idesc, acc);
+            for (int k = 0; k < TC_BK / 16; ++k) {                    // UMMA_K = 16 bf16 = 32 B
+              const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              if (kPasses == 3) {
+                umma_bf16(tacc, dal + koff, dbh + koff, idesc, acc);
+                umma_bf16(tacc, dah + koff, dbl + koff, idesc, 1u);
+                umma_bf16(tacc, dah + koff, dbh + koff, idesc, 1u);
+              } else {
+                umma_bf16(tacc, dah + koff, dbh + koff, idesc, acc);
+              }
+            }
+          } else {
+            const uint64_t dah = umma_desc_sw128(smem_u32(a_hi(s)));
+            const uint64_t dbh = umma_desc_sw128(smem_u32(b_hi(s)));
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);       // 32 B per k-step
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              if (kPasses == 3) {
+                const uint64_t dal = umma_desc_sw128(smem_u32(a_lo(s)));
+                const uint64_t dbl = umma_desc_sw128(smem_u32(b_lo(s)));
+                umma_tf32(tacc, dal + koff, dbh + koff, idesc, acc);
+                umma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
+                umma_tf32(tacc, dah + koff, dbh + koff, idesc, 1u);
+              } else {
+                umma_tf32(tacc, dah + koff, dbh + koff, idesc, acc);
+              }
             }
           }
           // smem slot reusable once these MMAs retire (in both CTAs of a pair)
@@ -213,10 +243,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else if (warp >= 6) {
-    // ===== transform (warps 6..13, 256 threads): split the A stage into tf32 hi / lo =====
-    // hi = v with the 13 low mantissa bits cleared (exactly representable in tf32), lo = v - hi
-    // (exact in fp32, |lo| < 2^-10 |v|; the tensor core reads its top 19 bits)
-    if (kPasses == 3) {
+    // ===== transform (warps 6..13, 256 threads): build the MMA A operand(s) from the fp32 stage =====
+    // tf32: hi = v with the 13 low mantissa bits cleared (exactly representable in tf32), lo = v - hi
+    //       (exact in fp32, |lo| < 2^-10 |v|; the tensor core reads its top 19 bits), in place.
+    // bf16: a1 = bf16(v), a2 = bf16(v - a1) written as 64-byte rows (64B swizzle: 16-byte chunk c of
+    //       row r lives at chunk c ^ ((r >> 1) & 3)); the source float4 sits at swizzled chunk q & 7 of
+    //       its 128-byte row, i.e. logical k-chunk (q & 7) ^ (r & 7).
+    if (kPasses == 3 || kBf16) {
       constexpr int PER = TC_A_BYTES / 16 / TC_XF_THREADS;
       const int t = threadIdx.x - 192;
       uint32_t it = 0;
@@ -225,21 +258,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(&full_bar[s], ph);
-          float4* hi = reinterpret_cast<float4*>(a_hi(s));
-          float4* lo = reinterpret_cast<float4*>(a_lo(s));
+          const float4* raw = reinterpret_cast<const float4*>(a_raw(s));
           float4 v[PER];
 #pragma unroll
-          for (int i = 0; i < PER; ++i) v[i] = hi[t + TC_XF_THREADS * i];
+          for (int i = 0; i < PER; ++i) v[i] = raw[t + TC_XF_THREADS * i];
+          if (kBf16) {
+            uint8_t* hi = a_hi(s);
+            uint8_t* lo = a_lo(s);
 #pragma unroll
-          for (int i = 0; i < PER; ++i) {
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
-            l.x = v[i].x - h.x; l.y = v[i].y - h.y; l.z = v[i].z - h.z; l.w = v[i].w - h.w;
-            hi[t + TC_XF_THREADS * i] = h;
-            lo[t + TC_XF_THREADS * i] = l;
+            for (int i = 0; i < PER; ++i) {
+              const int q = t + TC_XF_THREADS * i;
+              const int r = q >> 3;
+              const int lc = (q & 7) ^ (r & 7);                          // logical 4-float chunk 0..7
+              const uint32_t dst = (uint32_t)r * 64u + ((uint32_t)((lc >> 1) ^ ((r >> 1) & 3)) << 4) +
+                                   ((uint32_t)(lc & 1) << 3);
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[i].x, v[i].y);
+              const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[i].z, v[i].w);
+              uint2 hv;
+              hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+              hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(hi + dst) = hv;
+              if (kPasses == 3) {
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[i].x - f01.x, v[i].y - f01.y);
+                const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[i].z - f23.x, v[i].w - f23.y);
+                uint2 lv;
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01);
+                lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(lo + dst) = lv;
+              }
+            }
+          } else {
+            float4* hi = reinterpret_cast<float4*>(a_hi(s));
+            float4* lo = reinterpret_cast<float4*>(a_lo(s));
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+              float4 h, l;
+              h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+              h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+              h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+              h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+              l.x = v[i].x - h.x; l.y = v[i].y - h.y; l.z = v[i].z - h.z; l.w = v[i].w - h.w;
+              hi[t + TC_XF_THREADS * i] = h;
+              lo[t + TC_XF_THREADS * i] = l;
+            }
           }
           fence_proxy_async_smem();             // generic-proxy writes -> visible to the MMA (async proxy)
           mbar_arrive(&xf_bar[s]);
@@ -339,6 +401,21 @@ int tc_make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t co
   return 0;
 }
 
+int tc_make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows) {
+  EncodeTiledFn fn = tc_encode_fn();
+  GRAFP_REQUIRE(fn, "tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GRAFP_REQUIRE(r == CUDA_SUCCESS, "tc: cuTensorMapEncodeTiled(bf16) failed (%d)", (int)r);
+  return 0;
+}
+
 int tc_make_map_3d(CUtensorMap* map, const float* base, int64_t d0, int64_t d1, int64_t d2,
                    int64_t s1, int64_t s2, int box1, int box2) {
   EncodeTiledFn fn = tc_encode_fn();
@@ -378,14 +455,15 @@ int gemm_tc_supported(const grafp_gemm_args& a) {
     if (a.k1 % TC_BK != 0 || a.k2 % TC_BK != 0) return 0;
     if ((a.lda1 * 4) % 16 != 0 || (a.k2 && (a.lda2 * 4) % 16 != 0)) return 0;
   }
-  if ((a.ldw * 4) % 16 != 0) return 0;
+  if ((a.ldw * 4) % 16 != 0 || a.ldw % 8 != 0) return 0;
   if (a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15)) return 0;
   if (a.residual && (a.ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15))) return 0;
   return 1;
 }
 
-// For passes == 3 a.w_split addresses the stacked [W_hi ; W_lo] matrix (2 * groups * n rows).
-int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st) {
+// tf32 engines: passes == 3 reads a.w_split = stacked fp32 [W_hi ; W_lo] (2 * groups * n rows).
+// bf16 engines: a.w_split_bf16 = stacked bf16 [w1 ; w2]; passes == 1 uses only w1.
+int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t st) {
   const int bn = pick_bn(a.n);
   const int n_total = a.groups * a.n;
   CUtensorMap mA1, mA2, mW, mY;
@@ -412,8 +490,12 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st) {
   static int mc_env = -1;
   if (mc_env < 0) { const char* e = getenv("GRAFP_TC_CLUSTER"); mc_env = e ? atoi(e) : 2; }
   const int cluster = (mc_env == 2 && tiles_m >= 2 && bn % 64 == 0 && sm_count() % 2 == 0) ? 2 : 1;
-  if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
-                              a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
+  if (bf16) {
+    if (int rc = tc_make_map_2d_bf16(&mW, a.w_split_bf16, (int64_t)n_total * 2, a.k1 + a.k2, a.ldw,
+                                     cluster == 2 ? bn / 2 : bn))
+      return rc;
+  } else if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
+                                     a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
     return rc;
   if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) return rc;
   p.k1 = a.k1; p.k2 = a.k2; p.n = a.n; p.bn = bn; p.n_total = n_total; p.groups = a.groups; p.m = a.m;
@@ -422,7 +504,9 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st) {
   uint32_t cols = 32;
   while ((int)cols < 2 * bn) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t stage_bytes = (size_t)(passes == 3 ? 2 : 1) * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
+  const size_t np = passes == 3 ? 2 : 1;
+  const size_t stage_bytes = bf16 ? TC_A_BYTES + np * ((size_t)TC_BM * 64 + (size_t)bn * 64)
+                                  : np * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
   const int nkb = (a.k1 + a.k2) / TC_BK;
   int stages = (int)((225 * 1024 - 2 * TC_STORE_BYTES - 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -434,8 +518,10 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, cudaStream_t st) {
   int grid = sm_count() / cluster;
   if (units < grid) grid = (int)units;
   grid *= cluster;
-  auto kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2> : gemm_tc_kernel<3, 1>)
-                          : (cluster == 2 ? gemm_tc_kernel<1, 2> : gemm_tc_kernel<1, 1>);
+  auto kern = bf16 ? (passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true> : gemm_tc_kernel<3, 1, true>)
+                                  : (cluster == 2 ? gemm_tc_kernel<1, 2, true> : gemm_tc_kernel<1, 1, true>))
+                   : (passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, false> : gemm_tc_kernel<3, 1, false>)
+                                  : (cluster == 2 ? gemm_tc_kernel<1, 2, false> : gemm_tc_kernel<1, 1, false>));
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -465,9 +551,28 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
   }
 }
 
+// w1 = bf16(w), w2 = bf16(w - w1): out is bf16 (2*rows, cols) = [w1 ; w2]
+__global__ void split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = w[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    out[n + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 }  // namespace grafp
 
 using namespace grafp;
+
+extern "C" int grafp_split_bf16(const float* w, int64_t count, void* out_bf16_hi_lo, void* stream) {
+  GRAFP_REQUIRE(count >= 0 && (count == 0 || (w && out_bf16_hi_lo)), "split_bf16: bad arguments");
+  if (count == 0) return 0;
+  split_bf16_kernel<<<(unsigned)((count + 255) / 256), 256, 0, as_stream(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(out_bf16_hi_lo), count);
+  return check_launch("split_bf16");
+}
 
 extern "C" int grafp_split_tf32(const float* w, int64_t count, float* out_hi_lo, void* stream) {
   GRAFP_REQUIRE(count >= 0 && (count == 0 || (w && out_hi_lo)), "split_tf32: bad arguments");

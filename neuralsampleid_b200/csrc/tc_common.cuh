@@ -107,6 +107,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_64B descriptor (rows of 64 B = 32 bf16): SBO = 8 rows * 64 B = 512, layout_type=4
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with bf16 operands: D=F32, A=B=BF16 (1), K-major
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows *
 // 128 B = 1024) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
@@ -154,6 +177,9 @@ EncodeTiledFn tc_encode_fn();
 // fp32 row-major (rows, cols), row stride ld elements; box = (32 cols, box_rows), 128B swizzle
 int tc_make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
                    int box_rows);
+// bf16 row-major (rows, cols), row stride ld elements; box = (32 cols = 64 B, box_rows), 64B swizzle
+int tc_make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows);
 // fp32 (d2, d1, d0=cols) with element strides (s2, s1, 1); box = (32, box1, box2), 128B swizzle
 int tc_make_map_3d(CUtensorMap* map, const float* base, int64_t d0, int64_t d1, int64_t d2,
                    int64_t s1, int64_t s2, int box1, int box2);

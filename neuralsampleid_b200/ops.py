@@ -17,11 +17,14 @@ _ACTS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leakyrelu": ACT_LE
          "gelu": ACT_GELU, "elu": ACT_ELU}
 
 _engine = ENGINES[os.environ.get("GRAFP_ENGINE", "auto").lower()]
+# test/bench hook: a tensor-core engine name applied to every GEMM whose shape the tensor-core
+# kernels take (the others keep the exact SIMT engine), e.g. "3xtf32", "bf16"
+_engine_override = None
 
 
 def set_engine(name: str) -> None:
-    """Selects the GEMM engine: 'auto' (tcgen05 3xTF32 where shapes allow, else fp32 SIMT),
-    'simt', '3xtf32', 'tf32'."""
+    """Selects the GEMM engine: 'auto' (tcgen05 bf16x3 where shapes allow, else fp32 SIMT), 'simt',
+    '3xtf32', 'tf32', 'bf16x3', 'bf16'.  Prepared weights are re-split on the next call."""
     global _engine
     _engine = ENGINES[name.lower()]
 
@@ -138,18 +141,36 @@ def split_tf32(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def split_bf16(w: torch.Tensor) -> torch.Tensor:
+    """(n, k) fp32 -> bf16 (2n, k) stacked [bf16(w) ; bf16(w - bf16(w))] for the bf16 engines."""
+    w = _chk(w, name="w")
+    out = torch.empty((2 * w.shape[0], w.shape[1]), device=w.device, dtype=torch.bfloat16)
+    with torch.cuda.device(w.device):
+        check(_lib.load().grafp_split_bf16(_ptr(w), w.numel(), _ptr(out), _stream(w)), "split_bf16")
+    return out
+
+
+def tc_splits(w: torch.Tensor):
+    """The split copies of a weight the engines in use need: (tf32 split | None, bf16 split | None)."""
+    e = _engine
+    want_tf32 = e in (_lib.ENGINE_TC_3XTF32,)
+    want_bf16 = e in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16)
+    return (split_tf32(w) if want_tf32 else None), (split_bf16(w) if want_bf16 else None)
+
+
 def linear(a1: torch.Tensor, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
            tap3_nodes: int = 0, engine: Optional[int] = None) -> torch.Tensor:
     """ops.gemm over a prepared ``_prep.Linear``."""
     return gemm(a1, lin.w, lin.scale, lin.shift, act, act_param, residual, a2, lin.groups, tap3_nodes,
-                engine, None, lin.w_split)
+                engine, None, lin.w_split, lin.w_split_bf16)
 
 
 def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
          shift: Optional[torch.Tensor] = None, act=None, act_param: float = 0.0,
          residual: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          groups: int = 1, tap3_nodes: int = 0, engine: Optional[int] = None,
-         out: Optional[torch.Tensor] = None, w_split: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, w_split: Optional[torch.Tensor] = None,
+         w_split_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = act(scale * [a1 | a2] @ w.T + shift) + residual  (per-group, see include/grafp.h).
 
     a1: (M, groups*k1) (or the (2M', Cin) node matrix in tap3 mode), a2: (M, groups*k2) or None,
@@ -179,6 +200,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
         (a2.stride(0) if a2 is not None else 0), k2
     args.w, args.ldw = w.data_ptr(), w.stride(0)
     args.w_split = w_split.data_ptr() if w_split is not None else None
+    args.w_split_bf16 = w_split_bf16.data_ptr() if w_split_bf16 is not None else None
     args.scale = scale.data_ptr() if scale is not None else None
     args.shift = shift.data_ptr() if shift is not None else None
     if residual is not None:
@@ -191,6 +213,12 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     args.act, args.act_param = act_code(act) if not isinstance(act, int) else act, act_param
     args.tap3_nodes = tap3_nodes
     args.engine = _engine if engine is None else engine
+    if engine is None and _engine_override is not None:
+        ov = ENGINES[_engine_override]
+        if ov == _lib.ENGINE_SIMT:
+            args.engine = ov
+        elif w_split is not None and _lib.load().grafp_gemm_tc_supported(C.byref(args)):
+            args.engine = ov
     with torch.cuda.device(a1.device):
         check(_lib.load().grafp_gemm_fwd(C.byref(args), _stream(a1)), "gemm_fwd")
     return out

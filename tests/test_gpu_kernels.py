@@ -239,7 +239,7 @@ GEMM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("engine", ["simt", "3xtf32", "tf32", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "3xtf32", "tf32", "bf16x3", "bf16", "auto"])
 @pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: "m%d_k%d+%d_n%d_g%d_%s%s%s" % (
     c[0], c[1], c[2], c[3], c[4], c[5], "_res" if c[6] else "", "_tap3" if c[7] else ""))
 def test_gemm_engines(case, engine):
@@ -263,7 +263,7 @@ def test_gemm_engines(case, engine):
     # rows per graph tile 128 evenly
     tc_ok = lin.w_split is not None and n % 32 == 0 and \
         (not tap3 or ((k1 // 3) % 32 == 0 and (128 % tap3 == 0 or tap3 % 128 == 0)))
-    if engine in ("3xtf32", "tf32") and not tc_ok:
+    if engine in ("3xtf32", "tf32", "bf16x3", "bf16") and not tc_ok:
         with pytest.raises(_lib.GrafpError):
             ops.linear(a1.to(DEV), lin, act, 0.2, res.to(DEV) if use_res else None,
                        a2.to(DEV) if k2 else None, tap3, eng)
@@ -275,7 +275,9 @@ def test_gemm_engines(case, engine):
     # fp32 FFMA engine: 1e-5 of the output scale.  3xTF32: the tensor core's fp32 accumulator
     # truncates on every MMA, a bias that grows with the number of k-steps (measured 1.3e-5 at
     # k=2048, 3.0e-5 at k=4096) -> 5e-5.  Single-pass TF32: 2e-3.
-    tol = {"tf32": 2e-3, "simt": 1e-5}.get(engine, 5e-5)
+    # bf16x3 (the default tensor-core engine): <= 3 * 2^-18 per product + the same accumulator bias -> 5e-5.
+    # Plain bf16 operands: 1e-2.
+    tol = {"tf32": 2e-3, "bf16": 1e-2, "simt": 1e-5}.get(engine, 5e-5)
     assert err < tol, "engine %s rel err %.3g" % (engine, err)
 
 

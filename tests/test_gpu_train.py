@@ -191,12 +191,16 @@ def _compare_grads(got, want):
     fp32 vs fp64 (same graphs) shows per-parameter cosine >= 0.99993 and norm ratio within 2e-4.
     Bar here: per-parameter cosine > 0.999, norm within 1e-2; whole gradient cosine > 0.9999."""
     ga, wa = [], []
+    # Parameters whose true gradient is zero (conv biases AND the BatchNorm shift in front of another
+    # train-mode BatchNorm, e.g. Grapher.fc1's beta: a per-channel constant cancels in the next batch
+    # normalisation) hold pure rounding noise in both implementations: bound them, do not compare.
+    rms = {n: float(w.double().norm()) / max(1, w.numel()) ** 0.5 for n, w in want.items()}
+    floor = 1e-3 * float(np.median([v for v in rms.values() if v > 0]))
     for n, w in want.items():
         g_, w_ = got[n].double().reshape(-1), w.double().reshape(-1)
-        if float(g_.norm()) == 0.0 or float(w_.norm()) < 1e-6:
-            # conv biases in front of a train-mode BatchNorm: mathematically zero gradient (exactly
-            # zero here, ~1e-6 rounding noise in autograd)
-            assert float(w_.abs().max()) < 1e-4 and float(g_.abs().max()) < 1e-5, n
+        if rms[n] < floor or float(g_.norm()) == 0.0:
+            assert float(g_.norm()) / max(1, g_.numel()) ** 0.5 < 10 * floor, n
+            assert rms[n] < 10 * floor, n
             continue
         cos = float(g_ @ w_ / (g_.norm() * w_.norm()))
         assert cos > 0.999, (n, cos)
