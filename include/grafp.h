@@ -73,11 +73,14 @@ int grafp_nodes_to_nchw(const float* src, float* dst, int B, int C, int N, void*
  *            given, else the exact fp32 SIMT kernel; GRAFP_ENGINE_SIMT / GRAFP_ENGINE_TC_3XTF32
  *            force one of them.
  *   workspace  caller-owned scratch of grafp_knn_workspace_bytes() bytes (may be NULL -> SIMT)
+ *   row_sumsq  optional (B*N): sum_c x[m,c]^2 already computed by the producing GEMM
+ *            (grafp_gemm_args.row_sumsq); the tensor-core engine then skips its prepass and uses
+ *            rinv = 1/max(sqrt(s), 1e-12), sq = s * rinv^2
  * Limits: k*dilation <= N, C % 4 == 0, N <= 2048. */
 size_t grafp_knn_workspace_bytes(int B, int N, int C, int k, int dilation);
 int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dilation, int normalize,
-                  int engine, int32_t* idx_out, float* dist_out, void* workspace,
-                  size_t workspace_bytes, void* stream);
+                  int engine, const float* row_sumsq, int32_t* idx_out, float* dist_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- neighbour gather + max-relative aggregation ---------------------------------------
  * Replaces the two batched_index_select calls (encoder/gcn_lib/torch_nn.py:79-98) and
@@ -123,6 +126,8 @@ typedef struct {
   const float* shift;                       /* (groups*n) or NULL (= 0)                   */
   const float* residual; int64_t ldr;       /* (M, groups*n) or NULL                      */
   float* y; int64_t ldy;                    /* (M, groups*n)                              */
+  float* row_sumsq;                         /* optional (M): += sum_j y[m, j]^2 (atomic; caller
+                                               zeroes).  Lets grafp_knn_fwd skip its norm pass */
   int64_t m; int32_t n; int32_t groups;
   int32_t act; float act_param;
   int32_t tap3_nodes;

@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
                 ("w_split_bf16", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
-                ("y", C.c_void_p), ("ldy", C.c_int64),
+                ("y", C.c_void_p), ("ldy", C.c_int64), ("row_sumsq", C.c_void_p),
                 ("m", C.c_int64), ("n", C.c_int32), ("groups", C.c_int32),
                 ("act", C.c_int32), ("act_param", C.c_float),
                 ("tap3_nodes", C.c_int32), ("engine", C.c_int32)]
@@ -40,7 +40,7 @@ _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "grafp_nchw_to_nodes": [_P, _P, _I, _I, _I, _P],
     "grafp_nodes_to_nchw": [_P, _P, _I, _I, _I, _P],
-    "grafp_knn_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P],
+    "grafp_knn_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, C.c_size_t, _P],
     "grafp_mr_aggregate_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
     "grafp_mr_aggregate_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "grafp_index_select": [_P, _P, _I, _I, _I, _I, _P, _P],

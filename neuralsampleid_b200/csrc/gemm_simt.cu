@@ -15,6 +15,7 @@ struct GemmP {
   const float* scale; const float* shift;
   const float* residual; int64_t ldr;
   float* y; int64_t ldy;
+  float* row_sumsq;
   int64_t m; int n; int act; float act_param;
   int tap3_nodes;
 };
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmP p) {
   for (int i = 0; i < TM; ++i) {
     const int64_t m = m0 + ty * TM + i;
     if (m >= p.m) continue;
+    float rowsq = 0.0f;
 #pragma unroll
     for (int j = 0; j < TN; j += 4) {
       const int nn = n0 + tx * TN + j;
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmP p) {
           t = apply_act(t, p.act, p.act_param);
           if (p.residual) t += p.residual[m * p.ldr + col + q];
           v[q] = t;
+          rowsq = fmaf(t, t, rowsq);
         }
       }
       float* dst = p.y + m * p.ldy + col;
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmP p) {
           if (nn + q < p.n) dst[q] = v[q];
       }
     }
+    if (p.row_sumsq) atomicAdd(p.row_sumsq + m, rowsq);
   }
 }
 
@@ -168,7 +172,7 @@ int gemm_simt_launch(const grafp_gemm_args& a, cudaStream_t st) {
   p.a1 = a.a1; p.lda1 = a.lda1; p.k1 = a.k1;
   p.a2 = a.a2; p.lda2 = a.lda2; p.k2 = a.k2;
   p.w = a.w; p.ldw = a.ldw; p.scale = a.scale; p.shift = a.shift;
-  p.residual = a.residual; p.ldr = a.ldr; p.y = a.y; p.ldy = a.ldy;
+  p.residual = a.residual; p.ldr = a.ldr; p.y = a.y; p.ldy = a.ldy; p.row_sumsq = a.row_sumsq;
   p.m = a.m; p.n = a.n; p.act = a.act; p.act_param = a.act_param; p.tap3_nodes = a.tap3_nodes;
   const int64_t mt = (a.m + 127) / 128;
   GRAFP_REQUIRE(mt <= 0x7fffffff, "gemm: m too large");

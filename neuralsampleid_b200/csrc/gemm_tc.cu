@@ -44,6 +44,7 @@ struct TcParams {
   int tap3_cin;
   const float* scale; const float* shift;
   const float* residual; int64_t ldr;
+  float* row_sumsq;
   int act; float act_param;
   uint32_t tmem_cols;
 };
@@ -328,6 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const bool row_ok = row < p.m;
       const int64_t col0 = (int64_t)g * p.n + n0;
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
+      float rowsq = 0.0f;
       for (int c = 0; c < p.bn; c += 32, ++cc) {
         float v[32];
         tmem_ld16_nowait(tacc + (uint32_t)c, v);
@@ -347,6 +349,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, scp, shp, res, p.act_param); break;
           default:              epi_apply<GRAFP_ACT_ELU>(v, scp, shp, res, p.act_param); break;
         }
+        if (p.row_sumsq) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) rowsq = fmaf(v[q], v[q], rowsq);
+        }
         uint8_t* sb = store_buf + (cc & 1u) * TC_STORE_BYTES;
         if (store_thread) bulk_wait_group_read<1>();     // the store that last used `sb` has read it
         named_bar_sync(1, 128);
@@ -361,6 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           bulk_commit_group();
         }
       }
+      if (p.row_sumsq && row_ok) atomicAdd(p.row_sumsq + row, rowsq);
     }
     if (store_thread) bulk_wait_group_all();
   }
@@ -500,6 +507,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) return rc;
   p.k1 = a.k1; p.k2 = a.k2; p.n = a.n; p.bn = bn; p.n_total = n_total; p.groups = a.groups; p.m = a.m;
   p.scale = a.scale; p.shift = a.shift; p.residual = a.residual; p.ldr = a.ldr;
+  p.row_sumsq = a.row_sumsq;
   p.act = a.act; p.act_param = a.act_param;
   uint32_t cols = 32;
   while ((int)cols < 2 * bn) cols <<= 1;

@@ -189,7 +189,7 @@ namespace grafp {
 int knn_tc_supported(int B, int N, int C, int kk);
 size_t knn_tc_workspace_bytes(int B, int N);
 int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int normalize,
-                  int32_t* idx, float* dist, float* workspace, cudaStream_t st);
+                  const float* row_sumsq, int32_t* idx, float* dist, float* workspace, cudaStream_t st);
 }  // namespace grafp
 
 extern "C" size_t grafp_knn_workspace_bytes(int B, int N, int C, int k, int dilation) {
@@ -198,8 +198,8 @@ extern "C" size_t grafp_knn_workspace_bytes(int B, int N, int C, int k, int dila
 }
 
 extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dilation,
-                             int normalize, int engine, int32_t* idx_out, float* dist_out,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             int normalize, int engine, const float* row_sumsq, int32_t* idx_out,
+                             float* dist_out, void* workspace, size_t workspace_bytes, void* stream) {
   GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0 && dilation > 0, "knn: bad sizes");
   GRAFP_REQUIRE(B == 0 || (x && idx_out), "knn: null pointer");
   GRAFP_REQUIRE(C % 4 == 0, "knn: C=%d must be a multiple of 4", C);
@@ -215,7 +215,7 @@ extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dil
                          "and a workspace of grafp_knn_workspace_bytes()");
   }
   if ((engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_TC_3XTF32) && tc_ok)
-    return knn_tc_launch(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out,
+    return knn_tc_launch(x, B, N, C, kk, dilation, k, normalize, row_sumsq, idx_out, dist_out,
                          static_cast<float*>(workspace), st);
   GRAFP_REQUIRE(engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_SIMT, "knn: unknown engine %d", engine);
   if (N <= 16) return knn_launch<1>(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out, st);

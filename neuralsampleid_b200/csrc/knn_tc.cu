@@ -26,7 +26,8 @@ struct KnnTcParams {
   int64_t M;
   int bn;                 // columns per tile: N (N >= 128) or 128
   int stages;
-  const float* rinv; const float* sq;
+  const float* rinv; const float* sq;   // prepass outputs, or (rinv == nullptr) sq = raw sum of squares
+  int normalize;
   int32_t* idx; float* dist;
   uint32_t tmem_cols;
 };
@@ -65,6 +66,16 @@ knn_rownorm_kernel(const float* __restrict__ x, int64_t M, int C, int normalize,
   if (ok && sl == 0) { rinv[row] = ri; sq[row] = q; }
 }
 
+// (rinv, sq) of one node: from the prepass arrays, or derived from the raw sum of squares that the
+// producing GEMM's epilogue accumulated
+__device__ __forceinline__ float2 knn_node_norm(const KnnTcParams& p, int64_t node) {
+  if (p.rinv) return make_float2(__ldg(p.rinv + node), __ldg(p.sq + node));
+  const float s = __ldg(p.sq + node);
+  if (!p.normalize) return make_float2(1.0f, s);
+  const float ri = __frcp_rn(fmaxf(sqrtf(s), 1e-12f));
+  return make_float2(ri, s * ri * ri);
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
@@ -75,6 +86,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_sq[2][256];      // squared norms of the tile's column set
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -167,7 +179,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t node = c0 + (t >> 3) + 32 * i;
-        ri[i] = (i < per && node < p.M) ? __ldg(p.rinv + node) : 0.0f;
+        ri[i] = (i < per && node < p.M) ? knn_node_norm(p, node).x : 0.0f;
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S;
@@ -210,8 +222,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       const int64_t gs = row_ok ? (grow / p.N) * p.N : c0;     // first node of this row's graph
       const int lo_col = (int)(gs - c0);                       // its first column inside the tile
       const unsigned ncols = row_ok ? (unsigned)p.N : 0u;      // columns [lo_col, lo_col + N) are its graph
-      const float sqi = row_ok ? __ldg(p.sq + grow) : 0.0f;
-      const float4* sqv = reinterpret_cast<const float4*>(p.sq + c0);   // 16-byte aligned: c0 % 128 == 0
+      const float sqi = row_ok ? knn_node_norm(p, grow).y : 0.0f;
+      // stage the column set's squared norms (the workspace is padded: reads past M are harmless)
+      s_sq[buf][r] = (c0 + r < p.M) ? knn_node_norm(p, c0 + r).y : 0.0f;
+      if (p.bn > 128) s_sq[buf][r + 128] = (c0 + 128 + r < p.M) ? knn_node_norm(p, c0 + 128 + r).y : 0.0f;
+      named_bar_sync(1, 128);
+      const float4* sqv = reinterpret_cast<const float4*>(s_sq[buf]);
       float bd[KMAX];
       int bj[KMAX];
 #pragma unroll
@@ -219,23 +235,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       mbar_wait(&tmem_full_bar[buf], tph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
-      for (int c = 0; c < p.bn; c += 16) {
-        float v[16];
+      // software pipeline over 32-column chunks: while chunk c is scanned, the TMEM load and the
+      // squared norms of chunk c+32 are already in flight (two register buffers, loop unrolled by 2)
+      float va[32], vb[32];
+      auto fetch = [&](int c, float* v) {
         tmem_ld16_nowait(tacc + (uint32_t)c, v);
-        float sj[16];
+        tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
+      };
+      auto scan = [&](int c, const float* v) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {                            // (workspace is padded: no bounds issue)
-          const float4 s4 = __ldg(sqv + (c >> 2) + q);
-          sj[4 * q] = s4.x; sj[4 * q + 1] = s4.y; sj[4 * q + 2] = s4.z; sj[4 * q + 3] = s4.w;
-        }
-        tmem_ld_wait();
-        if (c + 16 >= p.bn) {
-          tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[buf]);
-        }
+        for (int q4 = 0; q4 < 32; q4 += 4) {
+          const float4 s4 = sqv[(c + q4) >> 2];                          // shared-memory broadcast
+          const float sj[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float dv = __fadd_rn(__fadd_rn(sqi, -2.0f * v[q]), sj[q]);
+          for (int u = 0; u < 4; ++u) {
+          const int q = q4 + u;
+          const float dv = __fadd_rn(fmaf(v[q], -2.0f, sqi), sj[u]);     // (sq_i + (-2 dot)) + sq_j
           const int jl = c + q - lo_col;
           if ((unsigned)jl < ncols && dv < bd[KMAX - 1]) {
             bd[KMAX - 1] = dv;
@@ -248,7 +263,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
               }
             }
           }
+          }
         }
+      };
+      fetch(0, va);
+      for (int c = 0; c < p.bn; c += 64) {                       // bn is a multiple of 64 (128 or 256)
+        tmem_ld_wait();                                          // chunk c landed
+        fetch(c + 32, vb);
+        scan(c, va);
+        tmem_ld_wait();                                          // chunk c+32 landed
+        if (c + 64 < p.bn) {
+          fetch(c + 64, va);
+        } else {                                                 // all of this accumulator has been read
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        scan(c + 32, vb);
       }
       if (row_ok) {
 #pragma unroll
@@ -290,20 +320,26 @@ static int knn_tc_launch_t(const CUtensorMap& mc, const KnnTcParams& p, size_t s
 }
 
 int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int normalize,
-                  int32_t* idx, float* dist, float* workspace, cudaStream_t st) {
+                  const float* row_sumsq, int32_t* idx, float* dist, float* workspace, cudaStream_t st) {
   const int64_t M = (int64_t)B * N;
   float* rinv = workspace;
   float* sq = workspace + M + 128;
+  KnnTcParams p;
+  p.normalize = normalize;
+  if (row_sumsq) {
+    p.rinv = nullptr; p.sq = row_sumsq;
+  } else {
   int lpr = 32;
   while (lpr > 1 && lpr * 4 > C) lpr >>= 1;               // power of two, <= C/4
   const int rows_per_block = 8 * (32 / lpr);
   knn_rownorm_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(
       x, M, C, normalize, lpr, rinv, sq);
   if (int rc = check_launch("knn_rownorm")) return rc;
-  KnnTcParams p;
+    p.rinv = rinv; p.sq = sq;
+  }
   p.N = N; p.C = C; p.kk = kk; p.d = d; p.k = k; p.M = M;
   p.bn = N >= TC_BM ? N : TC_BM;
-  p.rinv = rinv; p.sq = sq; p.idx = idx; p.dist = dist;
+  p.idx = idx; p.dist = dist;
   uint32_t cols = 32;
   while ((int)cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;

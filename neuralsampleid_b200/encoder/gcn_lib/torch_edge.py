@@ -57,11 +57,12 @@ class DenseDilatedKnnGraph(nn.Module):
         self.dilation, self.stochastic, self.epsilon, self.k = dilation, stochastic, epsilon, k
         self._dilated = DenseDilated(k, dilation, stochastic, epsilon)
 
-    def knn_nodes(self, x_nodes: torch.Tensor, B: int, N: int) -> torch.Tensor:
-        """node-major (B*N, C) -> int32 (B, N, k)."""
+    def knn_nodes(self, x_nodes: torch.Tensor, B: int, N: int, row_sumsq=None) -> torch.Tensor:
+        """node-major (B*N, C) -> int32 (B, N, k).  ``row_sumsq``: per-node sum of squares already
+        produced by the GEMM that wrote x_nodes (skips the kNN's own norm pass)."""
         if self.stochastic and self.training:
             raise NotImplementedError("stochastic dilation is not supported")
-        return ops.knn(x_nodes, B, N, self.k, self.dilation, normalize=True)
+        return ops.knn(x_nodes, B, N, self.k, self.dilation, normalize=True, row_sumsq=row_sumsq)
 
     def forward(self, x, y=None, relative_pos=None):
         if y is not None:

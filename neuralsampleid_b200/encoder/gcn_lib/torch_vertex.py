@@ -119,11 +119,13 @@ class Grapher(nn.Module):
         if self.training:
             raise RuntimeError("Grapher.forward_nodes is the eval path; training goes through "
                                "neuralsampleid_b200.autograd")
-        y = ops.linear(x, self._folded("fc1"))
+        # the fc1 epilogue also accumulates sum_c y^2 per node, which the kNN needs for F.normalize
+        rs = torch.zeros((x.shape[0],), device=x.device, dtype=torch.float32) if nn_idx is None else None
+        y = ops.linear(x, self._folded("fc1"), row_sumsq=rs)
+        if nn_idx is None:
+            nn_idx = self.graph_conv.dilated_knn_graph.knn_nodes(y, B, N, rs)
         if taps is not None:
             taps["fc1"] = y
-            if nn_idx is None:
-                nn_idx = self.graph_conv.dilated_knn_graph.knn_nodes(y, B, N)
             taps["idx"] = nn_idx
         g = self.graph_conv.forward_nodes(y, B, N, nn_idx)
         return ops.linear(g, self._folded("fc2"), residual=x)

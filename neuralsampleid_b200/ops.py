@@ -77,7 +77,7 @@ def nodes_to_nchw(x: torch.Tensor, B: int, N: int) -> torch.Tensor:
 
 
 def knn(x: torch.Tensor, B: int, N: int, k: int, dilation: int = 1, normalize: bool = True,
-        return_dist: bool = False, engine: Optional[int] = None):
+        return_dist: bool = False, engine: Optional[int] = None, row_sumsq: Optional[torch.Tensor] = None):
     """Dense dilated kNN over node-major features -> int32 (B, N, k) [, fp32 (B, N, k)]."""
     x = _chk(x, name="x")
     Cc = x.shape[1]
@@ -89,7 +89,7 @@ def knn(x: torch.Tensor, B: int, N: int, k: int, dilation: int = 1, normalize: b
     ws_bytes = int(lib.grafp_knn_workspace_bytes(B, N, Cc, k, dilation)) if eng != _lib.ENGINE_SIMT else 0
     ws = torch.empty((ws_bytes // 4,), device=x.device, dtype=torch.float32) if ws_bytes else None
     with torch.cuda.device(x.device):
-        check(lib.grafp_knn_fwd(_ptr(x), B, N, Cc, k, dilation, int(normalize), eng, _ptr(idx),
+        check(lib.grafp_knn_fwd(_ptr(x), B, N, Cc, k, dilation, int(normalize), eng, _ptr(row_sumsq), _ptr(idx),
                                 _ptr(dist), _ptr(ws), ws_bytes, _stream(x)), "knn_fwd")
     return (idx, dist) if return_dist else idx
 
@@ -159,10 +159,10 @@ def tc_splits(w: torch.Tensor):
 
 
 def linear(a1: torch.Tensor, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
-           tap3_nodes: int = 0, engine: Optional[int] = None) -> torch.Tensor:
+           tap3_nodes: int = 0, engine: Optional[int] = None, row_sumsq=None) -> torch.Tensor:
     """ops.gemm over a prepared ``_prep.Linear``."""
     return gemm(a1, lin.w, lin.scale, lin.shift, act, act_param, residual, a2, lin.groups, tap3_nodes,
-                engine, None, lin.w_split, lin.w_split_bf16)
+                engine, None, lin.w_split, lin.w_split_bf16, row_sumsq)
 
 
 def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
@@ -170,7 +170,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
          residual: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          groups: int = 1, tap3_nodes: int = 0, engine: Optional[int] = None,
          out: Optional[torch.Tensor] = None, w_split: Optional[torch.Tensor] = None,
-         w_split_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
+         w_split_bf16: Optional[torch.Tensor] = None, row_sumsq: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = act(scale * [a1 | a2] @ w.T + shift) + residual  (per-group, see include/grafp.h).
 
     a1: (M, groups*k1) (or the (2M', Cin) node matrix in tap3 mode), a2: (M, groups*k2) or None,
@@ -209,6 +209,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     else:
         args.residual, args.ldr = None, 0
     args.y, args.ldy = out.data_ptr(), out.stride(0)
+    args.row_sumsq = row_sumsq.data_ptr() if row_sumsq is not None else None
     args.m, args.n, args.groups = M, n, groups
     args.act, args.act_param = act_code(act) if not isinstance(act, int) else act, act_param
     args.tap3_nodes = tap3_nodes

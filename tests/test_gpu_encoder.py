@@ -195,7 +195,7 @@ def test_dygraph_dilated_matches_golden(golden_dir):
         ok = ~diff
         a = y.squeeze(-1).transpose(1, 2)[ok]
         b = yg.squeeze(-1).transpose(1, 2)[ok]
-        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(a, b, rtol=2e-4, atol=2e-4)      # bf16x3 engine: ~1e-5 of the output scale
 
 
 def test_grapher_module_api_matches_oracle():

@@ -92,6 +92,27 @@ def test_knn_engines(B, C, N, k, d, engine):
     _knn_check(x, k, d, tol=4e-6 if engine == "simt" else 1e-5, engine=engine)
 
 
+def test_knn_with_row_sumsq_from_gemm_epilogue():
+    """The fc1 GEMM epilogue accumulates sum_c y^2 per node; the kNN then skips its own norm pass."""
+    ops = _ops()
+    from neuralsampleid_b200 import _prep
+    B, N, C = 5, 256, 64
+    a = synth.synth_normal((B * N, C), 1).to(DEV)
+    w = (synth.synth_normal((C, C), 2) / 8.0).to(DEV)
+    lin = _prep.make_linear(w, None, None)
+    rs = torch.zeros(B * N, device=DEV)
+    y = ops.linear(a, lin, row_sumsq=rs)
+    assert torch.allclose(rs.cpu(), (y.cpu().double() ** 2).sum(1).float(), rtol=1e-5)
+    got = ops.knn(y, B, N, 3, 1, row_sumsq=rs).cpu().long()
+    x = y.cpu().view(B, N, C).transpose(1, 2).unsqueeze(-1).contiguous()
+    edge, dist = O.dilated_knn_graph(x, 3, 1)
+    tie = O.knn_tie_rows(dist, 3, 1e-5)
+    assert not ((got != edge[0]).any(-1) & ~tie).any()
+    rs2 = torch.zeros(B * N, device=DEV)                       # exact engine accumulates the same sums
+    ops.linear(a, lin, row_sumsq=rs2, engine=1)
+    assert torch.allclose(rs2, rs, rtol=1e-4)
+
+
 def test_knn_post_relu_features_and_duplicates():
     # post-ReLU style features with exact duplicates and all-zero nodes: the reference has exact
     # ties here; every differing row must be a documented tie and indices must stay valid
