@@ -250,19 +250,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
           const int q = q4 + u;
-          const float dv = __fadd_rn(fmaf(v[q], -2.0f, sqi), sj[u]);     // (sq_i + (-2 dot)) + sq_j
+          float dv = __fadd_rn(fmaf(v[q], -2.0f, sqi), sj[u]);           // (sq_i + (-2 dot)) + sq_j
           const int jl = c + q - lo_col;
-          if ((unsigned)jl < ncols && dv < bd[KMAX - 1]) {
-            bd[KMAX - 1] = dv;
-            bj[KMAX - 1] = jl;
+          // Branch-free sorted insertion (a select network): rows of a warp are independent, so a
+          // data-dependent branch here would be taken by some lane at almost every column and
+          // serialise the warp.  Strict '<' keeps the lower index ahead on exact ties.
+          if (!((unsigned)jl < ncols)) dv = INFINITY;                     // outside this row's graph
+          bool lt[KMAX];
 #pragma unroll
-            for (int t = KMAX - 1; t > 0; --t) {
-              if (bd[t] < bd[t - 1]) {
-                const float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td;
-                const int tj = bj[t]; bj[t] = bj[t - 1]; bj[t - 1] = tj;
-              }
-            }
+          for (int t = 0; t < KMAX; ++t) lt[t] = dv < bd[t];
+#pragma unroll
+          for (int t = KMAX - 1; t > 0; --t) {
+            bd[t] = lt[t - 1] ? bd[t - 1] : (lt[t] ? dv : bd[t]);
+            bj[t] = lt[t - 1] ? bj[t - 1] : (lt[t] ? jl : bj[t]);
           }
+          bd[0] = lt[0] ? dv : bd[0];
+          bj[0] = lt[0] ? jl : bj[0];
           }
         }
       };

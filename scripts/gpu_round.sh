@@ -5,7 +5,7 @@ OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r1}
 echo "== smoke" ; timeout 600 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/${TAG}_smoke.log
 echo "== tests"; timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider > $OUT/${TAG}_tests.log 2>&1; echo "rc=$?"; tail -12 $OUT/${TAG}_tests.log | cut -c1-200
 echo "== bench (default)"; timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "rc=$?"; cut -c1-300 $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
-echo "== bench (no cluster multicast)"; GRAFP_TC_CLUSTER=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_nomc.json 2> $OUT/${TAG}_bench_nomc.err; echo "rc=$?"; cut -c1-200 $OUT/${TAG}_bench_nomc.json
+echo "== bench (eager, no graph)"; timeout 900 python bench.py --no-graph --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_eager.json 2> $OUT/${TAG}_bench_eager.err; echo "rc=$?"; cut -c1-200 $OUT/${TAG}_bench_eager.json; tail -2 $OUT/${TAG}_bench_eager.err
 echo "== bench (3xtf32)"; timeout 900 python bench.py --engine 3xtf32 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_3xtf32.json 2> $OUT/${TAG}_bench_3xtf32.err; echo "rc=$?"; cut -c1-200 $OUT/${TAG}_bench_3xtf32.json
 echo "== bench (bf16)"; timeout 900 python bench.py --engine bf16 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_bf16.json 2> $OUT/${TAG}_bench_bf16.err; echo "rc=$?"; cut -c1-200 $OUT/${TAG}_bench_bf16.json
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/${TAG}_bench_ref.json 2>&1; cut -c1-200 $OUT/${TAG}_bench_ref.json
