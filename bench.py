@@ -189,8 +189,10 @@ class KernelTimer:
         if name == "grafp_gemm_fwd":
             m, k, n, g = self.last_gemm
             extra = 2.0 * m * k * n / g
-        elif name in ("grafp_knn_fwd", "grafp_mr_aggregate_fwd"):
-            extra = tuple(int(v) if isinstance(v, int) else v for v in args[1:5])
+        elif name == "grafp_knn_fwd":
+            info = "knn N=%d C=%d" % (args[2], args[3])
+        elif name == "grafp_mr_aggregate_fwd":
+            info = "aggregate N=%d C=%d" % (args[3], args[4])
         self.records.append((info, name, s, e, extra))
         return rc
 

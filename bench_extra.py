@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Secondary measurements for BASELINE.json configs 3-5 (bench.py is the judged contract, configs[1]).
+
+  python bench_extra.py train  [--pairs 32] [--steps 10]     config 3: contrastive train step (N ranks via torchrun)
+  python bench_extra.py db     [--segments 1000000]          config 4: spectrogram segments -> 128-d fingerprints
+  python bench_extra.py sweep                                 config 5: dynamic-graph stress sweep (kNN + aggregate)
+  python bench_extra.py chunks                                generate.py call shape: chunks of 128 segments
+
+Each mode prints one JSON line (rank 0).  Synthetic data, random-init weights.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+CFG = dict(n_mels=64, n_frames=128, patch_bins=4, patch_frames=8, n_filters=8, tau=0.05,
+           d=128, h=1024, u=32, dim=2048, arch="grafp", bsz_train=256, lr=8.0e-5)
+
+
+def _setup():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, dev
+
+
+def _model(dev, k):
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    from neuralsampleid_b200.simclr.simclr import SimCLR
+    torch.manual_seed(0)
+    model = SimCLR(CFG, encoder=GraphEncoder(cfg=CFG, in_channels=CFG["n_filters"], k=k))
+    return model.to(dev)
+
+
+def _timed(fn, steps, world, dev):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def mode_train(args):
+    from neuralsampleid_b200.train import FusedClipAdam, train_step
+    world, rank, dev = _setup()
+    model = _model(dev, 5).train()                     # train.py default --k 5
+    opt = FusedClipAdam(model.parameters(), lr=CFG["lr"], max_norm=1.0)
+    g = torch.Generator().manual_seed(2 + rank)
+    x_i = torch.randn((args.pairs, 64, 128), generator=g).to(dev)
+    x_j = (x_i.cpu() + 0.1 * torch.randn((args.pairs, 64, 128), generator=g)).to(dev)
+    losses = []
+
+    def step():
+        losses.append(train_step(model, x_i, x_j, CFG, opt, skip_nan=False))
+    for _ in range(3):
+        step()
+    ms = _timed(step, args.steps, world, dev)
+    if rank == 0:
+        print(json.dumps({"mode": "train", "metric": "contrastive train step encoder-segments/s",
+                          "value": 2 * args.pairs * world * args.steps / (ms * 1e-3), "unit": "segments/s",
+                          "n_gpus": world, "ms_per_step": ms / args.steps, "pairs_per_gpu": args.pairs,
+                          "global_pairs": args.pairs * world, "loss_first": float(losses[0]),
+                          "loss_last": float(losses[-1]),
+                          "config": "SimCLR(GraphEncoder t, k=5) fwd+bwd, NT-Xent (global negatives via NCCL "
+                                    "all-gather), summed grad all-reduce, clip 1.0, Adam 8e-5"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def mode_db(args):
+    from neuralsampleid_b200.graphed import GraphedSimCLR
+    from neuralsampleid_b200.parallel import shard_range
+    world, rank, dev = _setup()
+    model = _model(dev, 3).eval()
+    B = args.batch
+    lo, hi = shard_range(args.segments, rank, world)
+    n_batches = (hi - lo + B - 1) // B
+    g = GraphedSimCLR(model, B)
+    spec = torch.randn((B, 64, 128), generator=torch.Generator().manual_seed(rank)).pin_memory()
+    out = torch.empty((n_batches * B, 128), dtype=torch.float32).pin_memory()     # this rank's slice of the DB
+    for _ in range(2):
+        g(spec.to(dev))
+    it = [0]
+
+    def step():
+        i = it[0]
+        g.input.copy_(spec, non_blocking=True)
+        g.replay()
+        out[i * B:(i + 1) * B].copy_(g.z, non_blocking=True)
+        it[0] = i + 1
+    t0 = time.perf_counter()
+    ms = _timed(step, n_batches, world, dev)
+    wall = time.perf_counter() - t0
+    if rank == 0:
+        print(json.dumps({"mode": "db", "metric": "reference-database fingerprinting segments/s (spectrogram -> 128-d)",
+                          "value": args.segments / (ms * 1e-3), "unit": "segments/s", "n_gpus": world,
+                          "segments": args.segments, "batch": B, "seconds": ms * 1e-3, "wall_seconds": wall,
+                          "h2d_bytes_per_segment": 64 * 128 * 4, "d2h_bytes_per_segment": 128 * 4,
+                          "config": "SimCLR eval (peak extractor + GraphEncoder t k=3 + projector + L2 norm), CUDA graph "
+                                    "replay per batch, pinned host in/out, contiguous segment ranges per rank"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def mode_sweep(args):
+    from neuralsampleid_b200 import ops
+    world, rank, dev = _setup()
+    rows = []
+    for N in (256, 512, 1024, 2048):
+        for k in (9, 16, 32):
+            for d in (2,):
+                B = (1 << 20) // N // 4               # 2^18 nodes per call (keeps every case < 1 s)
+                x = torch.randn((B * N, 64), device=dev, generator=torch.Generator(device=dev).manual_seed(4))
+                idx = ops.knn(x, B, N, k, d)
+                ops.mr_aggregate(x, idx, B, N)
+                torch.cuda.synchronize()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+                idx = ops.knn(x, B, N, k, d)
+                ev[1].record()
+                m = ops.mr_aggregate(x, idx, B, N)
+                ev[2].record()
+                torch.cuda.synchronize()
+                t_knn, t_agg = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+                agg_bytes = B * (2 * N * 64 * 4 + 4 * N * k)
+                rows.append({"N": N, "k": k, "d": d, "graphs": B, "knn_ms": round(t_knn, 3), "agg_ms": round(t_agg, 3),
+                             "agg_GBps": round(agg_bytes / (t_agg * 1e-3) / 1e9, 1),
+                             "knn_engine": "tcgen05" if (N <= 256 and k * d <= 16) else "fp32 simt"})
+    if rank == 0:
+        print(json.dumps({"mode": "sweep", "metric": "dynamic-graph stress sweep (C=64, dilation 2)", "rows": rows}))
+
+
+def mode_chunks(args):
+    from neuralsampleid_b200.graphed import GraphedSimCLR
+    world, rank, dev = _setup()
+    model = _model(dev, 3).eval()
+    x = torch.randn((128, 64, 128), device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model(x, x)
+    ms_eager = _timed(lambda: model._one_view(x), 20, 1, dev) / 20
+    g = GraphedSimCLR(model, 128)
+    g(x)
+    ms_graph = _timed(g.replay, 50, 1, dev) / 50
+    if rank == 0:
+        print(json.dumps({"mode": "chunks", "metric": "generate.py call shape: 128-segment chunk, one view",
+                          "eager_ms": ms_eager, "graph_ms": ms_graph, "eager_seg_s": 128 / (ms_eager * 1e-3),
+                          "graph_seg_s": 128 / (ms_graph * 1e-3)}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["train", "db", "sweep", "chunks"])
+    ap.add_argument("--pairs", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--segments", type=int, default=1000000)
+    ap.add_argument("--batch", type=int, default=4096)
+    args = ap.parse_args()
+    with torch.no_grad():
+        {"train": mode_train, "db": mode_db, "sweep": mode_sweep, "chunks": mode_chunks}[args.mode](args)
+
+
+if __name__ == "__main__":
+    main()
