@@ -66,7 +66,7 @@ def _timed(fn, steps, world, dev):
 
 
 def mode_train(args):
-    from neuralsampleid_b200.train import FusedClipAdam, train_step
+    from neuralsampleid_b200.train import FusedClipAdam, GraphedTrainStep, train_step
     world, rank, dev = _setup()
     model = _model(dev, 5).train()                     # train.py default --k 5
     opt = FusedClipAdam(model.parameters(), lr=CFG["lr"], max_norm=1.0)
@@ -76,14 +76,22 @@ def mode_train(args):
     losses = []
 
     def step():
-        losses.append(train_step(model, x_i, x_j, CFG, opt, skip_nan=False))
+        losses.append(train_step(model, x_i, x_j, CFG, opt).clone())
     for _ in range(3):
         step()
-    ms = _timed(step, args.steps, world, dev)
+    ms_eager = _timed(step, args.steps, world, dev)
+    g = GraphedTrainStep(model, CFG, opt, args.pairs)
+
+    def gstep():
+        losses.append(g(x_i, x_j).clone())
+    for _ in range(2):
+        gstep()
+    ms = _timed(gstep, args.steps, world, dev)
     if rank == 0:
         print(json.dumps({"mode": "train", "metric": "contrastive train step encoder-segments/s",
                           "value": 2 * args.pairs * world * args.steps / (ms * 1e-3), "unit": "segments/s",
-                          "n_gpus": world, "ms_per_step": ms / args.steps, "pairs_per_gpu": args.pairs,
+                          "n_gpus": world, "ms_per_step": ms / args.steps, "ms_per_step_eager": ms_eager / args.steps,
+                          "launch": "cuda graph replay of the whole step", "pairs_per_gpu": args.pairs,
                           "global_pairs": args.pairs * world, "loss_first": float(losses[0]),
                           "loss_last": float(losses[-1]),
                           "config": "SimCLR(GraphEncoder t, k=5) fwd+bwd, NT-Xent (global negatives via NCCL "

@@ -224,6 +224,12 @@ int grafp_sq_norm(const float* g, int64_t n, double* out_accum, void* stream);
 int grafp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                          float beta2, float eps, int step, float max_norm, const double* sq_norm,
                          void* stream);
+/* CUDA-graph-capturable variant: the 1-based step counter (incremented here), the learning rate and
+ * an optional NaN guard (the loss; a NaN skips the whole update, train.py:65-68) are read from
+ * device memory, so a captured step stays valid across replays and LR-schedule changes. */
+int grafp_adam_clip_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                             float beta1, float beta2, float eps, int* step_dev, float max_norm,
+                             const double* sq_norm, const float* loss_guard, void* stream);
 int grafp_add_inplace(float* y, const float* x, int64_t n, void* stream);
 
 #ifdef __cplusplus

@@ -66,6 +66,7 @@ SIGNATURES = {
     "grafp_peak_extract_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "grafp_sq_norm": [_P, _L, _P, _P],
     "grafp_adam_clip_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P, _P],
+    "grafp_adam_clip_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _P, _F, _P, _P, _P],
     "grafp_add_inplace": [_P, _P, _L, _P],
 }
 SPECIAL = {"grafp_knn_workspace_bytes": ([_I, _I, _I, _I, _I], C.c_size_t),

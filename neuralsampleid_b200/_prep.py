@@ -8,10 +8,20 @@ from typing import Optional, Tuple
 import torch
 
 
+_epoch = 0
+
+
+def bump_epoch() -> None:
+    """Called by code that updates parameters through raw pointers (the fused optimizer kernels, CUDA
+    graph replays): torch's version counters do not see those writes."""
+    global _epoch
+    _epoch += 1
+
+
 def sig(*tensors) -> tuple:
     """Cheap identity+version signature of parameters, used to invalidate prepared weights after
     optimizer steps / load_state_dict / .to()."""
-    return tuple((t.data_ptr(), t._version, t.device.index) for t in tensors if t is not None)
+    return (_epoch,) + tuple((t.data_ptr(), t._version, t.device.index) for t in tensors if t is not None)
 
 
 @torch.no_grad()

@@ -380,6 +380,36 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
+// Graph-capturable form: the step counter, the learning rate and the NaN guard live in device memory
+__global__ void adam_step_counter_kernel(int* step, const float* loss_guard) {
+  if (loss_guard && isnan(*loss_guard)) return;
+  *step += 1;
+}
+
+__global__ void adam_clip_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                     const float* __restrict__ lr_dev, float b1, float b2, float eps,
+                                     const int* __restrict__ step_dev, float max_norm,
+                                     const double* __restrict__ sqnorm, const float* __restrict__ loss_guard) {
+  if (loss_guard && isnan(*loss_guard)) return;            // train.py:65-68: skip the batch
+  float coef = 1.0f;
+  if (max_norm > 0.0f) {
+    const float total = (float)sqrt(*sqnorm);
+    coef = fminf(max_norm / (total + 1e-6f), 1.0f);
+  }
+  const int t = *step_dev;
+  const float bc1 = 1.0f - powf(b1, (float)t), bc2 = 1.0f - powf(b2, (float)t);
+  const float step = *lr_dev / bc1, rs = 1.0f / sqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step * (mi / (sqrtf(vi) * rs + eps));
+  }
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
@@ -539,6 +569,19 @@ int grafp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n
   adam_clip_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2,
                                                               max_norm, sq_norm);
   return check_launch("adam_clip_step");
+}
+
+int grafp_adam_clip_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                             float beta1, float beta2, float eps, int* step_dev, float max_norm,
+                             const double* sq_norm, const float* loss_guard, void* stream) {
+  GRAFP_REQUIRE(n >= 0 && lr_dev && step_dev && (n == 0 || (p && g && m && v)), "adam_clip_step_dev: bad arguments");
+  GRAFP_REQUIRE(max_norm <= 0.0f || sq_norm, "adam_clip_step_dev: clipping needs the squared gradient norm");
+  adam_step_counter_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev, loss_guard);
+  if (int rc = check_launch("adam_step_counter")) return rc;
+  if (n == 0) return 0;
+  adam_clip_dev_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps,
+                                                                  step_dev, max_norm, sq_norm, loss_guard);
+  return check_launch("adam_clip_step_dev");
 }
 
 int grafp_add_inplace(float* y, const float* x, int64_t n, void* stream) {

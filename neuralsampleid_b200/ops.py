@@ -427,6 +427,13 @@ def adam_clip_step(p, g, m, v, lr, beta1, beta2, eps, step, max_norm, sq) -> Non
                                                step, max_norm, _ptr(sq), _stream(p)), "adam_clip_step")
 
 
+def adam_clip_step_dev(p, g, m, v, lr_dev, beta1, beta2, eps, step_dev, max_norm, sq, loss_guard) -> None:
+    with torch.cuda.device(p.device):
+        check(_lib.load().grafp_adam_clip_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(lr_dev),
+                                                   beta1, beta2, eps, _ptr(step_dev), max_norm, _ptr(sq),
+                                                   _ptr(loss_guard), _stream(p)), "adam_clip_step_dev")
+
+
 def add_inplace(y: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(y.device):
         check(_lib.load().grafp_add_inplace(_ptr(y), _ptr(x), y.numel(), _stream(y)), "add_inplace")

@@ -1,6 +1,7 @@
 """The contrastive train step of train.py:48-83 as a fused driver: both views forward in train mode,
 NT-Xent over the (global) batch, hand-written backward, gradient all-reduce, clip_grad_norm_(1.0)
 and Adam -- every arithmetic step a libgrafp_sm100a kernel, no autograd engine in the loop.
+`GraphedTrainStep` captures the whole step into one CUDA graph.
 
 Data parallelism follows nn.DataParallel's semantics (train.py:117-120) with one process per GPU:
 the global batch is split on dim 0, BatchNorm statistics are per rank, the loss sees the whole
@@ -14,7 +15,7 @@ from typing import Dict, Iterable, Optional
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _prep, ops
 from .autograd import view_bwd, view_fwd
 
 
@@ -45,8 +46,11 @@ class FusedClipAdam:
                 p.grad = gview
                 self.views[p] = gview
                 off += k
-        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
-        self.step_count = 0
+        self._lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        # step counter and learning rate also live on the device so a CUDA-graph-captured step
+        # (GraphedTrainStep) stays valid across replays and LR-schedule changes
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.lr_dev = torch.full((1,), lr, device=dev, dtype=torch.float32)
         self.sq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.last_grad_norm: Optional[torch.Tensor] = None
 
@@ -59,16 +63,27 @@ class FusedClipAdam:
             if view is not None:
                 ops.add_inplace(view, g.reshape(view.shape).contiguous())
 
-    def step(self) -> None:
-        self.step_count += 1
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float) -> None:          # e.g. CosineAnnealingLR per epoch (train.py:127)
+        self._lr = float(value)
+        self.lr_dev.fill_(self._lr)
+
+    @property
+    def step_count(self) -> int:
+        return int(self.step_dev.item())
+
+    def step(self, loss_guard: Optional[torch.Tensor] = None) -> None:
+        """clip_grad_norm_(max_norm) + Adam.  ``loss_guard``: a device scalar; NaN skips the update."""
         self.sq.zero_()
         ops.sq_norm(self.flat_g, self.sq)
         self.last_grad_norm = self.sq
-        ops.adam_clip_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1],
-                           self.eps, self.step_count, self.max_norm, self.sq)
-        # bump the version counters so prepared (folded / split) weights are rebuilt
-        for p in self.params:
-            p.data = p.data
+        ops.adam_clip_step_dev(self.flat_p, self.flat_g, self.m, self.v, self.lr_dev, self.betas[0],
+                               self.betas[1], self.eps, self.step_dev, self.max_norm, self.sq, loss_guard)
+        _prep.bump_epoch()          # parameters changed through raw pointers: rebuild prepared weights
 
     def grad_norm(self) -> float:
         return float(self.sq.sqrt().item())
@@ -101,8 +116,6 @@ def train_step(model, x_i: torch.Tensor, x_j: torch.Tensor, cfg, optimizer: Fuse
             dist.all_reduce(loss, group=group)
         else:
             lse_all = lse
-        if skip_nan and bool(torch.isnan(loss).item()):
-            return loss.reshape(())
         one = torch.ones(1, device=z_loc.device, dtype=torch.float32)
         dz = ops.ntxent_bwd(z_all, lse_all, tau, one, rank * rows, rows).view(-1, 2, z_loc.shape[1])
         grads: Dict = {}
@@ -111,5 +124,51 @@ def train_step(model, x_i: torch.Tensor, x_j: torch.Tensor, cfg, optimizer: Fuse
         optimizer.accumulate(grads)
         if world > 1:
             dist.all_reduce(optimizer.flat_g, op=dist.ReduceOp.SUM, group=group)
-        optimizer.step()
+        optimizer.step(loss if skip_nan else None)     # a NaN loss skips the update on the device
     return loss.reshape(())
+
+
+class GraphedTrainStep:
+    """One contrastive train step captured into a CUDA graph (every arithmetic node is a
+    libgrafp_sm100a kernel; the NCCL all-gather / all-reduce are captured too).  At the reference's
+    per-GPU batch (32 pairs) the eager step is bound by ~2000 host-side launches; replaying the
+    graph leaves only the kernels.
+
+        g = GraphedTrainStep(model, cfg, optimizer, pairs=32)
+        loss = g(x_i, x_j)            # copies the inputs into the static buffers and replays
+    """
+
+    def __init__(self, model, cfg, optimizer: FusedClipAdam, pairs: int, group=None, warmup: int = 2):
+        if not model.training:
+            raise RuntimeError("GraphedTrainStep needs model.train()")
+        dev = optimizer.flat_p.device
+        self.model, self.optimizer = model, optimizer
+        self.x_i = torch.zeros((pairs, cfg["n_mels"], cfg["n_frames"]), device=dev, dtype=torch.float32)
+        self.x_j = torch.zeros_like(self.x_i)
+        # warm-up steps run for real: snapshot and restore every piece of mutable state
+        keep = [optimizer.flat_p.clone(), optimizer.m.clone(), optimizer.v.clone(), optimizer.step_dev.clone()]
+        bufs = [(b, b.clone()) for b in model.buffers()]
+        self.x_i.normal_(generator=torch.Generator(device=dev).manual_seed(1))
+        self.x_j.copy_(self.x_i).add_(0.1)
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                train_step(model, self.x_i, self.x_j, cfg, optimizer, group)
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = train_step(model, self.x_i, self.x_j, cfg, optimizer, group)
+        with torch.no_grad():
+            optimizer.flat_p.copy_(keep[0]); optimizer.m.copy_(keep[1]); optimizer.v.copy_(keep[2])
+            optimizer.step_dev.copy_(keep[3])
+            for b, saved in bufs:
+                b.copy_(saved)
+        _prep.bump_epoch()
+
+    def __call__(self, x_i: torch.Tensor, x_j: torch.Tensor) -> torch.Tensor:
+        self.x_i.copy_(x_i, non_blocking=True)
+        self.x_j.copy_(x_j, non_blocking=True)
+        self.graph.replay()
+        _prep.bump_epoch()
+        return self.loss

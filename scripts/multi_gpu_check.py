@@ -73,12 +73,18 @@ def main():
             o2.accumulate(grads)
             o2.step()
         dl = abs(loss.item() - l2.item())
-        upd = (flat - o2.flat_p).abs().max().item()
-        # note: BatchNorm running statistics differ by design (rank r keeps its own, the emulation
-        # applies all shards' updates to one module); parameters and loss must agree
-        ok = ok and dl < 1e-4 * abs(l2.item()) and upd < 0.05 * CFG["lr"]
-        msg += "; loss %.6f vs %.6f; max param diff %.3e (lr %.1e); grad norm %.4f vs %.4f" % (
-            loss.item(), l2.item(), upd, CFG["lr"], opt.grad_norm(), o2.grad_norm())
+        # The all-reduced flat gradient must equal the emulation's (atomics make the summation
+        # order differ: relative L2 1e-4).  Post-Adam parameters are NOT compared element-wise: the
+        # first Adam step moves every weight by lr * sign(grad), and parameters whose true gradient
+        # is zero (biases in front of BatchNorm) carry sign noise.  BatchNorm running statistics
+        # differ by design (each rank keeps its own, as under nn.DataParallel replicas).
+        g1, g2 = opt.flat_g.double(), o2.flat_g.double()
+        rel = float((g1 - g2).norm() / g2.norm())
+        big = g2.abs() > 1e-3 * float(g2.abs().max())
+        upd = float((flat - o2.flat_p)[big].abs().max())
+        ok = ok and dl < 1e-4 * abs(l2.item()) and rel < 1e-4 and upd < 0.05 * CFG["lr"]
+        msg += "; loss %.6f vs %.6f; grad rel diff %.2e; max update diff on non-noise grads %.2e (lr %.1e); grad norm %.4f vs %.4f" % (
+            loss.item(), l2.item(), rel, upd, CFG["lr"], opt.grad_norm(), o2.grad_norm())
         print("MULTI_GPU_CHECK %s world=%d %s" % ("PASS" if ok else "FAIL", world, msg), flush=True)
     dist.barrier()
     dist.destroy_process_group()
