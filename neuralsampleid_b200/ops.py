@@ -159,10 +159,10 @@ def tc_splits(w: torch.Tensor):
 
 
 def linear(a1: torch.Tensor, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
-           tap3_nodes: int = 0, engine: Optional[int] = None, row_sumsq=None) -> torch.Tensor:
+           tap3_nodes: int = 0, engine: Optional[int] = None, row_sumsq=None, out=None) -> torch.Tensor:
     """ops.gemm over a prepared ``_prep.Linear``."""
     return gemm(a1, lin.w, lin.scale, lin.shift, act, act_param, residual, a2, lin.groups, tap3_nodes,
-                engine, None, lin.w_split, lin.w_split_bf16, row_sumsq)
+                engine, out, lin.w_split, lin.w_split_bf16, row_sumsq)
 
 
 def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
