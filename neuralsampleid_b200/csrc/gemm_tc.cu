@@ -12,12 +12,13 @@
 //
 // One persistent CTA per SM walks the tile list with n fastest: the CTAs running at the same time
 // share the same 128 rows of A (read from HBM once, L2 hits for the other column tiles) while the
-// weights, a few MB, stay L2-resident.  Warp roles (448 threads):
+// weights, a few MB, stay L2-resident.  Warp roles (480 threads):
 //   warp 0      TMA producer (A from one of two sources or the 3-tap Downsample view, W hi/lo)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
 //   warps 2-5   epilogue: TMEM -> registers -> scale/shift/activation/residual -> 128B-swizzled
 //               staging tile -> TMA store (coalesced, clipped at the matrix edge)
 //   warps 6-13  transform: tf32 hi / lo split of the A stage (hi = top 19 bits, lo = v - hi exact)
+//   warp 14     second TMA producer (weight tiles) of the bf16 engines
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.  Pipelines: full[s] (TMA -> transform), xf[s] (transform -> MMA),
 // empty[s] (MMA commit -> TMA), tmem_full[b] (MMA commit -> epilogue), tmem_empty[b].
@@ -28,7 +29,8 @@
 namespace grafp {
 
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 448;
+constexpr int TC_THREADS = 480;
+constexpr int TC_RAW = 3;                       // depth of the fp32 A staging ring (bf16 engines)
 constexpr int TC_XF_THREADS = 256;
 constexpr int TC_STORE_BYTES = TC_BM * 32 * 4;   // one 128 x 32 fp32 staging tile
 
@@ -90,6 +92,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t xf_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t raw_full_bar[TC_RAW];
+  __shared__ __align__(8) uint64_t raw_empty_bar[TC_RAW];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -100,14 +104,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   constexpr uint32_t kAop = TC_BM * kOpRow;                   // one A operand tile: 8 KB / 16 KB
   constexpr uint32_t kNP = kPasses == 3 ? 2u : 1u;            // operand copies (hi [+ lo])
   const uint32_t b_bytes = (uint32_t)p.bn * kOpRow;
-  const uint32_t stage_bytes = kBf16 ? TC_A_BYTES + kNP * (kAop + b_bytes) : kNP * (TC_A_BYTES + b_bytes);
+  const uint32_t stage_bytes = kNP * (kAop + b_bytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* store_buf = smem;                                  // 2 x 16 KB staging tiles
-  uint8_t* stage0 = smem + 2 * TC_STORE_BYTES;
-  // stage layout   tf32: [A raw = hi | A_lo (3x) | B_hi | B_lo (3x)]
-  //                bf16: [A raw fp32 | A_hi | A_lo (3x) | B_hi | B_lo (3x)]
-  auto a_raw = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
-  auto a_hi = [&](int s) { return a_raw(s) + (kBf16 ? TC_A_BYTES : 0); };
+  // tf32: operand stages [A raw = hi | A_lo (3x) | B_hi | B_lo (3x)]
+  // bf16: a separate ring of TC_RAW fp32 A tiles (freed as soon as the transform has read them, so the
+  //       HBM-latency-bound A loads run up to TC_RAW k-blocks ahead of the MMA), then operand stages
+  //       [A_hi | A_lo (3x) | B_hi | B_lo (3x)]
+  uint8_t* raw0 = smem + 2 * TC_STORE_BYTES;
+  uint8_t* stage0 = raw0 + (kBf16 ? TC_RAW * TC_A_BYTES : 0);
+  auto a_raw = [&](int s) { return kBf16 ? raw0 + (size_t)s * TC_A_BYTES : stage0 + (size_t)s * stage_bytes; };
+  auto a_hi = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return a_hi(s) + kAop; };
   auto b_hi = [&](int s) { return a_hi(s) + kNP * kAop; };
   auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
@@ -131,6 +138,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       mbar_init(&xf_bar[s], TC_XF_THREADS);
       mbar_init(&empty_bar[s], kCluster);
     }
+    for (int r = 0; r < TC_RAW; ++r) {
+      mbar_init(&raw_full_bar[r], 1);
+      mbar_init(&raw_empty_bar[r], TC_XF_THREADS);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 128);
@@ -143,9 +154,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+  if (warp == 0 || warp == 14) {
+    // ===== TMA producers =====
+    // tf32: warp 0 issues A and W of a k-block together.  bf16: warp 0 streams the fp32 A tiles through
+    // the raw ring (gated by the transform), warp 14 streams the W tiles into the operand stages
+    // (gated by the MMA commits), so A prefetch depth is not tied to the MMA's progress.
+    const bool do_a = warp == 0, do_w = kBf16 ? warp == 14 : warp == 0;
+    if (lane == 0 && (do_a || do_w)) {
       uint32_t it = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
         const int nt = (int)(tile % tiles_n);
@@ -156,35 +171,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[s], TC_A_BYTES + kNP * b_bytes);
           const int k = kb * TC_BK;
-          if (p.tap3_rows > 0) {
-            // Downsample: W columns are [tap0 | tap1 | tap2]; taps 1,2 = the (M, 2*Cin) view of
-            // the input, tap 0 = the same view shifted one output row up inside each graph
-            // (3-D map, out-of-range row -1 zero-filled by TMA)
-            if (k < p.tap3_cin) {
-              const int b0 = m0 / p.tap3_rows, j0 = m0 % p.tap3_rows;
-              tma_load_3d(a_raw(s), &tmA2, p.tap3_cin + k, j0 - 1, b0, &full_bar[s]);
-            } else {
-              tma_load_2d(a_raw(s), &tmA1, k - p.tap3_cin, m0, &full_bar[s]);
+          uint64_t* abar;
+          uint8_t* adst;
+          if (kBf16) {
+            const int r = it % TC_RAW;
+            abar = &raw_full_bar[r];
+            adst = a_raw(r);
+            if (do_a) {
+              mbar_wait(&raw_empty_bar[r], ((it / TC_RAW) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(abar, TC_A_BYTES);
             }
-          } else if (k < p.k1) {
-            tma_load_2d(a_raw(s), &tmA1, g * p.k1 + k, m0, &full_bar[s]);
+            if (do_w) {
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[s], kNP * b_bytes);
+            }
           } else {
-            tma_load_2d(a_raw(s), &tmA2, g * p.k2 + (k - p.k1), m0, &full_bar[s]);
+            abar = &full_bar[s];
+            adst = a_raw(s);
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[s], TC_A_BYTES + kNP * b_bytes);
           }
-          if (kCluster == 2) {
-            // my half of the weight tile, multicast to both CTAs of the pair (tmW box = bn/2 rows)
-            const int half = p.bn / 2;
-            const uint32_t off = crank * (uint32_t)half * kOpRow;
-            tma_load_2d_mc(b_hi(s) + off, &tmW, k, g * p.n + n0 + (int)crank * half, &full_bar[s], 0x3);
-            if (kPasses == 3)
-              tma_load_2d_mc(b_lo(s) + off, &tmW, k, p.n_total + g * p.n + n0 + (int)crank * half,
-                             &full_bar[s], 0x3);
-          } else {
-            tma_load_2d(b_hi(s), &tmW, k, g * p.n + n0, &full_bar[s]);
-            if (kPasses == 3) tma_load_2d(b_lo(s), &tmW, k, p.n_total + g * p.n + n0, &full_bar[s]);
+          if (do_a) {
+            if (p.tap3_rows > 0) {
+              // Downsample: W columns are [tap0 | tap1 | tap2]; taps 1,2 = the (M, 2*Cin) view of
+              // the input, tap 0 = the same view shifted one output row up inside each graph
+              // (3-D map, out-of-range row -1 zero-filled by TMA)
+              if (k < p.tap3_cin) {
+                const int b0 = m0 / p.tap3_rows, j0 = m0 % p.tap3_rows;
+                tma_load_3d(adst, &tmA2, p.tap3_cin + k, j0 - 1, b0, abar);
+              } else {
+                tma_load_2d(adst, &tmA1, k - p.tap3_cin, m0, abar);
+              }
+            } else if (k < p.k1) {
+              tma_load_2d(adst, &tmA1, g * p.k1 + k, m0, abar);
+            } else {
+              tma_load_2d(adst, &tmA2, g * p.k2 + (k - p.k1), m0, abar);
+            }
+          }
+          if (do_w) {
+            if (kCluster == 2) {
+              // my half of the weight tile, multicast to both CTAs of the pair (tmW box = bn/2 rows)
+              const int half = p.bn / 2;
+              const uint32_t off = crank * (uint32_t)half * kOpRow;
+              tma_load_2d_mc(b_hi(s) + off, &tmW, k, g * p.n + n0 + (int)crank * half, &full_bar[s], 0x3);
+              if (kPasses == 3)
+                tma_load_2d_mc(b_lo(s) + off, &tmW, k, p.n_total + g * p.n + n0 + (int)crank * half,
+                               &full_bar[s], 0x3);
+            } else {
+              tma_load_2d(b_hi(s), &tmW, k, g * p.n + n0, &full_bar[s]);
+              if (kPasses == 3) tma_load_2d(b_lo(s), &tmW, k, p.n_total + g * p.n + n0, &full_bar[s]);
+            }
           }
         }
       }
@@ -202,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
+          if (kBf16) mbar_wait(&full_bar[s], ph);             // W tiles landed (A comes via xf)
           mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph);
           tc_fence_after();
           if (kBf16) {
@@ -243,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         umma_commit(&tmem_full_bar[buf]);       // accumulator complete
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && warp < 14) {
     // ===== transform (warps 6..13, 256 threads): build the MMA A operand(s) from the fp32 stage =====
     // tf32: hi = v with the 13 low mantissa bits cleared (exactly representable in tf32), lo = v - hi
     //       (exact in fp32, |lo| < 2^-10 |v|; the tensor core reads its top 19 bits), in place.
@@ -258,12 +296,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          const float4* raw = reinterpret_cast<const float4*>(a_raw(s));
+          const int rs = kBf16 ? (int)(it % TC_RAW) : s;
+          mbar_wait(kBf16 ? &raw_full_bar[rs] : &full_bar[s], kBf16 ? (it / TC_RAW) & 1u : ph);
+          const float4* raw = reinterpret_cast<const float4*>(a_raw(rs));
           float4 v[PER];
 #pragma unroll
           for (int i = 0; i < PER; ++i) v[i] = raw[t + TC_XF_THREADS * i];
           if (kBf16) {
+            mbar_arrive(&raw_empty_bar[rs]);            // raw tile is in registers: its slot may be refilled
+            mbar_wait(&empty_bar[s], ph ^ 1u);          // operand stage s free (MMAs of k-block it - S retired)
             uint8_t* hi = a_hi(s);
             uint8_t* lo = a_lo(s);
 #pragma unroll
@@ -513,15 +554,16 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   while ((int)cols < 2 * bn) cols <<= 1;
   p.tmem_cols = cols;
   const size_t np = passes == 3 ? 2 : 1;
-  const size_t stage_bytes = bf16 ? TC_A_BYTES + np * ((size_t)TC_BM * 64 + (size_t)bn * 64)
+  const size_t stage_bytes = bf16 ? np * ((size_t)TC_BM * 64 + (size_t)bn * 64)
                                   : np * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
+  const size_t fixed_bytes = 2 * TC_STORE_BYTES + (bf16 ? (size_t)TC_RAW * TC_A_BYTES : 0);
   const int nkb = (a.k1 + a.k2) / TC_BK;
-  int stages = (int)((225 * 1024 - 2 * TC_STORE_BYTES - 1024) / stage_bytes);
+  int stages = (int)((226 * 1024 - fixed_bytes - 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 1) stages = 1;
   p.stages = stages;
   (void)nkb;
-  const size_t smem = stage_bytes * stages + 2 * TC_STORE_BYTES + 1024;
+  const size_t smem = stage_bytes * stages + fixed_bytes + 1024;
   const int64_t units = ((tiles_m + cluster - 1) / cluster) * (a.n / bn) * a.groups;
   int grid = sm_count() / cluster;
   if (units < grid) grid = (int)units;
