@@ -112,6 +112,7 @@ mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restric
         }
       }
     }
+    fence_proxy_async_smem();             // generic-proxy reads of stage s before its async-proxy refill
     __syncthreads();                      // every warp is done reading stage s
     if (tid == 0) {
       const int gn = g + stages * step;

@@ -21,7 +21,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 __device__ __forceinline__ float apply_act(float v, int act, float p) {
   switch (act) {
-    case GRAFP_ACT_RELU:  return fmaxf(v, 0.0f);
+    case GRAFP_ACT_RELU:  return v < 0.0f ? 0.0f : v;      // NaN propagates (torch.relu), unlike fmaxf
     case GRAFP_ACT_LEAKY: return v > 0.0f ? v : v * p;
     case GRAFP_ACT_GELU:  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
     case GRAFP_ACT_ELU:   return v > 0.0f ? v : expm1f(v);

@@ -303,7 +303,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < PER; ++i) v[i] = raw[t + TC_XF_THREADS * i];
           if (kBf16) {
-            mbar_arrive(&raw_empty_bar[rs]);            // raw tile is in registers: its slot may be refilled
+            // raw tile is in registers: its slot may be refilled.  The refill is an async-proxy (TMA) write
+            // after generic-proxy reads: without the proxy fence the write can overtake the reads.
+            fence_proxy_async_smem();
+            mbar_arrive(&raw_empty_bar[rs]);
             mbar_wait(&empty_bar[s], ph ^ 1u);          // operand stage s free (MMAs of k-block it - S retired)
             uint8_t* hi = a_hi(s);
             uint8_t* lo = a_lo(s);

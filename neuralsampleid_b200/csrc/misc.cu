@@ -116,12 +116,15 @@ __global__ void peak_extract_kernel(const float* __restrict__ spec, const float*
   const int hw = n_mels * n_frames;
   const float* sp = spec + (size_t)b * hw;
   float mn = INFINITY, mx = -INFINITY;
+  bool has_nan = false;                                 // torch.min / torch.max propagate NaN
   for (int i = tid; i < hw; i += nt) {
     float v = sp[i];
     s_spec[i] = v;
     mn = fminf(mn, v);
     mx = fmaxf(mx, v);
+    has_nan |= (v != v);
   }
+  if (has_nan) mx = INFINITY, mn = -INFINITY;           // inf - (-inf) below: every normalised value NaN
   for (int i = tid; i < F * 3 * pb * pf; i += nt) s_w[i] = w[i];
   mn = -warp_max(-mn);
   mx = warp_max(mx);
@@ -159,7 +162,7 @@ __global__ void peak_extract_kernel(const float* __restrict__ spec, const float*
       }
     }
     acc += bias[f];
-    out[((size_t)b * nodes + node) * F + f] = fmaxf(acc, 0.0f);
+    out[((size_t)b * nodes + node) * F + f] = acc < 0.0f ? 0.0f : acc;   // NaN propagates
   }
 }
 
