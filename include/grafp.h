@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 1
+#define GRAFP_ABI_VERSION 2
 
 /* activation codes (reference: act_layer, encoder/gcn_lib/torch_nn.py:9-25; ELU for the
  * projector, simclr/simclr.py:26) */
@@ -132,6 +132,17 @@ typedef struct {
   int32_t act; float act_param;
   int32_t tap3_nodes;
   int32_t engine;
+  /* ---- split-bf16 activation format (ABI 2; bf16 tensor-core engines only) --------------------
+   * An activation that only another GEMM consumes (the FFN hidden tensor, the MRConv output) can
+   * travel as the operand pair the bf16x3 engine computes with: a bf16 tensor (2, M, C), plane 0 =
+   * bf16(v), plane 1 = bf16(v - bf16(v)).  Same bytes as fp32, bit-identical operands, and the
+   * consuming GEMM needs no in-kernel conversion stage.
+   *   y_split   when non-NULL the output is written in this form (row stride ldys elements,
+   *             plane stride m*ldys) INSTEAD of y (y may then be NULL)
+   *   a1_split  when non-NULL the first A source is read in this form (row stride lda1s elements,
+   *             plane stride m*lda1s) instead of a1 (a1 may then be NULL); needs k2 == 0, no tap3 */
+  void* y_split; int64_t ldys;
+  const void* a1_split; int64_t lda1s;
 } grafp_gemm_args;
 int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream);
 /* 1 if the tcgen05 engine takes this problem (k1, k2 multiples of 32, n multiple of 16, no tap3) */

@@ -32,7 +32,9 @@ class GemmArgs(C.Structure):
                 ("y", C.c_void_p), ("ldy", C.c_int64), ("row_sumsq", C.c_void_p),
                 ("m", C.c_int64), ("n", C.c_int32), ("groups", C.c_int32),
                 ("act", C.c_int32), ("act_param", C.c_float),
-                ("tap3_nodes", C.c_int32), ("engine", C.c_int32)]
+                ("tap3_nodes", C.c_int32), ("engine", C.c_int32),
+                ("y_split", C.c_void_p), ("ldys", C.c_int64),
+                ("a1_split", C.c_void_p), ("lda1s", C.c_int64)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float

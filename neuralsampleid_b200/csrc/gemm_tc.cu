@@ -15,9 +15,12 @@
 // weights, a few MB, stay L2-resident.  Warp roles (480 threads):
 //   warp 0      TMA producer (A from one of two sources or the 3-tap Downsample view, W hi/lo)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5   epilogue: TMEM -> registers -> scale/shift/activation/residual -> 128B-swizzled
-//               staging tile -> TMA store (coalesced, clipped at the matrix edge)
-//   warps 6-13  transform: tf32 hi / lo split of the A stage (hi = top 19 bits, lo = v - hi exact)
+//   warps 2-9   epilogue, two groups of four warps (one per TMEM lane quadrant): group h takes the
+//               32-column chunks of parity h: TMEM -> registers -> scale/shift/activation/residual
+//               -> its own 128B-swizzled staging tile -> TMA store (coalesced, clipped at the edge).
+//               One warp per scheduler could not hide the TMEM / L2 / store latencies of a chunk
+//               (ncu: 17 % issue utilisation, 2.1 k cycles per chunk); two groups interleave them.
+//   warps 10-13 transform: hi / lo split of the A stage (tf32 in place, or fp32 -> bf16 tiles)
 //   warp 14     second TMA producer (weight tiles) of the bf16 engines
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.  Pipelines: full[s] (TMA -> transform), xf[s] (transform -> MMA),
@@ -31,7 +34,8 @@ namespace grafp {
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 480;
 constexpr int TC_RAW = 3;                       // depth of the fp32 A staging ring (bf16 engines)
-constexpr int TC_XF_THREADS = 256;
+constexpr int TC_XF_THREADS = 128;
+constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_STORE_BYTES = TC_BM * 32 * 4;   // one 128 x 32 fp32 staging tile
 
 struct TcParams {
@@ -49,21 +53,20 @@ struct TcParams {
   float* row_sumsq;
   int act; float act_param;
   uint32_t tmem_cols;
+  int y_split;         // output as bf16 [hi ; lo] planes (tmY is then the 3-D bf16 map)
 };
 
-// v = act(v * scale + shift) + residual over one 32-column chunk of a row; scale/shift are read
-// as 128-bit broadcast loads (every thread of the CTA reads the same 32 columns)
+// v = act(v * scale + shift) + residual over one 32-column chunk of a row; scale/shift come from
+// shared memory as 128-bit broadcast reads (every thread of the warp reads the same 32 columns), the
+// residual from registers (loaded before the TMEM wait so its latency overlaps it)
 template <int ACT>
-__device__ __forceinline__ void epi_apply(float (&v)[32], const float* __restrict__ scale,
-                                          const float* __restrict__ shift,
-                                          const float* __restrict__ res, float act_param) {
+__device__ __forceinline__ void epi_apply(float (&v)[32], const float* scale, const float* shift,
+                                          const float4 (&res)[8], float act_param) {
 #pragma unroll
   for (int q = 0; q < 32; q += 4) {
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + q));
-    if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + q));
-    if (res) r4 = *reinterpret_cast<const float4*>(res + q);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + q);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + q);
+    const float4 r4 = res[q >> 2];
     v[q + 0] = apply_act(fmaf(v[q + 0], sc.x, sh.x), ACT, act_param) + r4.x;
     v[q + 1] = apply_act(fmaf(v[q + 1], sc.y, sh.y), ACT, act_param) + r4.y;
     v[q + 2] = apply_act(fmaf(v[q + 2], sc.z, sh.z), ACT, act_param) + r4.z;
@@ -83,7 +86,11 @@ __device__ __forceinline__ void epi_apply(float (&v)[32], const float* __restric
 //   passes = 1 : plain bf16 operands, fp32 accumulate (reduced precision, stated separately)
 // A still arrives from HBM as fp32 (TMA, 128B swizzle); the transform warps convert it into
 // 64-byte-row bf16 tiles (64B swizzle); W is pre-split on the host into stacked bf16 [w1 ; w2].
-template <int kPasses, int kCluster, bool kBf16>
+//
+// kASplit (bf16 engines): the A operand arrives already split, as the bf16 (2, M, K) [hi ; lo] planes a
+// previous GEMM's epilogue wrote (p.y_split): the W producer warp TMA-loads the hi / lo tiles straight
+// into the operand stage, there is no fp32 ring and no transform, the MMA waits on full[s] alone.
+template <int kPasses, int kCluster, bool kBf16, bool kASplit>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -97,6 +104,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_scale[2][256];   // folded scale / shift of the tile's columns
+  __shared__ __align__(16) float s_shift[2][256];
+  __shared__ float s_rowsq[TC_BM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -112,7 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   //       HBM-latency-bound A loads run up to TC_RAW k-blocks ahead of the MMA), then operand stages
   //       [A_hi | A_lo (3x) | B_hi | B_lo (3x)]
   uint8_t* raw0 = smem + 2 * TC_STORE_BYTES;
-  uint8_t* stage0 = raw0 + (kBf16 ? TC_RAW * TC_A_BYTES : 0);
+  uint8_t* stage0 = raw0 + ((kBf16 && !kASplit) ? TC_RAW * TC_A_BYTES : 0);
   auto a_raw = [&](int s) { return kBf16 ? raw0 + (size_t)s * TC_A_BYTES : stage0 + (size_t)s * stage_bytes; };
   auto a_hi = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return a_hi(s) + kAop; };
@@ -144,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 128);
+      mbar_init(&tmem_empty_bar[b], TC_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -159,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // tf32: warp 0 issues A and W of a k-block together.  bf16: warp 0 streams the fp32 A tiles through
     // the raw ring (gated by the transform), warp 14 streams the W tiles into the operand stages
     // (gated by the MMA commits), so A prefetch depth is not tied to the MMA's progress.
-    const bool do_a = warp == 0, do_w = kBf16 ? warp == 14 : warp == 0;
+    const bool do_a = warp == 0 && !kASplit, do_w = kBf16 ? warp == 14 : warp == 0;
     if (lane == 0 && (do_a || do_w)) {
       uint32_t it = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
@@ -184,7 +194,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
             if (do_w) {
               mbar_wait(&empty_bar[s], ph ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[s], kNP * b_bytes);
+              mbar_arrive_expect_tx(&full_bar[s], kNP * (b_bytes + (kASplit ? kAop : 0u)));
+              if (kASplit) {
+                tma_load_3d(a_hi(s), &tmA1, g * p.k1 + k, m0, 0, &full_bar[s]);
+                if (kPasses == 3) tma_load_3d(a_lo(s), &tmA1, g * p.k1 + k, m0, 1, &full_bar[s]);
+              }
             }
           } else {
             abar = &full_bar[s];
@@ -240,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           if (kBf16) mbar_wait(&full_bar[s], ph);             // W tiles landed (A comes via xf)
-          mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph);
+          if (!kASplit) mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph);
           tc_fence_after();
           if (kBf16) {
             const uint64_t dah = umma_desc_sw64(smem_u32(a_hi(s))), dbh = umma_desc_sw64(smem_u32(b_hi(s)));
@@ -281,16 +295,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         umma_commit(&tmem_full_bar[buf]);       // accumulator complete
       }
     }
-  } else if (warp >= 6 && warp < 14) {
-    // ===== transform (warps 6..13, 256 threads): build the MMA A operand(s) from the fp32 stage =====
+  } else if (warp >= 10 && warp < 14) {
+    // ===== transform (warps 10..13, 128 threads): build the MMA A operand(s) from the fp32 stage =====
     // tf32: hi = v with the 13 low mantissa bits cleared (exactly representable in tf32), lo = v - hi
     //       (exact in fp32, |lo| < 2^-10 |v|; the tensor core reads its top 19 bits), in place.
     // bf16: a1 = bf16(v), a2 = bf16(v - a1) written as 64-byte rows (64B swizzle: 16-byte chunk c of
     //       row r lives at chunk c ^ ((r >> 1) & 3)); the source float4 sits at swizzled chunk q & 7 of
     //       its 128-byte row, i.e. logical k-chunk (q & 7) ^ (r & 7).
-    if (kPasses == 3 || kBf16) {
+    if ((kPasses == 3 || kBf16) && !kASplit) {
       constexpr int PER = TC_A_BYTES / 16 / TC_XF_THREADS;
-      const int t = threadIdx.x - 192;
+      const int t = threadIdx.x - 320;
       uint32_t it = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -353,13 +367,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       }
     }
-  } else {
-    // ===== epilogue (warps 2..5, 128 threads) =====
-    const int et = threadIdx.x - 64;             // 0..127
+  } else if (warp >= 2 && warp < 10) {
+    // ===== epilogue (warps 2..9): two groups of 128 threads, group h owns the chunks of parity h =====
+    const int ew = warp - 2;                     // 0..7
+    const int half = ew >> 2;
+    const int et = (ew & 3) * 32 + lane;         // 0..127 inside the group
+    const int e256 = ew * 32 + lane;             // 0..255 over both groups
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;              // row inside the tile
     const bool store_thread = (et == 0);
-    uint32_t ti = 0, cc = 0;
+    uint8_t* sb = store_buf + half * TC_STORE_BYTES;
+    uint32_t ti = 0;
     for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
       const int nt = (int)(tile % tiles_n);
       const int64_t rest = tile / tiles_n;
@@ -367,51 +385,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int64_t mt = (rest / p.groups) * kCluster + crank;
       const int m0 = (int)(mt * TC_BM), n0 = nt * p.bn;
       const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
-      mbar_wait(&tmem_full_bar[buf], tph);
-      tc_fence_after();
       const int64_t row = (int64_t)m0 + r;
       const bool row_ok = row < p.m;
       const int64_t col0 = (int64_t)g * p.n + n0;
+      // stage this tile's scale / shift (overlaps the tile's main loop) and pull the residual lines of
+      // my chunks towards L2 so the loads below do not pay the HBM latency
+      float* ssc = s_scale[ti & 1u];
+      float* ssh = s_shift[ti & 1u];
+      if (e256 < p.bn) {
+        ssc[e256] = p.scale ? __ldg(p.scale + col0 + e256) : 1.0f;
+        ssh[e256] = p.shift ? __ldg(p.shift + col0 + e256) : 0.0f;
+      }
+      const float* res_row = (p.residual && row_ok) ? p.residual + row * p.ldr + col0 : nullptr;
+      if (res_row)
+        for (int c = half * 32; c < p.bn; c += 64)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(res_row + c));
+      named_bar_sync(3, TC_EPI_THREADS);
+      mbar_wait(&tmem_full_bar[buf], tph);
+      tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
       float rowsq = 0.0f;
-      for (int c = 0; c < p.bn; c += 32, ++cc) {
+      if (half * 32 >= p.bn) {                    // a 32-column tile: nothing for group 1 to read
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[buf]);
+      }
+      for (int c = half * 32; c < p.bn; c += 64) {
+        float4 r4[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          r4[q] = res_row ? *reinterpret_cast<const float4*>(res_row + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         float v[32];
         tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
         tmem_ld_wait();
-        if (c + 32 >= p.bn) {                     // last read of this accumulator: hand it back
+        if (c + 64 >= p.bn) {                     // my last read of this accumulator: hand it back
           tc_fence_before();
           mbar_arrive(&tmem_empty_bar[buf]);
         }
-        const float* res = (p.residual && row_ok) ? p.residual + row * p.ldr + col0 + c : nullptr;
-        const float* scp = p.scale ? p.scale + col0 + c : nullptr;
-        const float* shp = p.shift ? p.shift + col0 + c : nullptr;
         switch (p.act) {        // one specialised, branch-free instance per activation
-          case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, scp, shp, res, p.act_param); break;
-          case GRAFP_ACT_RELU:  epi_apply<GRAFP_ACT_RELU>(v, scp, shp, res, p.act_param); break;
-          case GRAFP_ACT_LEAKY: epi_apply<GRAFP_ACT_LEAKY>(v, scp, shp, res, p.act_param); break;
-          case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, scp, shp, res, p.act_param); break;
-          default:              epi_apply<GRAFP_ACT_ELU>(v, scp, shp, res, p.act_param); break;
+          case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, ssc + c, ssh + c, r4, p.act_param); break;
+          case GRAFP_ACT_RELU:  epi_apply<GRAFP_ACT_RELU>(v, ssc + c, ssh + c, r4, p.act_param); break;
+          case GRAFP_ACT_LEAKY: epi_apply<GRAFP_ACT_LEAKY>(v, ssc + c, ssh + c, r4, p.act_param); break;
+          case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, ssc + c, ssh + c, r4, p.act_param); break;
+          default:              epi_apply<GRAFP_ACT_ELU>(v, ssc + c, ssh + c, r4, p.act_param); break;
         }
         if (p.row_sumsq) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) rowsq = fmaf(v[q], v[q], rowsq);
         }
-        uint8_t* sb = store_buf + (cc & 1u) * TC_STORE_BYTES;
-        if (store_thread) bulk_wait_group_read<1>();     // the store that last used `sb` has read it
-        named_bar_sync(1, 128);
+        if (store_thread) bulk_wait_group_read<0>();      // my group's previous store has read `sb`
+        named_bar_sync(1 + half, 128);
+        if (p.y_split) {
+          // bf16 [hi ; lo] planes: exactly the operand pair a consuming bf16x3 GEMM would derive from the
+          // fp32 value (hi = bf16(v), lo = bf16(v - hi)); two 128 x 64 B tiles, 64B swizzle
+          uint32_t hp[16], lp[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)                       // 128B swizzle: 16-byte chunk q -> q ^ (row & 7)
-          *reinterpret_cast<float4*>(sb + r * 128 + ((q ^ (r & 7)) << 4)) =
-              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 16; ++q) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            const float2 f = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * q] - f.x, v[2 * q + 1] - f.y);
+            hp[q] = *reinterpret_cast<const uint32_t*>(&h);
+            lp[q] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off = (uint32_t)r * 64u + ((uint32_t)(q ^ ((r >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(sb + off) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+            *reinterpret_cast<uint4*>(sb + TC_STORE_BYTES / 2 + off) =
+                make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)                     // 128B swizzle: 16-byte chunk q -> q ^ (row & 7)
+            *reinterpret_cast<float4*>(sb + r * 128 + ((q ^ (r & 7)) << 4)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + half, 128);
         if (store_thread) {
-          tma_store_2d(&tmY, sb, (int)(col0 + c), m0);
+          if (p.y_split) {
+            tma_store_3d(&tmY, sb, (int)(col0 + c), m0, 0);
+            tma_store_3d(&tmY, sb + TC_STORE_BYTES / 2, (int)(col0 + c), m0, 1);
+          } else {
+            tma_store_2d(&tmY, sb, (int)(col0 + c), m0);
+          }
           bulk_commit_group();
         }
       }
-      if (p.row_sumsq && row_ok) atomicAdd(p.row_sumsq + row, rowsq);
+      if (p.row_sumsq) {
+        // deterministic: group 1 hands its partial to group 0 (fixed order), one atomic per row and
+        // column tile (at most two column tiles: fp32 addition of two terms commutes)
+        if (half == 1) s_rowsq[r] = rowsq;
+        named_bar_sync(4, TC_EPI_THREADS);
+        if (half == 0 && row_ok) atomicAdd(p.row_sumsq + row, rowsq + (p.bn > 32 ? s_rowsq[r] : 0.0f));
+      }
     }
     if (store_thread) bulk_wait_group_all();
   }
@@ -467,6 +534,22 @@ int tc_make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_
   return 0;
 }
 
+// bf16 (planes, rows, cols) with element strides (plane_stride, ld, 1); box = (32 cols, box_rows, 1), 64B swizzle
+int tc_make_map_3d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t planes,
+                        int64_t ld, int64_t plane_stride, int box_rows) {
+  EncodeTiledFn fn = tc_encode_fn();
+  GRAFP_REQUIRE(fn, "tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GRAFP_REQUIRE(r == CUDA_SUCCESS, "tc: cuTensorMapEncodeTiled(3d bf16) failed (%d)", (int)r);
+  return 0;
+}
+
 int tc_make_map_3d(CUtensorMap* map, const float* base, int64_t d0, int64_t d1, int64_t d2,
                    int64_t s1, int64_t s2, int box1, int box2) {
   EncodeTiledFn fn = tc_encode_fn();
@@ -504,10 +587,20 @@ int gemm_tc_supported(const grafp_gemm_args& a) {
     if (!((r >= TC_BM && r % TC_BM == 0) || (r < TC_BM && TC_BM % r == 0))) return 0;
   } else {
     if (a.k1 % TC_BK != 0 || a.k2 % TC_BK != 0) return 0;
-    if ((a.lda1 * 4) % 16 != 0 || (a.k2 && (a.lda2 * 4) % 16 != 0)) return 0;
+    if (a.a1_split) {
+      if (a.k2 != 0 || a.lda1s % 8 != 0 || (reinterpret_cast<uintptr_t>(a.a1_split) & 15)) return 0;
+    } else if ((a.lda1 * 4) % 16 != 0) {
+      return 0;
+    }
+    if (a.k2 && (a.lda2 * 4) % 16 != 0) return 0;
   }
+  if (a.a1_split && a.tap3_nodes > 0) return 0;
   if ((a.ldw * 4) % 16 != 0 || a.ldw % 8 != 0) return 0;
-  if (a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15)) return 0;
+  if (a.y_split) {
+    if (a.ldys % 8 != 0 || (reinterpret_cast<uintptr_t>(a.y_split) & 15) || a.row_sumsq) return 0;
+  } else if (a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15)) {
+    return 0;
+  }
   if (a.residual && (a.ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15))) return 0;
   return 1;
 }
@@ -530,7 +623,14 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
       return rc;
     p.tap3_rows = r; p.tap3_cin = cin;
   } else {
-    if (int rc = tc_make_map_2d(&mA1, a.a1, a.m, (int64_t)a.groups * a.k1, a.lda1, TC_BM)) return rc;
+    if (a.a1_split) {
+      GRAFP_REQUIRE(bf16, "gemm_tc: a split-bf16 A operand needs a bf16 engine");
+      if (int rc = tc_make_map_3d_bf16(&mA1, a.a1_split, (int64_t)a.groups * a.k1, a.m, 2, a.lda1s,
+                                       a.m * a.lda1s, TC_BM))
+        return rc;
+    } else if (int rc = tc_make_map_2d(&mA1, a.a1, a.m, (int64_t)a.groups * a.k1, a.lda1, TC_BM)) {
+      return rc;
+    }
     if (a.k2 > 0) {
       if (int rc = tc_make_map_2d(&mA2, a.a2, a.m, (int64_t)a.groups * a.k2, a.lda2, TC_BM)) return rc;
     } else {
@@ -548,7 +648,13 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   } else if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
                                      a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
     return rc;
-  if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) return rc;
+  if (a.y_split) {
+    if (int rc = tc_make_map_3d_bf16(&mY, a.y_split, n_total, a.m, 2, a.ldys, a.m * a.ldys, TC_BM)) return rc;
+  } else if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) {
+    return rc;
+  }
+  p.y_split = a.y_split ? 1 : 0;
+  const bool asplit = a.a1_split != nullptr;
   p.k1 = a.k1; p.k2 = a.k2; p.n = a.n; p.bn = bn; p.n_total = n_total; p.groups = a.groups; p.m = a.m;
   p.scale = a.scale; p.shift = a.shift; p.residual = a.residual; p.ldr = a.ldr;
   p.row_sumsq = a.row_sumsq;
@@ -559,9 +665,9 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   const size_t np = passes == 3 ? 2 : 1;
   const size_t stage_bytes = bf16 ? np * ((size_t)TC_BM * 64 + (size_t)bn * 64)
                                   : np * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
-  const size_t fixed_bytes = 2 * TC_STORE_BYTES + (bf16 ? (size_t)TC_RAW * TC_A_BYTES : 0);
+  const size_t fixed_bytes = 2 * TC_STORE_BYTES + ((bf16 && !asplit) ? (size_t)TC_RAW * TC_A_BYTES : 0);
   const int nkb = (a.k1 + a.k2) / TC_BK;
-  int stages = (int)((226 * 1024 - fixed_bytes - 1024) / stage_bytes);
+  int stages = (int)((220 * 1024 - fixed_bytes - 1024) / stage_bytes);   // 227 KB minus ~6 KB static
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 1) stages = 1;
   p.stages = stages;
@@ -571,10 +677,17 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   int grid = sm_count() / cluster;
   if (units < grid) grid = (int)units;
   grid *= cluster;
-  auto kern = bf16 ? (passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true> : gemm_tc_kernel<3, 1, true>)
-                                  : (cluster == 2 ? gemm_tc_kernel<1, 2, true> : gemm_tc_kernel<1, 1, true>))
-                   : (passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, false> : gemm_tc_kernel<3, 1, false>)
-                                  : (cluster == 2 ? gemm_tc_kernel<1, 2, false> : gemm_tc_kernel<1, 1, false>));
+  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  KernFn kern;
+  if (asplit)
+    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, true> : gemm_tc_kernel<3, 1, true, true>)
+                       : (cluster == 2 ? gemm_tc_kernel<1, 2, true, true> : gemm_tc_kernel<1, 1, true, true>);
+  else if (bf16)
+    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, false> : gemm_tc_kernel<3, 1, true, false>)
+                       : (cluster == 2 ? gemm_tc_kernel<1, 2, true, false> : gemm_tc_kernel<1, 1, true, false>);
+  else
+    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, false, false> : gemm_tc_kernel<3, 1, false, false>)
+                       : (cluster == 2 ? gemm_tc_kernel<1, 2, false, false> : gemm_tc_kernel<1, 1, false, false>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

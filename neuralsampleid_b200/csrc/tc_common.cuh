@@ -51,6 +51,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0,
+                                             int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -183,5 +189,8 @@ int tc_make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_
 // fp32 (d2, d1, d0=cols) with element strides (s2, s1, 1); box = (32, box1, box2), 128B swizzle
 int tc_make_map_3d(CUtensorMap* map, const float* base, int64_t d0, int64_t d1, int64_t d2,
                    int64_t s1, int64_t s2, int box1, int box2);
+// bf16 (planes, rows, cols), element strides (plane_stride, ld, 1); box = (32, box_rows, 1), 64B swizzle
+int tc_make_map_3d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t planes,
+                        int64_t ld, int64_t plane_stride, int box_rows);
 
 }  // namespace grafp

@@ -102,15 +102,20 @@ class BasicConv(nn.Sequential):
         act = self[e["act"]] if e["act"] is not None else None
         return (hit[1],) + ((act.name, act.neg_slope) if act is not None else (None, 0.0))
 
-    def forward_nodes(self, x: torch.Tensor, x2: torch.Tensor = None) -> torch.Tensor:
+    def forward_nodes(self, x: torch.Tensor, x2: torch.Tensor = None, out_split: bool = False):
         """x: (M, C) node-major.  If ``x2`` is given, the first layer consumes the virtual
-        interleave [x0, x2_0, x1, x2_1, ...] (MRConv2d) without materialising it."""
+        interleave [x0, x2_0, x1, x2_1, ...] (MRConv2d) without materialising it.  ``out_split``:
+        the caller's consumer is a bf16 tensor-core GEMM, return an ops.SplitAct if this layer can
+        produce one."""
         if self.training:
             raise RuntimeError("BasicConv.forward_nodes is the eval path; training goes through "
                                "neuralsampleid_b200.autograd")
+        last = len(self._plan) - 1
         for i in range(len(self._plan)):
             lin, act, slope = self.layer_params(i, interleaved_sources=(i == 0 and x2 is not None))
-            x = ops.linear(x, lin, act, slope, a2=x2 if i == 0 else None)
+            k_total = lin.w.shape[1] * lin.groups
+            split = out_split and i == last and not isinstance(x, ops.SplitAct) and ops.split_ok(lin, k_total)
+            x = ops.linear(x, lin, act, slope, a2=x2 if i == 0 else None, out_split=split)
         return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

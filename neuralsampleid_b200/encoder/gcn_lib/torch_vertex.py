@@ -24,9 +24,9 @@ class MRConv2d(nn.Module):
         super().__init__()
         self.nn = BasicConv([in_channels * 2, out_channels], act, norm, bias)
 
-    def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int, out_split: bool = False):
         m = ops.mr_aggregate(x, nn_idx, B, N)
-        return self.nn.forward_nodes(x, m)
+        return self.nn.forward_nodes(x, m, out_split)
 
     def forward(self, x, edge_index, y=None):
         if y is not None:
@@ -65,10 +65,11 @@ class DyGraphConv2d(GraphConv2d):
         self.k, self.d, self.r = kernel_size, dilation, r
         self.dilated_knn_graph = DenseDilatedKnnGraph(kernel_size, dilation, stochastic, epsilon)
 
-    def forward_nodes(self, x: torch.Tensor, B: int, N: int, nn_idx: torch.Tensor = None) -> torch.Tensor:
+    def forward_nodes(self, x: torch.Tensor, B: int, N: int, nn_idx: torch.Tensor = None,
+                      out_split: bool = False):
         if nn_idx is None:
             nn_idx = self.dilated_knn_graph.knn_nodes(x, B, N)
-        return self.gconv.forward_nodes(x, nn_idx, B, N)
+        return self.gconv.forward_nodes(x, nn_idx, B, N, out_split)
 
     def forward(self, x, relative_pos=None):
         if relative_pos is not None:
@@ -127,8 +128,10 @@ class Grapher(nn.Module):
         if taps is not None:
             taps["fc1"] = y
             taps["idx"] = nn_idx
-        g = self.graph_conv.forward_nodes(y, B, N, nn_idx)
-        return ops.linear(g, self._folded("fc2"), residual=x)
+        fc2 = self._folded("fc2")
+        # the MRConv output feeds only fc2: split-bf16 on the bf16 tensor-core engines (ops.SplitAct)
+        g = self.graph_conv.forward_nodes(y, B, N, nn_idx, out_split=ops.split_ok(fc2, 2 * self.channels))
+        return ops.linear(g, fc2, residual=x)
 
     def forward(self, x):
         B, C, N = x.shape[:3]

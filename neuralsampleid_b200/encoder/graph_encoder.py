@@ -106,7 +106,10 @@ class FFN(_Cached):
         M, hid = x.shape[0], fc1.w.shape[0]
         slab = _ffn_slab_rows(hid)
         if slab <= 0 or M <= slab:
-            h = ops.linear(x, fc1, self.act.name, self.act.neg_slope)
+            # the hidden tensor feeds only fc2: on the bf16 tensor-core engines it travels as the
+            # split-bf16 operand pair (same bytes, bit-identical operands, no conversion stage in fc2)
+            split = ops.split_ok(fc1, x.shape[1]) and ops.split_ok(fc2, hid)
+            h = ops.linear(x, fc1, self.act.name, self.act.neg_slope, out_split=split)
             return ops.linear(h, fc2, residual=x)
         # Optional (off by default, see _ffn_slab_rows): row slabs sized so the hidden activations of
         # one slab stay L2-resident between the two GEMMs.

@@ -158,11 +158,45 @@ def tc_splits(w: torch.Tensor):
     return (split_tf32(w) if want_tf32 else None), (split_bf16(w) if want_bf16 else None)
 
 
-def linear(a1: torch.Tensor, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
-           tap3_nodes: int = 0, engine: Optional[int] = None, row_sumsq=None, out=None) -> torch.Tensor:
+class SplitAct:
+    """An activation in the split-bf16 format of include/grafp.h (ABI 2): bf16 (2, M, C), plane 0 =
+    bf16(v), plane 1 = bf16(v - bf16(v)) -- the operand pair the bf16x3 engine computes with.  Only a
+    GEMM may consume it (``ops.gemm`` / ``ops.linear`` as ``a1``)."""
+    __slots__ = ("t",)
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+    @property
+    def shape(self):
+        return self.t.shape[1:]
+
+    @property
+    def device(self):
+        return self.t.device
+
+    def float(self) -> torch.Tensor:
+        """fp32 value hi + lo (test / debugging helper)."""
+        return self.t[0].float() + self.t[1].float()
+
+
+def split_ok(lin, k_total: int) -> bool:
+    """True when the GEMM over ``lin`` (k_total input columns) runs on a bf16 tensor-core engine, i.e.
+    may produce or consume a SplitAct."""
+    eng = ENGINES[_engine_override] if _engine_override is not None else _engine
+    if eng not in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16):
+        return False
+    if lin.w_split_bf16 is None or os.environ.get("GRAFP_NO_SPLIT_ACT"):
+        return False
+    n = lin.w.shape[0] // lin.groups
+    return k_total % (32 * lin.groups) == 0 and n % 32 == 0
+
+
+def linear(a1, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
+           tap3_nodes: int = 0, engine: Optional[int] = None, row_sumsq=None, out=None, out_split: bool = False):
     """ops.gemm over a prepared ``_prep.Linear``."""
     return gemm(a1, lin.w, lin.scale, lin.shift, act, act_param, residual, a2, lin.groups, tap3_nodes,
-                engine, out, lin.w_split, lin.w_split_bf16, row_sumsq)
+                engine, out, lin.w_split, lin.w_split_bf16, row_sumsq, out_split)
 
 
 def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
@@ -170,16 +204,27 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
          residual: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          groups: int = 1, tap3_nodes: int = 0, engine: Optional[int] = None,
          out: Optional[torch.Tensor] = None, w_split: Optional[torch.Tensor] = None,
-         w_split_bf16: Optional[torch.Tensor] = None, row_sumsq: Optional[torch.Tensor] = None) -> torch.Tensor:
+         w_split_bf16: Optional[torch.Tensor] = None, row_sumsq: Optional[torch.Tensor] = None,
+         out_split: bool = False):
     """y = act(scale * [a1 | a2] @ w.T + shift) + residual  (per-group, see include/grafp.h).
 
     a1: (M, groups*k1) (or the (2M', Cin) node matrix in tap3 mode), a2: (M, groups*k2) or None,
-    w: (groups*n, k1+k2)."""
-    a1 = _chk(a1, name="a1")
+    w: (groups*n, k1+k2).  ``a1`` may be a SplitAct; ``out_split`` returns one (bf16 tensor-core engines
+    only: the library refuses anything else)."""
+    a1s = None
+    if isinstance(a1, SplitAct):
+        a1s = _chk(a1.t, torch.bfloat16, "a1 (split)")
+        a1 = None
+    else:
+        a1 = _chk(a1, name="a1")
     w = _chk(w, name="w")
     n_total, ktot = w.shape
     n = n_total // groups
-    if tap3_nodes > 0:
+    if a1s is not None:
+        if tap3_nodes > 0 or a2 is not None:
+            raise GrafpError("gemm: a SplitAct operand cannot be combined with tap3 / a second source")
+        k1, k2, M = a1s.shape[2] // groups, 0, a1s.shape[1]
+    elif tap3_nodes > 0:
         cin = a1.shape[1]
         k1, k2 = 3 * cin, 0
         M = a1.shape[0] // 2
@@ -192,10 +237,20 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
             k2 = a2.shape[1] // groups
     if k1 + k2 != ktot:
         raise GrafpError("gemm: weight has %d columns, operands give %d" % (ktot, k1 + k2))
-    if out is None:
-        out = torch.empty((M, n_total), device=a1.device, dtype=torch.float32)
+    dev = a1.device if a1 is not None else a1s.device
+    if out_split:
+        if out is not None or row_sumsq is not None:
+            raise GrafpError("gemm: out_split cannot be combined with out= / row_sumsq")
+        out = torch.empty((2, M, n_total), device=dev, dtype=torch.bfloat16)
+    elif out is None:
+        out = torch.empty((M, n_total), device=dev, dtype=torch.float32)
     args = GemmArgs()
-    args.a1, args.lda1, args.k1 = a1.data_ptr(), a1.stride(0), k1
+    if a1s is not None:
+        args.a1, args.lda1, args.k1 = None, 0, k1
+        args.a1_split, args.lda1s = a1s.data_ptr(), a1s.stride(1)
+    else:
+        args.a1, args.lda1, args.k1 = a1.data_ptr(), a1.stride(0), k1
+        args.a1_split, args.lda1s = None, 0
     args.a2, args.lda2, args.k2 = (a2.data_ptr() if a2 is not None else None), \
         (a2.stride(0) if a2 is not None else 0), k2
     args.w, args.ldw = w.data_ptr(), w.stride(0)
@@ -208,7 +263,12 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
         args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
     else:
         args.residual, args.ldr = None, 0
-    args.y, args.ldy = out.data_ptr(), out.stride(0)
+    if out_split:
+        args.y, args.ldy = None, 0
+        args.y_split, args.ldys = out.data_ptr(), out.stride(1)
+    else:
+        args.y, args.ldy = out.data_ptr(), out.stride(0)
+        args.y_split, args.ldys = None, 0
     args.row_sumsq = row_sumsq.data_ptr() if row_sumsq is not None else None
     args.m, args.n, args.groups = M, n, groups
     args.act, args.act_param = act_code(act) if not isinstance(act, int) else act, act_param
@@ -220,9 +280,9 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
             args.engine = ov
         elif w_split is not None and _lib.load().grafp_gemm_tc_supported(C.byref(args)):
             args.engine = ov
-    with torch.cuda.device(a1.device):
-        check(_lib.load().grafp_gemm_fwd(C.byref(args), _stream(a1)), "gemm_fwd")
-    return out
+    with torch.cuda.device(dev):
+        check(_lib.load().grafp_gemm_fwd(C.byref(args), _stream(out)), "gemm_fwd")
+    return SplitAct(out) if out_split else out
 
 
 def node_mean(x: torch.Tensor, B: int, N: int) -> torch.Tensor:

@@ -302,6 +302,50 @@ def test_gemm_engines(case, engine):
     assert err < tol, "engine %s rel err %.3g" % (engine, err)
 
 
+@pytest.mark.parametrize("engine", ["bf16x3", "bf16", "auto"])
+@pytest.mark.parametrize("M,k,hid,n,groups", [(640, 64, 256, 64, 1), (300, 256, 1024, 256, 1), (130, 512, 2048, 512, 1),
+                                              (1000, 64, 128, 64, 4), (128 * 5 + 7, 128, 512, 128, 1)])
+def test_gemm_split_bf16_activations_bit_exact(M, k, hid, n, groups, engine):
+    """The split-bf16 activation format (include/grafp.h, ABI 2): a producer writes bf16 [hi ; lo] planes,
+    the consumer reads them as its MMA operands.  Both must be BIT-identical to the fp32 route (the planes
+    are exactly what the consumer's in-kernel conversion derives from the fp32 tensor)."""
+    ops = _ops()
+    from neuralsampleid_b200 import _lib, _prep
+    eng = _lib.ENGINES[engine]
+    a = synth.synth_normal((M, groups * k), 30).to(DEV)
+    w1 = (synth.synth_normal((groups * hid, k), 31) / float(np.sqrt(k))).to(DEV)
+    w2 = (synth.synth_normal((n, groups * hid), 32) / float(np.sqrt(groups * hid))).to(DEV)
+    sc1 = synth.synth_uniform((groups * hid,), 33, 0.5, 1.5).to(DEV)
+    sh1 = synth.synth_uniform((groups * hid,), 34, -0.5, 0.5).to(DEV)
+    res = synth.synth_normal((M, n), 35).to(DEV)
+    l1 = _prep.make_linear(w1, sc1, sh1, groups)
+    l2 = _prep.make_linear(w2, None, None, 1)
+    assert ops.split_ok(l1, groups * k) and ops.split_ok(l2, groups * hid)
+    h32 = ops.linear(a, l1, "relu", 0.0, engine=eng)
+    hs = ops.linear(a, l1, "relu", 0.0, engine=eng, out_split=True)
+    assert isinstance(hs, ops.SplitAct) and hs.t.shape == (2, M, groups * hid) and hs.t.dtype == torch.bfloat16
+    hi = h32.bfloat16()
+    lo = (h32 - hi.float()).bfloat16()
+    assert torch.equal(hs.t[0], hi) and torch.equal(hs.t[1], lo)
+    y32 = ops.linear(h32, l2, None, 0.0, res, engine=eng)
+    ys = ops.linear(hs, l2, None, 0.0, res, engine=eng)
+    assert torch.equal(y32, ys)
+
+
+def test_gemm_split_bf16_needs_bf16_engine():
+    ops = _ops()
+    from neuralsampleid_b200 import _lib, _prep
+    a = synth.synth_normal((256, 64), 30).to(DEV)
+    w = (synth.synth_normal((64, 64), 31) / 8.0).to(DEV)
+    lin = _prep.make_linear(w, None, None, 1)
+    for name in ("simt", "3xtf32", "tf32"):
+        with pytest.raises(_lib.GrafpError):
+            ops.linear(a, lin, engine=_lib.ENGINES[name], out_split=True)
+    hs = ops.linear(a, lin, out_split=True)
+    with pytest.raises(_lib.GrafpError):
+        ops.linear(hs, lin, engine=_lib.ENGINES["simt"])
+
+
 def test_gemm_empty_and_errors():
     ops = _ops()
     from neuralsampleid_b200._lib import GrafpError
