@@ -12,14 +12,19 @@
 //   epilogue  dist = (sq_i + (-2 * dot)) + sq_j  (reference association, torch_edge.py:16-18),
 //             ascending (distance, index) insertion, lowest index first on exact ties
 //
-// Warp roles (448 threads): warp 0 TMA, warp 1 MMA issuer + TMEM allocator, warps 2-9 transform,
-// warps 10-13 epilogue.
+// Warp roles (576 threads): warp 0 TMA, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue,
+// warps 10-17 transform.  The epilogue is two groups of four warps (one warp per TMEM lane quadrant
+// each): group h scans the 32-column chunks of parity h into its own sorted list, the two lists are
+// merged through shared memory with a (distance, index) lexicographic insertion.  One warp per
+// scheduler left the select network latency-bound; two per scheduler interleave.
 #include "tc_common.cuh"
 
 namespace grafp {
 
-constexpr int KT_THREADS = 448;
+constexpr int KT_THREADS = 576;
 constexpr int KT_MAX_STAGES = 6;
+constexpr int KT_XF_THREADS = 256;
+constexpr int KT_EPI_THREADS = 256;
 
 struct KnnTcParams {
   int N, C, kk, d, k;
@@ -87,6 +92,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_sq[2][256];      // squared norms of the tile's column set
+  __shared__ float s_md[KMAX][TC_BM];               // group 1's sorted candidates, handed to group 0
+  __shared__ int s_mj[KMAX][TC_BM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -106,12 +113,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
     tma_prefetch_desc(&tmCols);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&xf_bar[s], 256);
+      mbar_init(&xf_bar[s], KT_XF_THREADS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 128);
+      mbar_init(&tmem_empty_bar[b], KT_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -167,11 +174,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
         umma_commit(&tmem_full_bar[buf]);
       }
     }
-  } else if (warp < 10) {
+  } else if (warp >= 10) {
     // ===== transform (256 threads): scale rows by rinv (F.normalize), split tf32 hi / lo =====
     // hi = top 19 bits of v, lo = v - hi (exact); each thread owns the same rows in every k-block
-    const int t = threadIdx.x - 64;
-    const int per = (int)(b_bytes / 16) / 256;          // float4 per thread per stage: 4 or 8
+    const int t = threadIdx.x - 320;
+    const int per = (int)(b_bytes / 16) / KT_XF_THREADS;          // float4 per thread per stage: 4 or 8
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int64_t c0 = col_start(tile * TC_BM);
@@ -187,22 +194,25 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
         mbar_wait(&full_bar[s], ph);
         float4* bh = reinterpret_cast<float4*>(b_hi(s));
         float4* bl = reinterpret_cast<float4*>(b_lo(s));
-        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < per) v[i] = bh[t + 256 * i];
+        for (int half4 = 0; half4 < 2; ++half4) {
+          if (half4 * 4 < per) {
+            float4 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < per) {
-            const float x0 = v[i].x * ri[i], x1 = v[i].y * ri[i], x2 = v[i].z * ri[i], x3 = v[i].w * ri[i];
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u);
-            l.x = x0 - h.x; l.y = x1 - h.y; l.z = x2 - h.z; l.w = x3 - h.w;
-            bh[t + 256 * i] = h;
-            bl[t + 256 * i] = l;
+            for (int i = 0; i < 4; ++i) v[i] = bh[t + KT_XF_THREADS * (half4 * 4 + i)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float rr = ri[half4 * 4 + i];
+              const float x0 = v[i].x * rr, x1 = v[i].y * rr, x2 = v[i].z * rr, x3 = v[i].w * rr;
+              float4 h, l;
+              h.x = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+              h.y = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+              h.z = __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u);
+              h.w = __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u);
+              l.x = x0 - h.x; l.y = x1 - h.y; l.z = x2 - h.z; l.w = x3 - h.w;
+              bh[t + KT_XF_THREADS * (half4 * 4 + i)] = h;
+              bl[t + KT_XF_THREADS * (half4 * 4 + i)] = l;
+            }
           }
         }
         fence_proxy_async_smem();
@@ -210,7 +220,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       }
     }
   } else {
-    // ===== epilogue (128 threads): streaming per-row top-(k*d) over the TMEM distance tile =====
+    // ===== epilogue (warps 2..9): streaming per-row top-(k*d) over the TMEM distance tile =====
+    const int ew = warp - 2;
+    const int half = ew >> 2;                    // this group scans the 32-column chunks of parity `half`
+    const int e256 = ew * 32 + lane;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     uint32_t ti = 0;
@@ -224,9 +237,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       const unsigned ncols = row_ok ? (unsigned)p.N : 0u;      // columns [lo_col, lo_col + N) are its graph
       const float sqi = row_ok ? knn_node_norm(p, grow).y : 0.0f;
       // stage the column set's squared norms (the workspace is padded: reads past M are harmless)
-      s_sq[buf][r] = (c0 + r < p.M) ? knn_node_norm(p, c0 + r).y : 0.0f;
-      if (p.bn > 128) s_sq[buf][r + 128] = (c0 + 128 + r < p.M) ? knn_node_norm(p, c0 + 128 + r).y : 0.0f;
-      named_bar_sync(1, 128);
+      if (e256 < p.bn) s_sq[buf][e256] = (c0 + e256 < p.M) ? knn_node_norm(p, c0 + e256).y : 0.0f;
+      named_bar_sync(1, KT_EPI_THREADS);
       const float4* sqv = reinterpret_cast<const float4*>(s_sq[buf]);
       float bd[KMAX];
       int bj[KMAX];
@@ -235,9 +247,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       mbar_wait(&tmem_full_bar[buf], tph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
-      // software pipeline over 32-column chunks: while chunk c is scanned, the TMEM load and the
-      // squared norms of chunk c+32 are already in flight (two register buffers, loop unrolled by 2)
-      float va[32], vb[32];
+      // my 32-column chunks, one TMEM load in flight: the other group's scan hides its latency
+      float va[32];
       auto fetch = [&](int c, float* v) {
         tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
@@ -269,27 +280,46 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
           }
         }
       };
-      fetch(0, va);
-      for (int c = 0; c < p.bn; c += 64) {                       // bn is a multiple of 64 (128 or 256)
-        tmem_ld_wait();                                          // chunk c landed
-        fetch(c + 32, vb);
-        scan(c, va);
-        tmem_ld_wait();                                          // chunk c+32 landed
-        if (c + 64 < p.bn) {
-          fetch(c + 64, va);
-        } else {                                                 // all of this accumulator has been read
+      for (int c = half * 32; c < p.bn; c += 64) {               // bn is 128 or 256: 2 or 4 chunks per group
+        fetch(c, va);
+        tmem_ld_wait();
+        if (c + 64 >= p.bn) {                                    // my share of this accumulator has been read
           tc_fence_before();
           mbar_arrive(&tmem_empty_bar[buf]);
         }
-        scan(c + 32, vb);
+        scan(c, va);
       }
-      if (row_ok) {
+      // merge: group 1 hands its sorted list to group 0, which inserts it under the (distance, index)
+      // lexicographic order (the two groups saw interleaved index ranges)
+      if (half == 1) {
 #pragma unroll
-        for (int t = 0; t < KMAX; ++t) {
-          if (t < p.kk && (t % p.d) == 0) {
-            const int64_t o = grow * p.k + t / p.d;
-            p.idx[o] = bj[t];
-            if (p.dist) p.dist[o] = bd[t];
+        for (int t = 0; t < KMAX; ++t) { s_md[t][r] = bd[t]; s_mj[t][r] = bj[t]; }
+      }
+      named_bar_sync(2, KT_EPI_THREADS);
+      if (half == 0) {
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) {
+          const float dv = s_md[c][r];
+          const int jl = s_mj[c][r];
+          bool lt[KMAX];
+#pragma unroll
+          for (int t = 0; t < KMAX; ++t) lt[t] = dv < bd[t] || (dv == bd[t] && jl < bj[t]);
+#pragma unroll
+          for (int t = KMAX - 1; t > 0; --t) {
+            bd[t] = lt[t - 1] ? bd[t - 1] : (lt[t] ? dv : bd[t]);
+            bj[t] = lt[t - 1] ? bj[t - 1] : (lt[t] ? jl : bj[t]);
+          }
+          bd[0] = lt[0] ? dv : bd[0];
+          bj[0] = lt[0] ? jl : bj[0];
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int t = 0; t < KMAX; ++t) {
+            if (t < p.kk && (t % p.d) == 0) {
+              const int64_t o = grow * p.k + t / p.d;
+              p.idx[o] = bj[t];
+              if (p.dist) p.dist[o] = bd[t];
+            }
           }
         }
       }
@@ -315,8 +345,16 @@ int knn_tc_supported(int B, int N, int C, int kk) {
 size_t knn_tc_workspace_bytes(int B, int N) { return ((size_t)B * N + 128) * 2 * sizeof(float); }
 
 template <int KMAX>
-static int knn_tc_launch_t(const CUtensorMap& mc, const KnnTcParams& p, size_t smem, int grid,
-                           cudaStream_t st) {
+static int knn_tc_launch_t(const CUtensorMap& mc, KnnTcParams p, int grid, cudaStream_t st) {
+  // stages: whatever fits beside the kernel's static shared memory (the merge lists grow with KMAX)
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, knn_tc_kernel<KMAX>);
+  const size_t stage_bytes = 2 * (size_t)p.bn * TC_BK * 4;
+  int stages = (int)((227 * 1024 - fa.sharedSizeBytes - 2048) / stage_bytes);
+  if (stages > KT_MAX_STAGES) stages = KT_MAX_STAGES;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = stage_bytes * stages + 1024;
   cudaFuncSetAttribute(knn_tc_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   knn_tc_kernel<KMAX><<<grid, KT_THREADS, smem, st>>>(mc, p);
   return check_launch("knn_tc");
@@ -346,20 +384,14 @@ int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int
   uint32_t cols = 32;
   while ((int)cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t stage_bytes = 2 * (size_t)p.bn * TC_BK * 4;
-  int stages = (int)((224 * 1024 - 1024) / stage_bytes);
-  if (stages > KT_MAX_STAGES) stages = KT_MAX_STAGES;
-  if (stages < 1) stages = 1;
-  p.stages = stages;
-  const size_t smem = stage_bytes * stages + 1024;
   CUtensorMap mc;
   if (int rc = tc_make_map_2d(&mc, x, M, C, C, p.bn)) return rc;
   const int64_t tiles = (M + TC_BM - 1) / TC_BM;
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;
-  if (kk <= 4) return knn_tc_launch_t<4>(mc, p, smem, grid, st);
-  if (kk <= 8) return knn_tc_launch_t<8>(mc, p, smem, grid, st);
-  return knn_tc_launch_t<16>(mc, p, smem, grid, st);
+  if (kk <= 4) return knn_tc_launch_t<4>(mc, p, grid, st);
+  if (kk <= 8) return knn_tc_launch_t<8>(mc, p, grid, st);
+  return knn_tc_launch_t<16>(mc, p, grid, st);
 }
 
 }  // namespace grafp
