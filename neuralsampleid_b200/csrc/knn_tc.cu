@@ -14,9 +14,22 @@
 //
 // Warp roles (576 threads): warp 0 TMA, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue,
 // warps 10-17 transform.  The epilogue is two groups of four warps (one warp per TMEM lane quadrant
-// each): group h scans the 32-column chunks of parity h into its own sorted list, the two lists are
-// merged through shared memory with a (distance, index) lexicographic insertion.  One warp per
-// scheduler left the select network latency-bound; two per scheduler interleave.
+// each); group g owns the tiles whose accumulator sits in TMEM buffer g, so the groups never exchange
+// data and two independent instruction streams share every scheduler.
+//
+// Selection.  A sorted-insertion select network costs ~20 ALU-pipe instructions per distance and the
+// ALU pipe issues a warp instruction every other cycle: ncu showed the first version ALU-bound (73 %
+// pipe utilisation, 483 us for the N = 256 stage).  The epilogue therefore selects in two passes over
+// the TMEM tile:
+//   pass 1  minimum of every group of bn/16 columns (one FMNMX per distance); the (k*d)-th smallest
+//           group minimum tau bounds the (k*d)-th smallest distance of the row from above
+//   pass 2  distances are recomputed (bit-identical) and the few with dist <= tau are appended, in
+//           column order, to a short per-row candidate list in shared memory (one FSETP + a predicated
+//           store per distance)
+//   final   exact (distance, lowest index first) insertion over the candidates only
+// A row whose list overflows (mass ties), or a shape with fewer column groups than k*d, takes the
+// full select-network scan instead, so the result is always the exact one.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace grafp {
@@ -30,6 +43,7 @@ struct KnnTcParams {
   int N, C, kk, d, k;
   int64_t M;
   int bn;                 // columns per tile: N (N >= 128) or 128
+  int thresh;             // two-pass threshold selection (needs k*d <= column groups of a graph)
   int stages;
   const float* rinv; const float* sq;   // prepass outputs, or (rinv == nullptr) sq = raw sum of squares
   int normalize;
@@ -91,9 +105,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float s_sq[2][256];      // squared norms of the tile's column set
-  __shared__ float s_md[KMAX][TC_BM];               // group 1's sorted candidates, handed to group 0
-  __shared__ int s_mj[KMAX][TC_BM];
+  __shared__ __align__(16) float s_sq[2][2][256];   // [group][tile parity]: squared norms of the column set
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -118,7 +130,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], KT_EPI_THREADS);
+      mbar_init(&tmem_empty_bar[b], 128);
     }
     fence_barrier_init();
   }
@@ -220,16 +232,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       }
     }
   } else {
-    // ===== epilogue (warps 2..9): streaming per-row top-(k*d) over the TMEM distance tile =====
+    // ===== epilogue (warps 2..9): per-row top-(k*d) over the TMEM distance tile =====
+    constexpr int L = KMAX + 8;                  // candidate slots per row (+8 overflow sink slots)
     const int ew = warp - 2;
-    const int half = ew >> 2;                    // this group scans the 32-column chunks of parity `half`
-    const int e256 = ew * 32 + lane;
+    const uint32_t grp = (uint32_t)(ew >> 2);    // owns the tiles of TMEM buffer `grp`
+    const int et = (ew & 3) * 32 + lane;         // 0..127 inside the group
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
+    float2* lst = reinterpret_cast<float2*>(smem + (size_t)S * stage_bytes) + (size_t)grp * (L + 8) * TC_BM + r;
+    const uint32_t lst_addr = smem_u32(lst), lst_sink = lst_addr + (uint32_t)L * TC_BM * 8u;
+    const bool full_tile = p.N >= p.bn;          // every column of the tile belongs to the row's graph
+    const int gshift = p.bn == 256 ? 4 : 3;      // log2(columns per group): 16 groups per tile
     uint32_t ti = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      if ((ti & 1u) != grp) continue;
       const int64_t m0 = tile * TC_BM, c0 = col_start(m0);
-      const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+      const uint32_t buf = grp, tph = (ti >> 1) & 1u;
       const int64_t grow = m0 + r;
       const bool row_ok = grow < p.M;
       const int64_t gs = row_ok ? (grow / p.N) * p.N : c0;     // first node of this row's graph
@@ -237,9 +255,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       const unsigned ncols = row_ok ? (unsigned)p.N : 0u;      // columns [lo_col, lo_col + N) are its graph
       const float sqi = row_ok ? knn_node_norm(p, grow).y : 0.0f;
       // stage the column set's squared norms (the workspace is padded: reads past M are harmless)
-      if (e256 < p.bn) s_sq[buf][e256] = (c0 + e256 < p.M) ? knn_node_norm(p, c0 + e256).y : 0.0f;
-      named_bar_sync(1, KT_EPI_THREADS);
-      const float4* sqv = reinterpret_cast<const float4*>(s_sq[buf]);
+      float* ssq = s_sq[grp][(ti >> 1) & 1u];
+      ssq[et] = (c0 + et < p.M) ? knn_node_norm(p, c0 + et).y : 0.0f;
+      if (p.bn > 128) ssq[et + 128] = (c0 + 128 + et < p.M) ? knn_node_norm(p, c0 + 128 + et).y : 0.0f;
+      named_bar_sync(1 + (int)grp, 128);
+      const float4* sqv = reinterpret_cast<const float4*>(ssq);
       float bd[KMAX];
       int bj[KMAX];
 #pragma unroll
@@ -247,79 +267,136 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       mbar_wait(&tmem_full_bar[buf], tph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
-      // my 32-column chunks, one TMEM load in flight: the other group's scan hides its latency
-      float va[32];
-      auto fetch = [&](int c, float* v) {
+      float v[32];
+      // distances of one 32-column chunk, in place: (sq_i + (-2 dot)) + sq_j (reference association)
+      auto load_dist = [&](int c) {
         tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
-      };
-      auto scan = [&](int c, const float* v) {
+        tmem_ld_wait();
 #pragma unroll
         for (int q4 = 0; q4 < 32; q4 += 4) {
           const float4 s4 = sqv[(c + q4) >> 2];                          // shared-memory broadcast
-          const float sj[4] = {s4.x, s4.y, s4.z, s4.w};
+          v[q4 + 0] = __fadd_rn(fmaf(v[q4 + 0], -2.0f, sqi), s4.x);
+          v[q4 + 1] = __fadd_rn(fmaf(v[q4 + 1], -2.0f, sqi), s4.y);
+          v[q4 + 2] = __fadd_rn(fmaf(v[q4 + 2], -2.0f, sqi), s4.z);
+          v[q4 + 3] = __fadd_rn(fmaf(v[q4 + 3], -2.0f, sqi), s4.w);
+        }
+      };
+      // Branch-free sorted insertion (a select network): rows of a warp are independent, so a
+      // data-dependent branch would be taken by some lane at almost every column and serialise the
+      // warp.  Strict '<' keeps the earlier (lower index) entry ahead on exact ties.
+      auto insert = [&](float dv, int jl) {
+        bool lt[KMAX];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-          const int q = q4 + u;
-          float dv = __fadd_rn(fmaf(v[q], -2.0f, sqi), sj[u]);           // (sq_i + (-2 dot)) + sq_j
-          const int jl = c + q - lo_col;
-          // Branch-free sorted insertion (a select network): rows of a warp are independent, so a
-          // data-dependent branch here would be taken by some lane at almost every column and
-          // serialise the warp.  Strict '<' keeps the lower index ahead on exact ties.
-          if (!((unsigned)jl < ncols)) dv = INFINITY;                     // outside this row's graph
-          bool lt[KMAX];
+        for (int t = 0; t < KMAX; ++t) lt[t] = dv < bd[t];
 #pragma unroll
-          for (int t = 0; t < KMAX; ++t) lt[t] = dv < bd[t];
+        for (int t = KMAX - 1; t > 0; --t) {
+          bd[t] = lt[t - 1] ? bd[t - 1] : (lt[t] ? dv : bd[t]);
+          bj[t] = lt[t - 1] ? bj[t - 1] : (lt[t] ? jl : bj[t]);
+        }
+        bd[0] = lt[0] ? dv : bd[0];
+        bj[0] = lt[0] ? jl : bj[0];
+      };
+      auto full_scan = [&]() {
+        for (int c = 0; c < p.bn; c += 32) {
+          load_dist(c);
 #pragma unroll
-          for (int t = KMAX - 1; t > 0; --t) {
-            bd[t] = lt[t - 1] ? bd[t - 1] : (lt[t] ? dv : bd[t]);
-            bj[t] = lt[t - 1] ? bj[t - 1] : (lt[t] ? jl : bj[t]);
-          }
-          bd[0] = lt[0] ? dv : bd[0];
-          bj[0] = lt[0] ? jl : bj[0];
+          for (int q = 0; q < 32; ++q) {
+            const int jl = c + q - lo_col;
+            insert(((unsigned)jl < ncols) ? v[q] : INFINITY, jl);         // outside this row's graph: never
           }
         }
       };
-      for (int c = half * 32; c < p.bn; c += 64) {               // bn is 128 or 256: 2 or 4 chunks per group
-        fetch(c, va);
-        tmem_ld_wait();
-        if (c + 64 >= p.bn) {                                    // my share of this accumulator has been read
-          tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[buf]);
-        }
-        scan(c, va);
-      }
-      // merge: group 1 hands its sorted list to group 0, which inserts it under the (distance, index)
-      // lexicographic order (the two groups saw interleaved index ranges)
-      if (half == 1) {
+      if (p.thresh) {
+        // ---- pass 1: tau = (k*d)-th smallest of the 16 column-group minima ----
+        float tb[KMAX];
 #pragma unroll
-        for (int t = 0; t < KMAX; ++t) { s_md[t][r] = bd[t]; s_mj[t][r] = bj[t]; }
-      }
-      named_bar_sync(2, KT_EPI_THREADS);
-      if (half == 0) {
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-          const float dv = s_md[c][r];
-          const int jl = s_mj[c][r];
-          bool lt[KMAX];
-#pragma unroll
-          for (int t = 0; t < KMAX; ++t) lt[t] = dv < bd[t] || (dv == bd[t] && jl < bj[t]);
-#pragma unroll
-          for (int t = KMAX - 1; t > 0; --t) {
-            bd[t] = lt[t - 1] ? bd[t - 1] : (lt[t] ? dv : bd[t]);
-            bj[t] = lt[t - 1] ? bj[t - 1] : (lt[t] ? jl : bj[t]);
-          }
-          bd[0] = lt[0] ? dv : bd[0];
-          bj[0] = lt[0] ? jl : bj[0];
-        }
-        if (row_ok) {
+        for (int t = 0; t < KMAX; ++t) tb[t] = INFINITY;
+        auto push_min = [&](float x) {                  // value-only sorted insertion (min / max chain)
 #pragma unroll
           for (int t = 0; t < KMAX; ++t) {
-            if (t < p.kk && (t % p.d) == 0) {
-              const int64_t o = grow * p.k + t / p.d;
-              p.idx[o] = bj[t];
-              if (p.dist) p.dist[o] = bd[t];
+            const float lo = fminf(tb[t], x);
+            x = fmaxf(tb[t], x);
+            tb[t] = lo;
+          }
+        };
+        for (int c = 0; c < p.bn; c += 32) {
+          load_dist(c);
+          float m8[4];
+#pragma unroll
+          for (int b8 = 0; b8 < 4; ++b8) {
+            float m = fminf(fminf(fminf(v[8 * b8], v[8 * b8 + 1]), fminf(v[8 * b8 + 2], v[8 * b8 + 3])),
+                            fminf(fminf(v[8 * b8 + 4], v[8 * b8 + 5]), fminf(v[8 * b8 + 6], v[8 * b8 + 7])));
+            if (!full_tile && !((unsigned)(c + 8 * b8 - lo_col) < ncols)) m = INFINITY;
+            m8[b8] = m;
+          }
+          if (gshift == 4) {
+            push_min(fminf(m8[0], m8[1]));
+            push_min(fminf(m8[2], m8[3]));
+          } else {
+#pragma unroll
+            for (int b8 = 0; b8 < 4; ++b8) push_min(m8[b8]);
+          }
+        }
+        float tau = INFINITY;
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t)
+          if (t == p.kk - 1) tau = tb[t];
+        // ---- pass 2: append every distance <= tau (column order) to the row's candidate list ----
+        // Predicated PTX (a compare, a predicated 64-bit shared store, a predicated pointer bump): as C++
+        // the compiler emitted a divergent branch per distance (45 cycles each in the profile).  The
+        // write pointer is clamped into the 8-slot sink once per 8 columns; reaching the sink = overflow.
+        uint32_t wp = lst_addr;
+        for (int c = 0; c < p.bn; c += 32) {
+          load_dist(c);
+#pragma unroll
+          for (int b8 = 0; b8 < 4; ++b8) {
+            const float tq = (full_tile || (unsigned)(c + 8 * b8 - lo_col) < ncols) ? tau : -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int q = 8 * b8 + u;
+              // the bump goes through a fresh register (selp + add): bumping the store's own address
+              // register in place made every add wait for the store to release it (short-scoreboard
+              // stall, ~30 cycles per distance in the profile)
+              uint32_t bump;
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t"
+                  "setp.le.f32 p, %2, %3;\n\t"
+                  "@p st.shared.v2.b32 [%1], {%4, %5};\n\t"
+                  "selp.u32 %0, 1024, 0, p;\n\t}"
+                  : "=r"(bump)
+                  : "r"(wp), "f"(v[q]), "f"(tq), "r"(__float_as_uint(v[q])), "r"(c + q)
+                  : "memory");
+              wp += bump;
             }
+            wp = min(wp, lst_sink);
+          }
+        }
+        const int cnt = (int)((wp - lst_addr) >> 10);   // == L: the list may have overflowed
+        if (__any_sync(0xffffffffu, cnt >= L)) {
+          full_scan();                                  // mass ties: exact fallback for this warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[buf]);
+        } else {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[buf]);            // TMEM reads done: the accumulator may be overwritten
+          for (int i = 0; i < cnt; ++i) {               // divergent trip count, a handful per row
+            const float2 e = lst[i * TC_BM];
+            insert(e.x, __float_as_int(e.y) - lo_col);
+          }
+        }
+      } else {
+        full_scan();
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[buf]);
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+          if (t < p.kk && (t % p.d) == 0) {
+            const int64_t o = grow * p.k + t / p.d;
+            p.idx[o] = bj[t];
+            if (p.dist) p.dist[o] = bd[t];
           }
         }
       }
@@ -346,15 +423,16 @@ size_t knn_tc_workspace_bytes(int B, int N) { return ((size_t)B * N + 128) * 2 *
 
 template <int KMAX>
 static int knn_tc_launch_t(const CUtensorMap& mc, KnnTcParams p, int grid, cudaStream_t st) {
-  // stages: whatever fits beside the kernel's static shared memory (the merge lists grow with KMAX)
+  // dynamic shared memory: operand stages, then the two groups' candidate lists
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, knn_tc_kernel<KMAX>);
   const size_t stage_bytes = 2 * (size_t)p.bn * TC_BK * 4;
-  int stages = (int)((227 * 1024 - fa.sharedSizeBytes - 2048) / stage_bytes);
+  const size_t list_bytes = 2 * (size_t)(KMAX + 8 + 8) * TC_BM * sizeof(float2);
+  int stages = (int)((227 * 1024 - fa.sharedSizeBytes - 2048 - list_bytes) / stage_bytes);
   if (stages > KT_MAX_STAGES) stages = KT_MAX_STAGES;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const size_t smem = stage_bytes * stages + 1024;
+  const size_t smem = stage_bytes * stages + list_bytes + 1024;
   cudaFuncSetAttribute(knn_tc_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   knn_tc_kernel<KMAX><<<grid, KT_THREADS, smem, st>>>(mc, p);
   return check_launch("knn_tc");
@@ -381,6 +459,12 @@ int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int
   p.N = N; p.C = C; p.kk = kk; p.d = d; p.k = k; p.M = M;
   p.bn = N >= TC_BM ? N : TC_BM;
   p.idx = idx; p.dist = dist;
+  {
+    static int no_thresh = -1;
+    if (no_thresh < 0) { const char* e = getenv("GRAFP_KNN_NO_THRESH"); no_thresh = e ? atoi(e) : 0; }
+    const int groups_per_graph = (N < p.bn ? N : p.bn) / (p.bn / 16);   // column groups of one graph
+    p.thresh = (!no_thresh && kk <= groups_per_graph) ? 1 : 0;
+  }
   uint32_t cols = 32;
   while ((int)cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
