@@ -640,7 +640,9 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   const int64_t tiles_m = (a.m + TC_BM - 1) / TC_BM;
   static int mc_env = -1;
   if (mc_env < 0) { const char* e = getenv("GRAFP_TC_CLUSTER"); mc_env = e ? atoi(e) : 2; }
-  const int cluster = (mc_env == 2 && tiles_m >= 2 && bn % 64 == 0 && sm_count() % 2 == 0) ? 2 : 1;
+  // CTA pairs with weight multicast pay off only for full-width tiles (measured on B200: bn = 256 3-7 % faster,
+  // bn <= 128 10-30 % slower than independent CTAs -- the pair's lock-step costs more than the L2 traffic saved)
+  const int cluster = (mc_env == 2 && tiles_m >= 2 && bn >= 256 && sm_count() % 2 == 0) ? 2 : 1;
   if (bf16) {
     if (int rc = tc_make_map_2d_bf16(&mW, a.w_split_bf16, (int64_t)n_total * 2, a.k1 + a.k2, a.ldw,
                                      cluster == 2 ? bn / 2 : bn))
