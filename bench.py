@@ -210,6 +210,21 @@ class KernelTimer:
         return out
 
 
+def ncu_traffic(segments: int) -> dict:
+    """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum summed over a kernel class's launches of
+    one forward), from the committed ncu capture profiles/ncu_traffic.json (bytes per segment, measured at 4096
+    segments per GPU, scripts/ncu_launches.py), scaled to this run's batch.  Empty if the file is absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except (OSError, ValueError):
+        return {}
+    out = {k: v * segments for k, v in d.get("bytes_per_segment", {}).items()}
+    out["note"] = d.get("note")
+    return out
+
+
 def run_native(args):
     import torch.distributed as dist
     from neuralsampleid_b200 import _lib, ops
@@ -281,6 +296,14 @@ def run_native(args):
     with torch.no_grad():
         for _ in range(max(3, args.warmup)):
             forward_resident()
+        if os.environ.get("GRAFP_NCU_RANGE"):
+            # one eager, real-data forward inside a profiler range: `ncu --profile-from-start off` then sees
+            # exactly the kernels of one step (weights already prepared, no graph replay)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
+            enc(x_dev)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
         # ---- device-resident timing ----
         sampler = ClockSampler(local)
         barrier()
@@ -360,6 +383,7 @@ def run_native(args):
     value = seg_per_step * args.steps / (ms_total * 1e-3)
     e2e_value = seg_per_step * args.steps / (ms_e2e * 1e-3)
     pk = peaks()
+    traffic = ncu_traffic(Bl_for_traffic := (hi - lo))
 
     # dominant kernel class (by C-ABI entry point) and its roofline
     by_entry = {}
@@ -383,14 +407,16 @@ def run_native(args):
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "ms_per_step": knn["ms"],
                 "algorithmic_bytes_per_step": knn_b},
     }
-    for v in stage_rooflines.values():
+    for kname, v in stage_rooflines.items():
         v["frac"] = v["achieved"] / v["peak"] if v["achieved"] else None
+        v["traffic"] = traffic.get(kname)
     if dominant == "grafp_gemm_fwd":
         g_all = by_entry["grafp_gemm_fwd"]
         achieved = g_all["flops"] / (g_all["ms"] * 1e-3) / 1e12
         roofline = {"kernel": "gemm_tc_kernel / gemm_simt_kernel (all 1x1-conv GEMMs of the step)",
                     "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic.get("gemm"),
+                    "traffic_note": traffic.get("note"),
                     "peak_source": pk["source"] + " dense bf16 (cuBLAS, sustained)",
                     "note": "achieved counts useful 2*M*N*K flops; the fp32-parity engines issue 3 MMA passes "
                             "per k-step (auto/bf16x3: kind::f16 -> ceiling peak/3; 3xtf32: kind::tf32 at half "
@@ -403,7 +429,7 @@ def run_native(args):
         key = "aggregate" if dominant == "grafp_mr_aggregate_fwd" else "knn"
         r = stage_rooflines[key]
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": r["achieved"], "peak": r["peak"],
-                    "unit": "GB/s", "frac": r["frac"], "traffic": None,
+                    "unit": "GB/s", "frac": r["frac"], "traffic": r.get("traffic"),
                     "peak_source": pk["source"], "share_of_step": by_entry[dominant]["ms"] / step_ms_instr}
 
     if rank != 0:
