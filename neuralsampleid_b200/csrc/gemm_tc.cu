@@ -519,6 +519,22 @@ int tc_make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t co
   return 0;
 }
 
+// fp32 row-major, box = (16 cols = 64 B, box_rows), 64B swizzle (kNN's narrow k-blocks)
+int tc_make_map_2d_bk16(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows) {
+  EncodeTiledFn fn = tc_encode_fn();
+  GRAFP_REQUIRE(fn, "tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GRAFP_REQUIRE(r == CUDA_SUCCESS, "tc: cuTensorMapEncodeTiled(2d bk16) failed (%d)", (int)r);
+  return 0;
+}
+
 int tc_make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
                         int box_rows) {
   EncodeTiledFn fn = tc_encode_fn();

@@ -43,6 +43,7 @@ struct KnnTcParams {
   int N, C, kk, d, k;
   int64_t M;
   int bn;                 // columns per tile: N (N >= 128) or 128
+  int kbk;                // k-block width in fp32 elements: 32 (128-byte rows, 128B swizzle) or 16 (64B)
   int thresh;             // two-pass threshold selection (needs k*d <= column groups of a graph)
   int stages;
   const float* rinv; const float* sq;   // prepass outputs, or (rinv == nullptr) sq = raw sum of squares
@@ -109,7 +110,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 4;
+  // 256-column tiles use 16-wide k-blocks: a 32-wide stage is 64 KB, only two fit, and the TMA -> transform
+  // -> MMA chain of one tile could not overlap the next tile's loads (measured 11 k cycles per tile, all latency)
+  const uint32_t b_bytes = (uint32_t)p.bn * p.kbk * 4;
   // The 128 rows of a tile are a subset of its column set (same graph), so one stage holds only
   // the column operand [hi | lo]; the row operand is a 1024-aligned window into it.
   const uint32_t stage_bytes = 2u * b_bytes;
@@ -117,7 +120,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
   auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
   auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + b_bytes; };
 
-  const int nkb = p.C / TC_BK;
+  const int nkb = p.C / p.kbk;
   const int64_t total_tiles = (p.M + TC_BM - 1) / TC_BM;
   auto col_start = [&](int64_t m0) -> int64_t { return p.N >= TC_BM ? (m0 / p.N) * p.N : m0; };
 
@@ -150,7 +153,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], b_bytes);
-          tma_load_2d(b_hi(s), &tmCols, kb * TC_BK, (int)c0, &full_bar[s]);
+          tma_load_2d(b_hi(s), &tmCols, kb * p.kbk, (int)c0, &full_bar[s]);
         }
       }
     }
@@ -164,18 +167,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn;
         const int64_t m0 = tile * TC_BM;
-        const uint32_t row_off = (uint32_t)(m0 - col_start(m0)) * (TC_BK * 4);   // 0 or 16 KB
+        const uint32_t row_off = (uint32_t)(m0 - col_start(m0)) * (uint32_t)(p.kbk * 4);   // 0 or 128 rows
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(&xf_bar[s], ph);
           tc_fence_after();
-          const uint64_t dah = umma_desc_sw128(smem_u32(b_hi(s)) + row_off);
-          const uint64_t dal = umma_desc_sw128(smem_u32(b_lo(s)) + row_off);
-          const uint64_t dbh = umma_desc_sw128(smem_u32(b_hi(s)));
-          const uint64_t dbl = umma_desc_sw128(smem_u32(b_lo(s)));
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
+          const bool w64 = p.kbk == 16;                  // 64-byte operand rows: 64B swizzle descriptors
+          const uint64_t dah = w64 ? umma_desc_sw64(smem_u32(b_hi(s)) + row_off) : umma_desc_sw128(smem_u32(b_hi(s)) + row_off);
+          const uint64_t dal = w64 ? umma_desc_sw64(smem_u32(b_lo(s)) + row_off) : umma_desc_sw128(smem_u32(b_lo(s)) + row_off);
+          const uint64_t dbh = w64 ? umma_desc_sw64(smem_u32(b_hi(s))) : umma_desc_sw128(smem_u32(b_hi(s)));
+          const uint64_t dbl = w64 ? umma_desc_sw64(smem_u32(b_lo(s))) : umma_desc_sw128(smem_u32(b_lo(s)));
+          const int ksteps = p.kbk / 8;
+          for (int k = 0; k < ksteps; ++k) {
             const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
             umma_tf32(tacc, dal + koff, dbh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             umma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
@@ -192,14 +196,31 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
     const int t = threadIdx.x - 320;
     const int per = (int)(b_bytes / 16) / KT_XF_THREADS;          // float4 per thread per stage: 4 or 8
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // the row scales of a tile come from global memory: they are fetched one tile ahead so their latency
+    // hides behind the previous tile's k-loop (the profile showed the transform warps stalled ~45 % of
+    // the time on these loads at every tile start, with the MMA starving behind them)
+    // Only the raw loads are issued ahead; the sqrt / reciprocal that consume them run at the next tile's
+    // start, when the data has long arrived.
+    auto load_raw = [&](int64_t tile, float (&dst)[8]) {
       const int64_t c0 = col_start(tile * TC_BM);
+      const int rsh = p.kbk == 16 ? 2 : 3;             // float4 per operand row: 4 or 8
+      const float* src = p.rinv ? p.rinv : p.sq;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t node = c0 + (t >> rsh) + (KT_XF_THREADS >> rsh) * i;
+        dst[i] = (tile < total_tiles && i < per && node < p.M) ? __ldg(src + node) : 0.0f;
+      }
+    };
+    float ri_next[8];
+    load_raw(blockIdx.x, ri_next);
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       float ri[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int64_t node = c0 + (t >> 3) + 32 * i;
-        ri[i] = (i < per && node < p.M) ? knn_node_norm(p, node).x : 0.0f;
+        const float s0 = ri_next[i];                   // rinv itself (prepass) or the raw sum of squares
+        ri[i] = p.rinv ? s0 : (p.normalize ? __frcp_rn(fmaxf(sqrtf(s0), 1e-12f)) : 1.0f);
       }
+      load_raw(tile + gridDim.x, ri_next);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1u;
@@ -243,21 +264,38 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
     const uint32_t lst_addr = smem_u32(lst), lst_sink = lst_addr + (uint32_t)L * TC_BM * 8u;
     const bool full_tile = p.N >= p.bn;          // every column of the tile belongs to the row's graph
     const int gshift = p.bn == 256 ? 4 : 3;      // log2(columns per group): 16 groups per tile
+    // squared norms (own row + two staged columns) are fetched one of MY tiles ahead (raw loads only)
+    auto sq_final = [&](float s0) {
+      if (p.rinv || !p.normalize) return s0;
+      const float ri = __frcp_rn(fmaxf(sqrtf(s0), 1e-12f));
+      return s0 * ri * ri;
+    };
+    auto load_sq_raw = [&](int64_t tile, float (&dst)[3]) {
+      const int64_t m0 = tile * TC_BM, c0 = col_start(m0);
+      const bool ok = tile < total_tiles;
+      dst[0] = (ok && m0 + r < p.M) ? __ldg(p.sq + m0 + r) : 0.0f;
+      dst[1] = (ok && c0 + et < p.M) ? __ldg(p.sq + c0 + et) : 0.0f;
+      dst[2] = (ok && p.bn > 128 && c0 + 128 + et < p.M) ? __ldg(p.sq + c0 + 128 + et) : 0.0f;
+    };
+    float sq_next[3];
+    load_sq_raw((int64_t)blockIdx.x + (int64_t)grp * gridDim.x, sq_next);
     uint32_t ti = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       if ((ti & 1u) != grp) continue;
       const int64_t m0 = tile * TC_BM, c0 = col_start(m0);
+      const float sq_now[3] = {sq_final(sq_next[0]), sq_final(sq_next[1]), sq_final(sq_next[2])};
+      load_sq_raw(tile + 2 * (int64_t)gridDim.x, sq_next);
       const uint32_t buf = grp, tph = (ti >> 1) & 1u;
       const int64_t grow = m0 + r;
       const bool row_ok = grow < p.M;
       const int64_t gs = row_ok ? (grow / p.N) * p.N : c0;     // first node of this row's graph
       const int lo_col = (int)(gs - c0);                       // its first column inside the tile
       const unsigned ncols = row_ok ? (unsigned)p.N : 0u;      // columns [lo_col, lo_col + N) are its graph
-      const float sqi = row_ok ? knn_node_norm(p, grow).y : 0.0f;
-      // stage the column set's squared norms (the workspace is padded: reads past M are harmless)
+      const float sqi = row_ok ? sq_now[0] : 0.0f;
+      // stage the column set's squared norms
       float* ssq = s_sq[grp][(ti >> 1) & 1u];
-      ssq[et] = (c0 + et < p.M) ? knn_node_norm(p, c0 + et).y : 0.0f;
-      if (p.bn > 128) ssq[et + 128] = (c0 + 128 + et < p.M) ? knn_node_norm(p, c0 + 128 + et).y : 0.0f;
+      ssq[et] = sq_now[1];
+      if (p.bn > 128) ssq[et + 128] = sq_now[2];
       named_bar_sync(1 + (int)grp, 128);
       const float4* sqv = reinterpret_cast<const float4*>(ssq);
       float bd[KMAX];
@@ -412,7 +450,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
 
 int knn_tc_supported(int B, int N, int C, int kk) {
   if (kk > 16) return 0;
-  if (C % TC_BK != 0) return 0;
+  if (C % TC_BK != 0) return 0;   // (16-wide k-blocks are an internal choice for 256-column tiles)
   if (N > 256) return 0;
   if (N >= TC_BM) return N % TC_BM == 0;
   return N >= 16 && TC_BM % N == 0;
@@ -426,7 +464,7 @@ static int knn_tc_launch_t(const CUtensorMap& mc, KnnTcParams p, int grid, cudaS
   // dynamic shared memory: operand stages, then the two groups' candidate lists
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, knn_tc_kernel<KMAX>);
-  const size_t stage_bytes = 2 * (size_t)p.bn * TC_BK * 4;
+  const size_t stage_bytes = 2 * (size_t)p.bn * p.kbk * 4;
   const size_t list_bytes = 2 * (size_t)(KMAX + 8 + 8) * TC_BM * sizeof(float2);
   int stages = (int)((227 * 1024 - fa.sharedSizeBytes - 2048 - list_bytes) / stage_bytes);
   if (stages > KT_MAX_STAGES) stages = KT_MAX_STAGES;
@@ -468,8 +506,13 @@ int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int
   uint32_t cols = 32;
   while ((int)cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
+  p.kbk = p.bn > 128 ? 16 : TC_BK;
   CUtensorMap mc;
-  if (int rc = tc_make_map_2d(&mc, x, M, C, C, p.bn)) return rc;
+  if (p.kbk == 16) {
+    if (int rc = tc_make_map_2d_bk16(&mc, x, M, C, C, p.bn)) return rc;
+  } else if (int rc = tc_make_map_2d(&mc, x, M, C, C, p.bn)) {
+    return rc;
+  }
   const int64_t tiles = (M + TC_BM - 1) / TC_BM;
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;

@@ -183,6 +183,9 @@ EncodeTiledFn tc_encode_fn();
 // fp32 row-major (rows, cols), row stride ld elements; box = (32 cols, box_rows), 128B swizzle
 int tc_make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
                    int box_rows);
+// fp32 row-major, box = (16 cols = 64 B, box_rows), 64B swizzle
+int tc_make_map_2d_bk16(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows);
 // bf16 row-major (rows, cols), row stride ld elements; box = (32 cols = 64 B, box_rows), 64B swizzle
 int tc_make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
                         int box_rows);
