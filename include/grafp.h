@@ -153,6 +153,15 @@ int grafp_split_tf32(const float* w, int64_t count, float* out_hi_lo, void* stre
 /* bf16 operand split: out (bf16)[0:count] = bf16(w), out[count:2*count] = bf16(w - bf16(w)) */
 int grafp_split_bf16(const float* w, int64_t count, void* out_bf16_hi_lo, void* stream);
 
+/* Stem: Conv2d(Cin -> Cout, 1x1, no bias) + BatchNorm2d + activation on a tiny input width
+ * (encoder/graph_encoder.py:151-153, 201-202), fused with the layout change: reads the reference's
+ * (B, Cin, N) tensor directly (nchw != 0) or node-major (B*N, Cin) features (nchw == 0, what
+ * grafp_peak_extract_fwd emits) and writes node-major (B*N, Cout):
+ *   out[b*N + n, j] = act(scale[j] * sum_k x[b, k, n] * w[j, k] + shift[j]).
+ * Cin in {4, 8, 16}; Cout = 4 * (a divisor of 256). */
+int grafp_stem_fwd(const float* x, const float* w, const float* scale, const float* shift, int B, int Cin,
+                   int N, int Cout, int nchw, int act, float act_param, float* out, void* stream);
+
 /* mean over the nodes of each graph: x (B*N, C) -> out (B, C)   (graph_encoder.py:211) */
 int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "grafp_split_tf32": [_P, _L, _P, _P],
     "grafp_split_bf16": [_P, _L, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
+    "grafp_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P],
     "grafp_peak_extract_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "grafp_l2_normalize_rows": [_P, _L, _I, _F, _P, _P],
     "grafp_ntxent_fwd": [_P, _I, _I, _F, _I, _I, _P, _P, _P],

@@ -166,6 +166,62 @@ __global__ void peak_extract_kernel(const float* __restrict__ spec, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Stem: per-node linear with a tiny input width (Conv2d(Cin -> Cout, 1x1) + BN + activation,
+// graph_encoder.py:151-153) straight from the reference's (B, Cin, N) layout.  K = Cin <= 16 is
+// far below a tensor-core k-block; the op is one streaming write of the (B*N, Cout) output, so a
+// graph per CTA is staged in shared memory and every warp store covers whole output rows.
+// ---------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256)
+stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+            const float* __restrict__ shift, int B, int N, int Cout, int nchw, int act, float act_param,
+            float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* xs = sm;                          // [CIN][N] (k-major)
+  float* ws = xs + (size_t)CIN * N;        // [CIN][Cout] (k-major)
+  const int tid = threadIdx.x;
+  for (int i = tid; i < CIN * Cout; i += 256) {
+    const int n = i / CIN, k = i - n * CIN;            // w is (Cout, CIN) row-major
+    ws[k * Cout + n] = w[i];
+  }
+  const int cgs = Cout >> 2;                           // float4 column groups per row
+  const int cg = tid % cgs, rl = tid / cgs, rows_in_flight = 256 / cgs;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (scale) sc = *reinterpret_cast<const float4*>(scale + 4 * cg);
+  if (shift) sh = *reinterpret_cast<const float4*>(shift + 4 * cg);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();                                   // previous graph fully consumed (and ws written)
+    const float* xb = x + (size_t)b * CIN * N;
+    if (nchw) {
+      for (int i = tid; i < CIN * N; i += 256) xs[i] = xb[i];
+    } else {
+      for (int i = tid; i < CIN * N; i += 256) {       // (N, CIN) node-major -> k-major
+        const int n = i / CIN, k = i - n * CIN;
+        xs[k * N + n] = xb[i];
+      }
+    }
+    __syncthreads();
+    float4* ob = reinterpret_cast<float4*>(out + (size_t)b * N * Cout);
+    for (int n = rl; n < N; n += rows_in_flight) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < CIN; ++k) {
+        const float a = xs[k * N + n];
+        const float4 wv = *reinterpret_cast<const float4*>(ws + k * Cout + 4 * cg);
+        acc.x = fmaf(a, wv.x, acc.x); acc.y = fmaf(a, wv.y, acc.y);
+        acc.z = fmaf(a, wv.z, acc.z); acc.w = fmaf(a, wv.w, acc.w);
+      }
+      float4 o;
+      o.x = apply_act(fmaf(acc.x, sc.x, sh.x), act, act_param);
+      o.y = apply_act(fmaf(acc.y, sc.y, sh.y), act, act_param);
+      o.z = apply_act(fmaf(acc.z, sc.z, sh.z), act, act_param);
+      o.w = apply_act(fmaf(acc.w, sc.w, sh.w), act, act_param);
+      stg_stream(ob + (size_t)n * cgs + cg, o);
+    }
+  }
+}
+
 }  // namespace grafp
 
 using namespace grafp;
@@ -220,6 +276,34 @@ int grafp_peak_extract_fwd(const float* spec, const float* w, const float* bias,
   peak_extract_kernel<<<B, 256, smem, as_stream(stream)>>>(spec, w, bias, n_mels, n_frames, F, pb,
                                                           pf, out);
   return check_launch("peak_extract");
+}
+
+int grafp_stem_fwd(const float* x, const float* w, const float* scale, const float* shift, int B, int Cin,
+                   int N, int Cout, int nchw, int act, float act_param, float* out, void* stream) {
+  GRAFP_REQUIRE(B == 0 || (x && w && out), "stem: null pointer");
+  GRAFP_REQUIRE(Cin == 4 || Cin == 8 || Cin == 16, "stem: Cin=%d (supported: 4, 8, 16; use grafp_gemm_fwd)", Cin);
+  GRAFP_REQUIRE(Cout % 4 == 0 && Cout >= 4 && Cout <= 1024 && 256 % (Cout / 4) == 0,
+                "stem: Cout=%d must be 4 * a divisor of 256", Cout);
+  GRAFP_REQUIRE(act >= GRAFP_ACT_NONE && act <= GRAFP_ACT_ELU, "stem: unknown activation %d", act);
+  GRAFP_REQUIRE(N > 0, "stem: N must be positive");
+  if (B == 0) return 0;
+  const size_t smem = ((size_t)Cin * N + (size_t)Cin * Cout) * sizeof(float);
+  GRAFP_REQUIRE(smem <= 96 * 1024, "stem: graph too large for shared memory");
+  int grid = sm_count() * 4;
+  if (B < grid) grid = B;
+  cudaStream_t st = as_stream(stream);
+#define GRAFP_STEM_CASE(C)                                                                           \
+  case C:                                                                                            \
+    cudaFuncSetAttribute(stem_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);    \
+    stem_kernel<C><<<grid, 256, smem, st>>>(x, w, scale, shift, B, N, Cout, nchw, act, act_param, out); \
+    break;
+  switch (Cin) {
+    GRAFP_STEM_CASE(4)
+    GRAFP_STEM_CASE(8)
+    GRAFP_STEM_CASE(16)
+  }
+#undef GRAFP_STEM_CASE
+  return check_launch("stem");
 }
 
 }  // extern "C"

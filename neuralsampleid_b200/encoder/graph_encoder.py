@@ -167,10 +167,16 @@ class GraphEncoder(_Cached):
                     m.bias.requires_grad = True
 
     # ------------------------------------------------------------------------------------
-    def _stem_nodes(self, x_nodes):
+    def _stem_lin(self):
         conv, bn = self.stem[0], self.stem[1]
-        lin = self._memo("stem", (conv.weight,) + _bn_tensors(bn),
-                         lambda: make_linear(*fold_conv_bn(conv.weight, None, bn)))
+        return self._memo("stem", (conv.weight,) + _bn_tensors(bn),
+                          lambda: make_linear(*fold_conv_bn(conv.weight, None, bn)))
+
+    def _stem_nodes(self, x_nodes, B=None, N=None):
+        lin = self._stem_lin()
+        cout, cin = lin.w.shape
+        if B is not None and lin.groups == 1 and ops.stem_supported(cin, cout, N):
+            return ops.stem(x_nodes, lin, "leakyrelu", self.stem[2].negative_slope, B, N)
         return ops.linear(x_nodes, lin, "leakyrelu", self.stem[2].negative_slope)
 
     def _proj(self, mean):
@@ -195,13 +201,18 @@ class GraphEncoder(_Cached):
                                "statistics); call .eval() for inference")
         if x.dim() != 3:
             raise ValueError("expected (B, C, N) input, got %s" % (tuple(x.shape),))
-        B, _, N = x.shape
+        B, cin, N = x.shape
+        lin = self._stem_lin()
+        if lin.groups == 1 and ops.stem_supported(cin, lin.w.shape[0], N):
+            # stem fused with the layout change: reads (B, C, N) directly, writes node-major
+            h = ops.stem(x, lin, "leakyrelu", self.stem[2].negative_slope)
+            return self.forward_nodes(None, B, N, return_pre_proj, forced_idx, taps, stem_out=h)
         return self.forward_nodes(ops.nchw_to_nodes(x), B, N, return_pre_proj, forced_idx, taps)
 
-    def forward_nodes(self, x_nodes, B, N, return_pre_proj=False, forced_idx=None, taps=None):
+    def forward_nodes(self, x_nodes, B, N, return_pre_proj=False, forced_idx=None, taps=None, stem_out=None):
         """Eval forward from node-major (B*N, in_channels) features (what the peak extractor
         kernel emits), skipping the NCHW round trip."""
-        h = self._stem_nodes(x_nodes)
+        h = stem_out if stem_out is not None else self._stem_nodes(x_nodes, B, N)
         blk = 0
         for entry in self.backbone:
             if isinstance(entry, Downsample):

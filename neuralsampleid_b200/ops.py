@@ -285,6 +285,28 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     return SplitAct(out) if out_split else out
 
 
+def stem_supported(cin: int, cout: int, N: int) -> bool:
+    return cin in (4, 8, 16) and cout % 4 == 0 and 4 <= cout <= 1024 and 256 % (cout // 4) == 0 and \
+        (cin * N + cin * cout) * 4 <= 96 * 1024
+
+
+def stem(x: torch.Tensor, lin, act=None, act_param: float = 0.0, B: int = None, N: int = None) -> torch.Tensor:
+    """Stem layer (tiny input width) over a prepared ``_prep.Linear``: x is the reference's (B, Cin, N)
+    tensor, or node-major (B*N, Cin) when B and N are given.  -> node-major (B*N, Cout)."""
+    x = _chk(x, name="x")
+    nchw = x.dim() == 3
+    if nchw:
+        B, cin, N = x.shape
+    else:
+        cin = x.shape[1]
+    cout = lin.w.shape[0]
+    out = torch.empty((B * N, cout), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_stem_fwd(_ptr(x), _ptr(lin.w), _ptr(lin.scale), _ptr(lin.shift), B, cin, N, cout,
+                                         int(nchw), act_code(act), act_param, _ptr(out), _stream(x)), "stem_fwd")
+    return out
+
+
 def node_mean(x: torch.Tensor, B: int, N: int) -> torch.Tensor:
     x = _chk(x, name="x")
     out = torch.empty((B, x.shape[1]), device=x.device, dtype=torch.float32)

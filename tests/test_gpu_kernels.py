@@ -346,6 +346,32 @@ def test_gemm_split_bf16_needs_bf16_engine():
         ops.linear(hs, lin, engine=_lib.ENGINES["simt"])
 
 
+@pytest.mark.parametrize("B,cin,N,cout", [(5, 8, 256, 64), (3, 4, 96, 32), (2, 16, 128, 128), (300, 8, 256, 64)])
+def test_stem_kernel_matches_gemm_route(B, cin, N, cout):
+    """grafp_stem_fwd (stem fused with the NCHW -> node-major layout change) against the generic route
+    (transpose + fp32 SIMT GEMM) and the fp64 reference; both input layouts."""
+    ops = _ops()
+    from neuralsampleid_b200 import _lib, _prep
+    x = synth.synth_uniform((B, cin, N), 40)
+    w = synth.synth_normal((cout, cin), 41) / float(np.sqrt(cin))
+    scale = synth.synth_uniform((cout,), 42, 0.5, 1.5)
+    shift = synth.synth_uniform((cout,), 43, -0.5, 0.5)
+    lin = _prep.make_linear(w.to(DEV), scale.to(DEV), shift.to(DEV), 1)
+    assert ops.stem_supported(cin, cout, N)
+    nodes = ops.nchw_to_nodes(x.to(DEV))
+    via_gemm = ops.linear(nodes, lin, "leakyrelu", 0.2, engine=_lib.ENGINE_SIMT)
+    got_nchw = ops.stem(x.to(DEV), lin, "leakyrelu", 0.2)
+    got_nodes = ops.stem(nodes, lin, "leakyrelu", 0.2, B, N)
+    assert torch.equal(got_nchw, got_nodes)
+    want = _gemm_ref(nodes.cpu(), w, scale, shift, "leakyrelu", 0.2, None, None, 1, 0)
+    for got in (got_nchw, via_gemm):
+        err = float((got.cpu().double() - want).abs().max() / want.abs().max())
+        assert err < 1e-5, err
+    assert not ops.stem_supported(12, 64, 256) and not ops.stem_supported(8, 20, 256)
+    with pytest.raises(_lib.GrafpError):
+        ops.stem(torch.zeros((2, 12, 64), device=DEV), _prep.make_linear(torch.zeros((64, 12), device=DEV), None, None, 1))
+
+
 def test_gemm_empty_and_errors():
     ops = _ops()
     from neuralsampleid_b200._lib import GrafpError
