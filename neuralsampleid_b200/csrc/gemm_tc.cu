@@ -33,7 +33,7 @@ namespace grafp {
 
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 480;
-constexpr int TC_RAW = 3;                       // depth of the fp32 A staging ring (bf16 engines)
+constexpr int TC_RAW_MAX = 8;                   // max depth of the fp32 A staging ring (bf16 engines)
 constexpr int TC_XF_THREADS = 128;
 constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_STORE_BYTES = TC_BM * 32 * 4;   // one 128 x 32 fp32 staging tile
@@ -54,6 +54,7 @@ struct TcParams {
   int act; float act_param;
   uint32_t tmem_cols;
   int y_split;         // output as bf16 [hi ; lo] planes (tmY is then the 3-D bf16 map)
+  int raw;             // depth of the fp32 A ring (bf16 engines with an fp32 A operand)
 };
 
 // v = act(v * scale + shift) + residual over one 32-column chunk of a row; scale/shift come from
@@ -99,8 +100,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t xf_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t raw_full_bar[TC_RAW];
-  __shared__ __align__(8) uint64_t raw_empty_bar[TC_RAW];
+  __shared__ __align__(8) uint64_t raw_full_bar[TC_RAW_MAX];
+  __shared__ __align__(8) uint64_t raw_empty_bar[TC_RAW_MAX];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -118,11 +119,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* store_buf = smem;                                  // 2 x 16 KB staging tiles
   // tf32: operand stages [A raw = hi | A_lo (3x) | B_hi | B_lo (3x)]
-  // bf16: a separate ring of TC_RAW fp32 A tiles (freed as soon as the transform has read them, so the
-  //       HBM-latency-bound A loads run up to TC_RAW k-blocks ahead of the MMA), then operand stages
+  // bf16: a separate ring of p.raw fp32 A tiles (freed as soon as the transform has read them, so the
+  //       HBM-latency-bound A loads run up to p.raw k-blocks ahead of the MMA), then operand stages
   //       [A_hi | A_lo (3x) | B_hi | B_lo (3x)]
   uint8_t* raw0 = smem + 2 * TC_STORE_BYTES;
-  uint8_t* stage0 = raw0 + ((kBf16 && !kASplit) ? TC_RAW * TC_A_BYTES : 0);
+  const int RAW = p.raw;
+  uint8_t* stage0 = raw0 + ((kBf16 && !kASplit) ? RAW * TC_A_BYTES : 0);
   auto a_raw = [&](int s) { return kBf16 ? raw0 + (size_t)s * TC_A_BYTES : stage0 + (size_t)s * stage_bytes; };
   auto a_hi = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return a_hi(s) + kAop; };
@@ -148,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       mbar_init(&xf_bar[s], TC_XF_THREADS);
       mbar_init(&empty_bar[s], kCluster);
     }
-    for (int r = 0; r < TC_RAW; ++r) {
+    for (int r = 0; r < TC_RAW_MAX; ++r) {
       mbar_init(&raw_full_bar[r], 1);
       mbar_init(&raw_empty_bar[r], TC_XF_THREADS);
     }
@@ -185,11 +187,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint64_t* abar;
           uint8_t* adst;
           if (kBf16) {
-            const int r = it % TC_RAW;
+            const int r = it % RAW;
             abar = &raw_full_bar[r];
             adst = a_raw(r);
             if (do_a) {
-              mbar_wait(&raw_empty_bar[r], ((it / TC_RAW) & 1u) ^ 1u);
+              mbar_wait(&raw_empty_bar[r], ((it / RAW) & 1u) ^ 1u);
               mbar_arrive_expect_tx(abar, TC_A_BYTES);
             }
             if (do_w) {
@@ -310,8 +312,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
-          const int rs = kBf16 ? (int)(it % TC_RAW) : s;
-          mbar_wait(kBf16 ? &raw_full_bar[rs] : &full_bar[s], kBf16 ? (it / TC_RAW) & 1u : ph);
+          const int rs = kBf16 ? (int)(it % RAW) : s;
+          mbar_wait(kBf16 ? &raw_full_bar[rs] : &full_bar[s], kBf16 ? (it / RAW) & 1u : ph);
           const float4* raw = reinterpret_cast<const float4*>(a_raw(rs));
           float4 v[PER];
 #pragma unroll
@@ -683,9 +685,25 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   const size_t np = passes == 3 ? 2 : 1;
   const size_t stage_bytes = bf16 ? np * ((size_t)TC_BM * 64 + (size_t)bn * 64)
                                   : np * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
-  const size_t fixed_bytes = 2 * TC_STORE_BYTES + ((bf16 && !asplit) ? (size_t)TC_RAW * TC_A_BYTES : 0);
+  // Shared-memory plan.  The fp32 A ring covers the HBM latency (a memory-bound shape needs ~75 KB in flight
+  // per SM to stream at the HBM rate), the operand stages only the transform -> MMA hand-off: narrow tiles
+  // (small stages) get a deep ring and three operand stages, 256-wide tiles keep three ring slots.
+  const size_t budget = 220 * 1024 - 1024 - 2 * TC_STORE_BYTES;      // 227 KB minus ~6 KB static
+  int raw = 0, stages;
+  if (bf16 && !asplit) {
+    static int raw_env = -1;
+    if (raw_env < 0) { const char* e = getenv("GRAFP_TC_RAW"); raw_env = e ? atoi(e) : 0; }
+    raw = 3;
+    if (3 * stage_bytes + 4 * TC_A_BYTES <= budget) {
+      raw = (int)((budget - 3 * stage_bytes) / TC_A_BYTES);
+      if (raw > TC_RAW_MAX) raw = TC_RAW_MAX;
+    }
+    if (raw_env >= 2 && raw_env <= TC_RAW_MAX) raw = raw_env;
+  }
+  p.raw = raw > 0 ? raw : 1;
+  const size_t fixed_bytes = 2 * TC_STORE_BYTES + (size_t)raw * TC_A_BYTES;
   const int nkb = (a.k1 + a.k2) / TC_BK;
-  int stages = (int)((220 * 1024 - fixed_bytes - 1024) / stage_bytes);   // 227 KB minus ~6 KB static
+  stages = (int)((220 * 1024 - fixed_bytes - 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 1) stages = 1;
   p.stages = stages;

@@ -17,6 +17,11 @@ SHAPES = [  # M, K, N, a_split, out_split, residual
     (1048576, 256, 64, True, False, True),
     (1048576, 64, 256, False, True, False),
     (524288, 512, 128, True, False, True),
+    # narrow fp32-A shapes of stages 1-2 (memory-bound)
+    (1048576, 64, 64, False, False, False),
+    (524288, 128, 128, False, False, False),
+    (524288, 128, 512, False, True, False),
+    (1048576, 128, 64, True, False, True),
     # what the fp32-A shapes would cost with a pre-split A (dual-output producers)
     (262144, 256, 1024, True, True, False),
     (131072, 512, 2048, True, True, False),
