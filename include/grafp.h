@@ -93,6 +93,18 @@ int grafp_mr_aggregate_fwd(const float* x, const int32_t* idx, int B, int N, int
  * dx must be initialised by the caller (it accumulates). */
 int grafp_mr_aggregate_bwd(const float* dm, const int32_t* idx, const uint8_t* arg, int B,
                            int N, int C, int k, float* dx, void* stream);
+/* Neighbour reductions of the other GraphConv2d variants (encoder/gcn_lib/torch_vertex.py:37-89),
+ * evaluated per node.  x (B*N, C), idx (B, N, k) int32 -> out (B*N, C) with row stride ldo >= C:
+ *   GRAFP_NBR_MAX       out = max_k x[idx]                              GraphSAGE (:66-67), applied to nn1(x)
+ *   GRAFP_NBR_SUM_SELF  out = (1 + *eps) * x + sum_k x[idx]             GINConv2d (:86-87); eps: device scalar
+ *                                                                       (may be NULL = 0)
+ *   GRAFP_NBR_EDGE_MAX  out = max_k act(scale * (x[idx] - x) + shift)   EdgeConv2d (:50-51) on P = W x: the
+ *                       1x1 conv commutes with the gather, the (B, 2C, N, k) edge tensor is never formed;
+ *                       scale / shift (C) = folded conv bias + BatchNorm (NULL = 1 / 0) */
+enum { GRAFP_NBR_MAX = 1, GRAFP_NBR_SUM_SELF = 2, GRAFP_NBR_EDGE_MAX = 3 };
+int grafp_nbr_reduce_fwd(const float* x, const int32_t* idx, int B, int N, int C, int k, int mode,
+                         const float* scale, const float* shift, int act, float act_param,
+                         const float* eps, float* out, int64_t ldo, void* stream);
 /* plain batched_index_select (torch_nn.py:79-98): out (B, C, N, k) from x (B*N, C). */
 int grafp_index_select(const float* x, const int32_t* idx, int B, int N, int C, int k,
                        float* out_bcnk, void* stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "grafp_mr_aggregate_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
     "grafp_mr_aggregate_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "grafp_index_select": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "grafp_nbr_reduce_fwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P, _P, _L, _P],
     "grafp_gemm_fwd": [C.POINTER(GemmArgs), _P],
     "grafp_gemm_tc_supported": [C.POINTER(GemmArgs)],
     "grafp_split_tf32": [_P, _L, _P, _P],

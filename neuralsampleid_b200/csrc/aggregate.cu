@@ -189,6 +189,152 @@ mr_aggregate_bwd_kernel(const float* __restrict__ dm, const int32_t* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Generalised neighbour reductions: the aggregation halves of the reference's other GraphConv2d
+// variants (encoder/gcn_lib/torch_vertex.py:37-89), evaluated per NODE instead of per edge:
+//   GRAFP_NBR_MAX       out = max_k x_j                                   (GraphSAGE, :66-67)
+//   GRAFP_NBR_SUM_SELF  out = (1 + eps) * x_i + sum_k x_j                 (GINConv2d, :86-87)
+//   GRAFP_NBR_EDGE_MAX  out = max_k act(scale * (x_j - x_i) + shift)      (EdgeConv2d, :50-51, applied to
+//                       P = W x: the 1x1 conv commutes with the gather, so the k-times larger edge tensor
+//                       and its GEMM are never formed; the activation is applied per edge, so any
+//                       activation -- monotone or not -- is exact)
+// Same staging as the max-relative kernel: whole graphs in shared memory via 1-D bulk copies.
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ float4 nbr_item(const float* __restrict__ sx, const int32_t* __restrict__ nb, int k,
+                                           int C, int node, int c0, float4 sc, float4 sh, int act,
+                                           float act_param, float self_w) {
+  const float4 xi = *reinterpret_cast<const float4*>(sx + (size_t)node * C + c0);
+  float4 r;
+  if (MODE == GRAFP_NBR_SUM_SELF) r = make_float4(0.f, 0.f, 0.f, 0.f);
+  else r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int t = 0; t < k; ++t) {
+    const int j = nb[t];
+    const float4 xj = *reinterpret_cast<const float4*>(sx + (size_t)j * C + c0);
+    if (MODE == GRAFP_NBR_MAX) {
+      r.x = fmaxf(r.x, xj.x); r.y = fmaxf(r.y, xj.y); r.z = fmaxf(r.z, xj.z); r.w = fmaxf(r.w, xj.w);
+    } else if (MODE == GRAFP_NBR_SUM_SELF) {
+      r.x += xj.x; r.y += xj.y; r.z += xj.z; r.w += xj.w;
+    } else {
+      const float ex = apply_act(fmaf(xj.x - xi.x, sc.x, sh.x), act, act_param);
+      const float ey = apply_act(fmaf(xj.y - xi.y, sc.y, sh.y), act, act_param);
+      const float ez = apply_act(fmaf(xj.z - xi.z, sc.z, sh.z), act, act_param);
+      const float ew = apply_act(fmaf(xj.w - xi.w, sc.w, sh.w), act, act_param);
+      r.x = fmaxf(r.x, ex); r.y = fmaxf(r.y, ey); r.z = fmaxf(r.z, ez); r.w = fmaxf(r.w, ew);
+    }
+  }
+  if (MODE == GRAFP_NBR_SUM_SELF) {
+    r.x = fmaf(self_w, xi.x, r.x); r.y = fmaf(self_w, xi.y, r.y);
+    r.z = fmaf(self_w, xi.z, r.z); r.w = fmaf(self_w, xi.w, r.w);
+  }
+  return r;
+}
+
+struct NbrParams {
+  const float* x; const int32_t* idx; int B, N, C, k;
+  const float* scale; const float* shift; int act; float act_param; const float* eps;
+  float* out; int64_t ldo;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(AGG_THREADS, 1)
+nbr_reduce_staged_kernel(const NbrParams p, int stages, uint32_t stage_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[AGG_MAX_STAGES];
+  const int N = p.N, C = p.C, k = p.k;
+  const uint32_t graph_bytes = (uint32_t)N * C * 4u, idx_bytes = (uint32_t)N * k * 4u;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int s, int g) {
+    unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
+    mbar_arrive_expect_tx(&full[s], graph_bytes + idx_bytes);
+    bulk_g2s(dst, p.x + (size_t)g * N * C, graph_bytes, &full[s]);
+    bulk_g2s(dst + graph_bytes, p.idx + (size_t)g * N * k, idx_bytes, &full[s]);
+  };
+  const int first = blockIdx.x, step = gridDim.x;
+  if (tid == 0)
+    for (int s = 0; s < stages; ++s)
+      if (first + s * step < p.B) issue(s, first + s * step);
+  const float self_w = (MODE == GRAFP_NBR_SUM_SELF) ? 1.0f + (p.eps ? __ldg(p.eps) : 0.0f) : 0.0f;
+  const int c4n = C >> 2, items = N * c4n;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int g = first; g < p.B; g += step) {
+    mbar_wait(&full[s], phase);
+    const float* gx = reinterpret_cast<const float*>(smem_raw + (size_t)s * stage_bytes);
+    const int32_t* gidx = reinterpret_cast<const int32_t*>(smem_raw + (size_t)s * stage_bytes + graph_bytes);
+    float* go = p.out + (size_t)g * N * p.ldo;
+    for (int it = tid; it < items; it += AGG_THREADS) {
+      const int node = it / c4n, c0 = (it - node * c4n) * 4;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == GRAFP_NBR_EDGE_MAX) {
+        if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+        if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+      }
+      const float4 r = nbr_item<MODE>(gx, gidx + node * k, k, C, node, c0, sc, sh, p.act, p.act_param, self_w);
+      __stcs(reinterpret_cast<float4*>(go + (size_t)node * p.ldo + c0), r);
+    }
+    fence_proxy_async_smem();             // generic-proxy reads of stage s before its async-proxy refill
+    __syncthreads();
+    if (tid == 0) {
+      const int gn = g + stages * step;
+      if (gn < p.B) issue(s, gn);
+    }
+    if (++s == stages) { s = 0; phase ^= 1u; }
+  }
+}
+
+// un-staged form (graphs that do not fit a stage, or unaligned sizes): gathers from global / L2
+template <int MODE>
+__global__ void __launch_bounds__(256)
+nbr_reduce_direct_kernel(const NbrParams p, int g0) {
+  const int g = g0 + blockIdx.y;
+  const int N = p.N, C = p.C, k = p.k;
+  const int c4n = C >> 2, items = N * c4n;
+  const float* gx = p.x + (size_t)g * N * C;
+  const int32_t* gidx = p.idx + (size_t)g * N * k;
+  float* go = p.out + (size_t)g * N * p.ldo;
+  const float self_w = (MODE == GRAFP_NBR_SUM_SELF) ? 1.0f + (p.eps ? __ldg(p.eps) : 0.0f) : 0.0f;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    const int node = it / c4n, c0 = (it - node * c4n) * 4;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == GRAFP_NBR_EDGE_MAX) {
+      if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+      if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    }
+    const float4 r = nbr_item<MODE>(gx, gidx + (size_t)node * k, k, C, node, c0, sc, sh, p.act, p.act_param, self_w);
+    *reinterpret_cast<float4*>(go + (size_t)node * p.ldo + c0) = r;
+  }
+}
+
+template <int MODE>
+static int nbr_reduce_launch(const NbrParams& p, cudaStream_t st) {
+  const size_t graph_bytes = (size_t)p.N * p.C * 4, idx_bytes = (size_t)p.N * p.k * 4;
+  const size_t budget = 216 * 1024, stage_bytes = graph_bytes + idx_bytes;
+  if (stage_bytes <= budget / 2 && graph_bytes % 16 == 0 && idx_bytes % 16 == 0) {
+    int stages = (int)(budget / stage_bytes);
+    if (stages > AGG_MAX_STAGES) stages = AGG_MAX_STAGES;
+    int grid = sm_count();
+    if (grid > p.B) grid = p.B;
+    const size_t smem = (size_t)stages * stage_bytes;
+    cudaFuncSetAttribute(nbr_reduce_staged_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    nbr_reduce_staged_kernel<MODE><<<grid, AGG_THREADS, smem, st>>>(p, stages, (uint32_t)stage_bytes);
+    return check_launch("nbr_reduce_staged");
+  }
+  for (int b0 = 0; b0 < p.B; b0 += 65535) {
+    const int nb = p.B - b0 < 65535 ? p.B - b0 : 65535;
+    const int items = p.N * (p.C / 4);
+    dim3 grid((items + 255) / 256 > 64 ? 64 : (items + 255) / 256, nb);
+    nbr_reduce_direct_kernel<MODE><<<grid, 256, 0, st>>>(p, b0);
+    if (int rc = check_launch("nbr_reduce_direct")) return rc;
+  }
+  return 0;
+}
+
 }  // namespace grafp
 
 using namespace grafp;
@@ -244,6 +390,27 @@ int grafp_mr_aggregate_bwd(const float* dm, const int32_t* idx, const uint8_t* a
   mr_aggregate_bwd_kernel<<<B, 256, use_smem ? bytes : 0, as_stream(stream)>>>(dm, idx, arg, N, C,
                                                                                k, use_smem, dx);
   return check_launch("mr_aggregate_bwd");
+}
+
+int grafp_nbr_reduce_fwd(const float* x, const int32_t* idx, int B, int N, int C, int k, int mode,
+                         const float* scale, const float* shift, int act, float act_param,
+                         const float* eps, float* out, int64_t ldo, void* stream) {
+  GRAFP_REQUIRE(B <= 0 || (x && idx && out), "nbr_reduce: null pointer");
+  GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0 && k <= 255, "nbr_reduce: bad sizes");
+  GRAFP_REQUIRE(C % 4 == 0 && ldo % 4 == 0 && ldo >= C, "nbr_reduce: C=%d and ldo=%lld must be multiples of 4, ldo >= C",
+                C, (long long)ldo);
+  GRAFP_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                "nbr_reduce: x / out must be 16-byte aligned");
+  GRAFP_REQUIRE(act >= GRAFP_ACT_NONE && act <= GRAFP_ACT_ELU, "nbr_reduce: unknown activation %d", act);
+  if (B == 0) return 0;
+  NbrParams p{x, idx, B, N, C, k, scale, shift, act, act_param, eps, out, ldo};
+  cudaStream_t st = as_stream(stream);
+  switch (mode) {
+    case GRAFP_NBR_MAX:      return nbr_reduce_launch<GRAFP_NBR_MAX>(p, st);
+    case GRAFP_NBR_SUM_SELF: return nbr_reduce_launch<GRAFP_NBR_SUM_SELF>(p, st);
+    case GRAFP_NBR_EDGE_MAX: return nbr_reduce_launch<GRAFP_NBR_EDGE_MAX>(p, st);
+    default: return fail("nbr_reduce: unknown mode %d", mode);
+  }
 }
 
 int grafp_index_select(const float* x, const int32_t* idx, int B, int N, int C, int k,

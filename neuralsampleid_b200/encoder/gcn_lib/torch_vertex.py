@@ -37,16 +37,118 @@ class MRConv2d(nn.Module):
         return ops.nodes_to_nchw(out, B, N).unsqueeze(-1)
 
 
+def _concat_halves(conv_seq, tag_cache, act_mod):
+    """Prepared operands of a BasicConv layer whose input is a PLAIN channel concat [a | b] (EdgeConv2d,
+    GraphSAGE.nn2): with groups=4 the first two groups read only `a`, the last two only `b`, so the layer
+    is two independent 2-group GEMMs writing the two column halves of the output.
+    Returns ((lin_a, lin_b), act_name, slope)."""
+    e = conv_seq._plan[0]
+    conv = conv_seq[e["conv"]]
+    bn = conv_seq[e["bn"]] if e["bn"] is not None else None
+    key = sig(conv.weight, conv.bias) + (sig(bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else ())
+    hit = tag_cache.get("halves")
+    if hit is None or hit[0] != key:
+        w, scale, shift = fold_conv_bn(conv.weight, conv.bias, bn)
+        h = w.shape[0] // 2
+        sl = lambda t, a, b: t[a:b].contiguous() if t is not None else None
+        hit = (key, (make_linear(w[:h].contiguous(), sl(scale, 0, h), sl(shift, 0, h), 2),
+                     make_linear(w[h:].contiguous(), sl(scale, h, 2 * h), sl(shift, h, 2 * h), 2)))
+        tag_cache["halves"] = hit
+    act = conv_seq[e["act"]] if e["act"] is not None else None
+    return hit[1], (act.name if act is not None else None), (act.neg_slope if act is not None else 0.0)
+
+
+class _NodeGraphConv(nn.Module):
+    """Shared NCHW wrapper of the node-major graph convolutions below."""
+
+    def forward(self, x, edge_index, y=None):
+        if y is not None:
+            raise NotImplementedError("r > 1 (pooled y) graphs are not reached by GraphEncoder (r=1)")
+        if self.training:
+            raise RuntimeError("%s has an eval-mode sm_100a path only (the train path covers conv='mr')"
+                               % type(self).__name__)
+        B, C, N = x.shape[:3]
+        nodes = ops.nchw_to_nodes(x.reshape(B, C, N))
+        out = self.forward_nodes(nodes, edge_index[0].to(torch.int32), B, N)
+        return ops.nodes_to_nchw(out, B, N).unsqueeze(-1)
+
+
+class EdgeConv2d(_NodeGraphConv):
+    """Edge convolution max_k nn(cat[x_i, x_j - x_i]) (reference torch_vertex.py:37-52), evaluated per node:
+    the grouped 1x1 conv commutes with the gather, so groups 0-1 (which only see x_i) are one GEMM on the
+    nodes and groups 2-3 are max_k act(scale * (P_j - P_i) + shift) over P = W x -- k times less GEMM work
+    than the reference's (B, 2C, N, k) edge tensor, exact for any activation (it is applied per edge)."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.nn = BasicConv([in_channels * 2, out_channels], act, norm, bias)
+        self._cache = {}
+
+    def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int, out_split: bool = False):
+        (lin_a, lin_b), act, slope = _concat_halves(self.nn, self._cache, None)
+        h = lin_a.w.shape[0]
+        out = torch.empty((x.shape[0], 2 * h), device=x.device, dtype=torch.float32)
+        ops.linear(x, lin_a, act, slope, out=out[:, :h])                       # groups 0-1: functions of x_i only
+        raw = Linear_raw(lin_b)
+        p = ops.linear(x, raw)                                                 # P = W x (no bias / BN / act)
+        ops.nbr_reduce(p, nn_idx, B, N, ops.NBR_EDGE_MAX, lin_b.scale, lin_b.shift, act, slope, out=out[:, h:])
+        return out
+
+
+class GraphSAGE(_NodeGraphConv):
+    """nn2(cat[x, max_k nn1(x_j)]) (reference torch_vertex.py:55-68): nn1 is applied once per node, then
+    gathered and max-reduced."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.nn1 = BasicConv([in_channels, in_channels], act, norm, bias)
+        self.nn2 = BasicConv([in_channels * 2, out_channels], act, norm, bias)
+        self._cache = {}
+
+    def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int, out_split: bool = False):
+        q = self.nn1.forward_nodes(x)
+        xj = ops.nbr_reduce(q, nn_idx, B, N, ops.NBR_MAX)
+        (lin_a, lin_b), act, slope = _concat_halves(self.nn2, self._cache, None)
+        h = lin_a.w.shape[0]
+        out = torch.empty((x.shape[0], 2 * h), device=x.device, dtype=torch.float32)
+        ops.linear(x, lin_a, act, slope, out=out[:, :h])
+        ops.linear(xj, lin_b, act, slope, out=out[:, h:])
+        return out
+
+
+class GINConv2d(_NodeGraphConv):
+    """nn((1 + eps) x + sum_k x_j) (reference torch_vertex.py:71-88)."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.nn = BasicConv([in_channels, out_channels], act, norm, bias)
+        self.eps = nn.Parameter(torch.Tensor([0.0]))
+
+    def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int, out_split: bool = False):
+        h = ops.nbr_reduce(x, nn_idx, B, N, ops.NBR_SUM_SELF, eps=self.eps.detach())
+        return self.nn.forward_nodes(h)
+
+
+def Linear_raw(lin):
+    """The same prepared weights without the epilogue (scale / shift dropped)."""
+    from ..._prep import Linear
+    return Linear(lin.w, None, None, lin.groups, lin.w_split, lin.w_split_bf16)
+
+
 class GraphConv2d(nn.Module):
-    """Static graph convolution dispatch.  GraphEncoder hard-codes conv='mr' (SURVEY Q2); the other
-    reference variants (edge / sage / gin) are outside the accelerated path."""
+    """Static graph convolution dispatch (reference torch_vertex.py:92-111).  GraphEncoder hard-codes
+    conv='mr' (SURVEY Q2); edge / sage / gin are the reference's other variants, eval-mode only here."""
 
     def __init__(self, in_channels, out_channels, conv="edge", act="relu", norm=None, bias=True):
         super().__init__()
-        if conv == "mr":
+        if conv == "edge":
+            self.gconv = EdgeConv2d(in_channels, out_channels, act, norm, bias)
+        elif conv == "mr":
             self.gconv = MRConv2d(in_channels, out_channels, act, norm, bias)
-        elif conv in ("edge", "sage", "gin"):
-            raise NotImplementedError("conv:{} has no sm_100a kernel (GraphEncoder uses 'mr')".format(conv))
+        elif conv == "sage":
+            self.gconv = GraphSAGE(in_channels, out_channels, act, norm, bias)
+        elif conv == "gin":
+            self.gconv = GINConv2d(in_channels, out_channels, act, norm, bias)
         else:
             raise NotImplementedError("conv:{} is not supported".format(conv))
 

@@ -107,6 +107,28 @@ def mr_aggregate(x: torch.Tensor, idx: torch.Tensor, B: int, N: int, want_arg: b
     return (m, arg) if want_arg else m
 
 
+NBR_MAX, NBR_SUM_SELF, NBR_EDGE_MAX = 1, 2, 3
+
+
+def nbr_reduce(x: torch.Tensor, idx: torch.Tensor, B: int, N: int, mode: int, scale=None, shift=None, act=None,
+               act_param: float = 0.0, eps: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """Per-node neighbour reductions of the other GraphConv2d variants (include/grafp.h):
+    NBR_MAX max_k x_j; NBR_SUM_SELF (1+eps) x_i + sum_k x_j; NBR_EDGE_MAX max_k act(scale (x_j - x_i) + shift).
+    ``out`` may be a column slice of a wider row-major matrix (row stride = out.stride(0))."""
+    x = _chk(x, name="x")
+    idx = _chk(idx, torch.int32, "idx")
+    Cc, k = x.shape[1], idx.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.stride(1) != 1 or not out.is_cuda or out.dtype != torch.float32:
+        raise GrafpError("nbr_reduce: out must be an fp32 CUDA (M, C) view with unit column stride")
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_nbr_reduce_fwd(_ptr(x), _ptr(idx), B, N, Cc, k, mode, _ptr(scale), _ptr(shift),
+                                               act_code(act), act_param, _ptr(eps), _ptr(out), out.stride(0),
+                                               _stream(x)), "nbr_reduce_fwd")
+    return out
+
+
 def mr_aggregate_bwd(dm: torch.Tensor, idx: torch.Tensor, arg: torch.Tensor, B: int, N: int,
                      dx: torch.Tensor) -> torch.Tensor:
     """Accumulates the aggregation gradient into dx (in place)."""
@@ -244,6 +266,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
         out = torch.empty((2, M, n_total), device=dev, dtype=torch.bfloat16)
     elif out is None:
         out = torch.empty((M, n_total), device=dev, dtype=torch.float32)
+    elif out.shape != (M, n_total) or out.stride(1) != 1:
+        raise GrafpError("gemm: out must be an (M, groups*n) view with unit column stride")
     args = GemmArgs()
     if a1s is not None:
         args.a1, args.lda1, args.k1 = None, 0, k1

@@ -185,6 +185,33 @@ def edge_conv(p: Params, prefix: str, x: Tensor, edge_index: Tensor, act: str,
     return mx
 
 
+def _basic_conv_any(p: Params, prefix: str, x: Tensor, act: str, training: bool,
+                    stats: Optional[dict]) -> Tensor:
+    """BasicConv with the norm layer optional (keys decide): Conv2d 1x1 groups=4 [-> BN] -> act,
+    encoder/gcn_lib/torch_nn.py:52-64."""
+    y = F.conv2d(x, p[prefix + ".0.weight"], p.get(prefix + ".0.bias"), groups=4)
+    if prefix + ".1.weight" in p:
+        y = _bn(p, prefix + ".1", y, training, stats)
+    return _act(act, y)
+
+
+def sage_conv(p: Params, prefix: str, x: Tensor, edge_index: Tensor, act: str,
+              training: bool, stats: Optional[dict]) -> Tensor:
+    """GraphSAGE.forward, encoder/gcn_lib/torch_vertex.py:60-68:
+    nn2(cat[x, max_k nn1(x_j)])."""
+    x_j = gather_nodes(x, edge_index[0])
+    x_j, _ = torch.max(_basic_conv_any(p, prefix + ".nn1", x_j, act, training, stats), -1, keepdim=True)
+    return _basic_conv_any(p, prefix + ".nn2", torch.cat([x, x_j], dim=1), act, training, stats)
+
+
+def gin_conv(p: Params, prefix: str, x: Tensor, edge_index: Tensor, act: str,
+             training: bool, stats: Optional[dict]) -> Tensor:
+    """GINConv2d.forward, encoder/gcn_lib/torch_vertex.py:81-88:
+    nn((1 + eps) * x + sum_k x_j)."""
+    x_j = torch.sum(gather_nodes(x, edge_index[0]), -1, keepdim=True)
+    return _basic_conv_any(p, prefix + ".nn", (1 + p[prefix + ".eps"]) * x + x_j, act, training, stats)
+
+
 def dy_graph_conv(p: Params, prefix: str, x: Tensor, k: int, dilation: int, conv: str,
                   act: str, training: bool, stats: Optional[dict],
                   taps: Optional[dict] = None) -> Tensor:
@@ -200,6 +227,10 @@ def dy_graph_conv(p: Params, prefix: str, x: Tensor, k: int, dilation: int, conv
         y = mr_conv(p, prefix + ".gconv", x, edge_index, act, training, stats, taps)
     elif conv == "edge":
         y = edge_conv(p, prefix + ".gconv", x, edge_index, act, training, stats)
+    elif conv == "sage":
+        y = sage_conv(p, prefix + ".gconv", x, edge_index, act, training, stats)
+    elif conv == "gin":
+        y = gin_conv(p, prefix + ".gconv", x, edge_index, act, training, stats)
     else:
         raise NotImplementedError("conv:{} is not supported".format(conv))
     return y.reshape(B, -1, H, W).contiguous()

@@ -79,6 +79,24 @@ def simclr_state_spec(cfg: dict, size: str = "t") -> Spec:
     return enc + pk + pr
 
 
+def graphconv_state_spec(conv: str, cin: int, cout: int, signed_bn: bool = True) -> Spec:
+    """state_dict of DyGraphConv2d(cin, cout, ..., conv, act, 'batch', True) for the reference's four
+    GraphConv2d variants (encoder/gcn_lib/torch_vertex.py:11-111); BasicConv = Conv2d(groups=4)+BN."""
+    def bn(prefix, c):
+        spec = _bn(prefix, c)
+        return [(n, sh, "bn_ws" if (signed_bn and r == "bn_w") else r) for n, sh, r in spec]
+
+    def basic(prefix, ci, co):
+        return [(prefix + ".0.weight", (co, ci // 4, 1, 1), "w"), (prefix + ".0.bias", (co,), "b")] + bn(prefix + ".1", co)
+    if conv in ("mr", "edge"):
+        return basic("gconv.nn", 2 * cin, cout)
+    if conv == "sage":
+        return basic("gconv.nn1", cin, cin) + basic("gconv.nn2", 2 * cin, cout)
+    if conv == "gin":
+        return [("gconv.eps", (1,), "eps")] + basic("gconv.nn", cin, cout)
+    raise ValueError(conv)
+
+
 def _uniform(rng: np.random.Generator, shape, lo: float, hi: float) -> np.ndarray:
     """Exact-arithmetic uniform floats: 24-bit integers / 2^24 in float64, affine, -> fp32."""
     n = int(np.prod(shape)) if len(shape) else 1
@@ -106,6 +124,10 @@ def synth_state(spec: Spec, seed: int = 1234) -> Dict[str, torch.Tensor]:
             a = _uniform(rng, shape, -0.3, 0.3)
         elif role == "bn_rv":
             a = _uniform(rng, shape, 0.5, 1.5)
+        elif role == "bn_ws":                             # signed BatchNorm scale (max over edges then is
+            a = _uniform(rng, shape, -1.2, 1.2)           # not a monotone function of the pre-activation)
+        elif role == "eps":
+            a = _uniform(rng, shape, 0.1, 0.4)
         elif role == "count":
             out[name] = torch.zeros((), dtype=torch.int64)
             continue

@@ -82,6 +82,19 @@ def capture_dygraph(ref, k, d, N, B, seed):
     return {"x": x.numpy(), "idx": edge[0].numpy().astype(np.int16), "y": y.numpy()}
 
 
+def capture_graphconv(ref, conv, act, k, d, cin, cout, N, B, seed):
+    """The reference's other GraphConv2d variants (edge / sage / gin) through DyGraphConv2d."""
+    m = ref.DyGraphConv2d(cin, cout, k, d, conv, act, "batch", True).eval()
+    sd = synth.synth_state(synth.graphconv_state_spec(conv, cin, cout), WEIGHT_SEED + 3)
+    assert sorted(sd.keys()) == sorted(m.state_dict().keys()), (conv, sorted(m.state_dict().keys()))
+    m.load_state_dict(sd)
+    x = synth.synth_normal((B, cin, N, 1), seed)
+    with torch.no_grad():
+        edge = m.dilated_knn_graph(x)
+        y = m(x)
+    return {"x": x.numpy(), "idx": edge[0].numpy().astype(np.int16), "y": y.numpy()}
+
+
 def capture_ntxent(ref, B, seed):
     z_i = torch.nn.functional.normalize(synth.synth_normal((B, 128), seed), dim=1)
     z_j = torch.nn.functional.normalize(z_i + 0.3 * synth.synth_normal((B, 128), seed + 1), dim=1)
@@ -151,6 +164,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "encoder_t_k5.npz"), **g5)
     np.savez_compressed(os.path.join(HERE, "dygraph_k9_d2.npz"), **capture_dygraph(ref, 9, 2, 256, 2, 31))
     np.savez_compressed(os.path.join(HERE, "dygraph_k4_d3_n96.npz"), **capture_dygraph(ref, 4, 3, 96, 3, 32))
+    for conv, act in (("edge", "gelu"), ("edge", "relu"), ("sage", "relu"), ("gin", "leakyrelu")):
+        np.savez_compressed(os.path.join(HERE, "graphconv_%s_%s.npz" % (conv, act)),
+                            **capture_graphconv(ref, conv, act, 4, 2, 64, 128, 64, 3, 51))
     np.savez_compressed(os.path.join(HERE, "ntxent_b16.npz"), **capture_ntxent(ref, 16, 41))
     np.savez_compressed(os.path.join(HERE, "simclr_eval_b4.npz"), **capture_simclr(ref, 3, 4, False))
     np.savez_compressed(os.path.join(HERE, "simclr_train_b8.npz"), **capture_simclr(ref, 5, 8, True))

@@ -198,6 +198,37 @@ def test_dygraph_dilated_matches_golden(golden_dir):
         assert torch.allclose(a, b, rtol=2e-4, atol=2e-4)      # bf16x3 engine: ~1e-5 of the output scale
 
 
+@pytest.mark.parametrize("conv,act", [("edge", "gelu"), ("edge", "relu"), ("sage", "relu"), ("gin", "leakyrelu")])
+def test_other_graph_convs_match_golden_and_oracle(golden_dir, conv, act):
+    """EdgeConv2d / GraphSAGE / GINConv2d (reference torch_vertex.py:37-111) through DyGraphConv2d: the
+    node-level evaluation (conv commuted with the gather) against vectors minted from the reference and
+    against the oracle on a second, larger input; BatchNorm scales of both signs, non-monotone GELU."""
+    from neuralsampleid_b200.encoder.gcn_lib.torch_vertex import DyGraphConv2d
+    g = np.load(os.path.join(golden_dir, "graphconv_%s_%s.npz" % (conv, act)))
+    k, d, cin, cout = 4, 2, 64, 128
+    m = DyGraphConv2d(cin, cout, k, d, conv, act, "batch", True)
+    sd = synth.synth_state(synth.graphconv_state_spec(conv, cin, cout), 1237)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    for x, want, want_idx in ((torch.from_numpy(g["x"]), torch.from_numpy(g["y"]), torch.from_numpy(g["idx"].astype(np.int64))),
+                              (synth.synth_normal((5, cin, 128, 1), 77), None, None)):
+        if want is None:
+            want = O.dy_graph_conv({"gc." + n: t for n, t in sd.items()}, "gc", x, k, d, conv, act, False, None)
+            want_idx = O.dilated_knn_graph(x, k, d)[0][0]
+        with torch.no_grad():
+            y = m(x.to(DEV)).cpu()
+            edge = m.dilated_knn_graph(x.to(DEV)).cpu()
+        _, dist = O.dilated_knn_graph(x, k, d)
+        tie = O.knn_tie_rows(dist, k * d, TIE_TOL)
+        diff = (edge[0] != want_idx).any(-1)
+        assert not (diff & ~tie).any()
+        ok = ~diff
+        a = y.squeeze(-1).transpose(1, 2)[ok]
+        b = want.squeeze(-1).transpose(1, 2)[ok]
+        assert a.shape == b.shape and int(ok.sum()) > 0.95 * ok.numel()
+        assert torch.allclose(a, b, rtol=3e-4, atol=3e-4), float((a - b).abs().max())
+
+
 def test_grapher_module_api_matches_oracle():
     from neuralsampleid_b200.encoder.gcn_lib.torch_vertex import Grapher
     from neuralsampleid_b200.encoder.gcn_lib.torch_nn import batched_index_select

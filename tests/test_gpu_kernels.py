@@ -176,6 +176,33 @@ def test_mr_aggregate_bit_exact(B, C, N, k):
     assert torch.equal(vals.reshape(B * N, C), m.cpu())
 
 
+@pytest.mark.parametrize("B,C,N,k", [(5, 64, 256, 3), (3, 128, 64, 9), (2, 32, 40, 4), (2, 64, 2048, 5)])
+def test_nbr_reduce_modes(B, C, N, k):
+    """grafp_nbr_reduce_fwd: plain max, (1+eps) x + sum, and max_k act(scale (x_j - x_i) + shift), staged and
+    direct forms, contiguous and strided outputs."""
+    ops = _ops()
+    x = synth.synth_normal((B, C, N, 1), 61)
+    rng = np.random.Generator(np.random.PCG64(7))
+    idx = torch.from_numpy(rng.integers(0, N, size=(B, N, k), dtype=np.int64))
+    xj = O.gather_nodes(x, idx)                                        # (B, C, N, k)
+    nodes = _nodes(x).to(DEV)
+    i32 = idx.int().to(DEV)
+    got = ops.nbr_reduce(nodes, i32, B, N, ops.NBR_MAX).cpu()
+    assert torch.equal(got, _nodes(xj.max(-1, keepdim=True)[0]))
+    eps = torch.tensor([0.25], device=DEV)
+    got = ops.nbr_reduce(nodes, i32, B, N, ops.NBR_SUM_SELF, eps=eps).cpu()
+    want = _nodes(1.25 * x + xj.sum(-1, keepdim=True))
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    scale = synth.synth_uniform((C,), 62, -1.2, 1.2)
+    shift = synth.synth_uniform((C,), 63, -0.5, 0.5)
+    for act, fn in (("relu", torch.relu), ("gelu", torch.nn.functional.gelu), (None, lambda t: t)):
+        wide = torch.full((B * N, 2 * C), -7.0, device=DEV)
+        ops.nbr_reduce(nodes, i32, B, N, ops.NBR_EDGE_MAX, scale.to(DEV), shift.to(DEV), act, 0.0, out=wide[:, C:])
+        e = fn((xj - x) * scale.view(1, C, 1, 1) + shift.view(1, C, 1, 1)).max(-1, keepdim=True)[0]
+        assert torch.allclose(wide[:, C:].cpu(), _nodes(e), rtol=1e-5, atol=1e-5)
+        assert bool((wide[:, :C] == -7.0).all())                      # the other column half is untouched
+
+
 def test_index_select_matches_oracle():
     ops = _ops()
     x = synth.synth_normal((3, 16, 40, 1), 12)

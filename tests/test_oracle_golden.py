@@ -196,3 +196,27 @@ def test_oracle_vs_live_reference_edgeconv_and_select():
     assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
     idx = torch.randint(0, 40, (2, 40, 5))
     assert torch.equal(ref.batched_index_select(x, idx), O.gather_nodes(x, idx))
+
+
+@needs_ref
+@pytest.mark.reference
+@pytest.mark.parametrize("conv,act", [("sage", "relu"), ("gin", "leakyrelu"), ("edge", "relu")])
+def test_oracle_vs_live_reference_other_graph_convs(conv, act):
+    ref = import_reference()
+    torch.manual_seed(3)
+    m = ref.DyGraphConv2d(32, 64, 4, 2, conv, act, "batch", True).eval()
+    with torch.no_grad():                               # non-trivial BN statistics / GIN eps
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.uniform_(-0.3, 0.3)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(-1.2, 1.2)          # negative scales too (EdgeConv max is not monotone then)
+                mod.bias.uniform_(-0.2, 0.2)
+        if conv == "gin":
+            m.gconv.eps.fill_(0.25)
+    sd = {"gc." + n: t for n, t in m.state_dict().items()}
+    x = torch.randn(2, 32, 48, 1)
+    with torch.no_grad():
+        a = m(x)
+        b = O.dy_graph_conv(sd, "gc", x, 4, 2, conv, act, False, None)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
