@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 2
+#define GRAFP_ABI_VERSION 3
 
 /* activation codes (reference: act_layer, encoder/gcn_lib/torch_nn.py:9-25; ELU for the
  * projector, simclr/simclr.py:26) */
@@ -155,6 +155,14 @@ typedef struct {
    *             plane stride m*lda1s) instead of a1 (a1 may then be NULL); needs k2 == 0, no tap3 */
   void* y_split; int64_t ldys;
   const void* a1_split; int64_t lda1s;
+  /* ---- fused max-relative aggregation (ABI 3; bf16 tensor-core engines, fp32 a1) ---------------
+   * MRConv2d (encoder/gcn_lib/torch_vertex.py:19-34) in ONE kernel: when a2_gather_idx is non-NULL the
+   * second A source is not read from memory (a2 must be NULL, k2 = k1) but computed on the fly,
+   *   a2[m, c] = max_t ( a1[graph(m) + a2_gather_idx[m, t], c] - a1[m, c] ),
+   * graph(m) = (m / a2_gather_nodes) * a2_gather_nodes, idx (M, a2_gather_k) int32 graph-local (what
+   * grafp_knn_fwd emits).  Same arithmetic as grafp_mr_aggregate_fwd, bit-identical results; the
+   * (M, C) max-relative tensor never reaches HBM. */
+  const int32_t* a2_gather_idx; int32_t a2_gather_nodes; int32_t a2_gather_k;
 } grafp_gemm_args;
 int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream);
 /* 1 if the tcgen05 engine takes this problem (k1, k2 multiples of 32, n multiple of 16, no tap3) */

@@ -34,7 +34,8 @@ class GemmArgs(C.Structure):
                 ("act", C.c_int32), ("act_param", C.c_float),
                 ("tap3_nodes", C.c_int32), ("engine", C.c_int32),
                 ("y_split", C.c_void_p), ("ldys", C.c_int64),
-                ("a1_split", C.c_void_p), ("lda1s", C.c_int64)]
+                ("a1_split", C.c_void_p), ("lda1s", C.c_int64),
+                ("a2_gather_idx", C.c_void_p), ("a2_gather_nodes", C.c_int32), ("a2_gather_k", C.c_int32)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float

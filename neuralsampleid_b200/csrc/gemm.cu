@@ -14,7 +14,7 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
   const grafp_gemm_args& a = *args;
   GRAFP_REQUIRE(a.m >= 0 && a.n > 0 && a.groups > 0 && a.k1 > 0 && a.k2 >= 0, "gemm: bad sizes");
   GRAFP_REQUIRE(a.m == 0 || ((a.a1 || a.a1_split) && a.w && (a.y || a.y_split)), "gemm: null pointer");
-  GRAFP_REQUIRE(a.m == 0 || (a.k2 == 0) == (a.a2 == nullptr), "gemm: a2/k2 mismatch");
+  GRAFP_REQUIRE(a.m == 0 || (a.k2 == 0) == (a.a2 == nullptr && a.a2_gather_idx == nullptr), "gemm: a2/k2 mismatch");
   GRAFP_REQUIRE(a.k1 % 4 == 0 && a.k2 % 4 == 0, "gemm: k1=%d, k2=%d must be multiples of 4", a.k1,
                 a.k2);
   GRAFP_REQUIRE(a.k2 == 0 || a.k1 % 16 == 0, "gemm: dual-source needs k1 %% 16 == 0 (k1=%d)", a.k1);
@@ -28,6 +28,17 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
   GRAFP_REQUIRE(a.act >= GRAFP_ACT_NONE && a.act <= GRAFP_ACT_ELU, "gemm: unknown activation %d", a.act);
   if (a.m == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (a.a2_gather_idx) {
+    GRAFP_REQUIRE(!a.a2 && !a.a1_split && a.a1 && a.k2 == a.k1 && a.tap3_nodes == 0,
+                  "gemm: a2_gather needs fp32 a1, a2 == NULL, k2 == k1, no tap3");
+    GRAFP_REQUIRE(a.a2_gather_nodes > 0 && a.a2_gather_k > 0 && a.m % a.a2_gather_nodes == 0,
+                  "gemm: a2_gather needs m to be a multiple of a2_gather_nodes");
+    GRAFP_REQUIRE(a.engine == GRAFP_ENGINE_AUTO || a.engine == GRAFP_ENGINE_TC_BF16X3 ||
+                      a.engine == GRAFP_ENGINE_TC_BF16,
+                  "gemm: a2_gather needs a bf16 tensor-core engine (engine=%d)", a.engine);
+    GRAFP_REQUIRE(a.w_split_bf16 && gemm_tc_supported(a), "gemm: a2_gather needs w_split_bf16 and a tcgen05-supported shape");
+    return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_BF16 ? 1 : 3, 1, st);
+  }
   if (a.a1_split || a.y_split) {
     // split-bf16 activations exist only on the bf16 tensor-core engines: fail loudly, never convert
     GRAFP_REQUIRE(a.engine == GRAFP_ENGINE_AUTO || a.engine == GRAFP_ENGINE_TC_BF16X3 ||

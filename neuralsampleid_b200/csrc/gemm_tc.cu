@@ -55,6 +55,9 @@ struct TcParams {
   uint32_t tmem_cols;
   int y_split;         // output as bf16 [hi ; lo] planes (tmY is then the 3-D bf16 map)
   int raw;             // depth of the fp32 A ring (bf16 engines with an fp32 A operand)
+  // fused max-relative aggregation: the second A source is not read but computed by the transform warps,
+  // a2[m, c] = max_t (a1[graph(m) + idx[m, t], c] - a1[m, c])  (bf16 engines, fp32 A)
+  const int32_t* gat_idx; const float* gat_x; int64_t gat_ld; int gat_n, gat_k;
 };
 
 // v = act(v * scale + shift) + residual over one 32-column chunk of a row; scale/shift come from
@@ -91,7 +94,9 @@ __device__ __forceinline__ void epi_apply(float (&v)[32], const float* scale, co
 // kASplit (bf16 engines): the A operand arrives already split, as the bf16 (2, M, K) [hi ; lo] planes a
 // previous GEMM's epilogue wrote (p.y_split): the W producer warp TMA-loads the hi / lo tiles straight
 // into the operand stage, there is no fp32 ring and no transform, the MMA waits on full[s] alone.
-template <int kPasses, int kCluster, bool kBf16, bool kASplit>
+// kGather: fused max-relative aggregation of the second A source (opt-in, see TcParams::gat_idx); a separate
+// instantiation so the default kernels carry none of its registers or code.
+template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -173,7 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // (gated by the MMA commits), so A prefetch depth is not tied to the MMA's progress.
     const bool do_a = warp == 0 && !kASplit, do_w = kBf16 ? warp == 14 : warp == 0;
     if (lane == 0 && (do_a || do_w)) {
-      uint32_t it = 0;
+      uint32_t it = 0, ra = 0;                  // ra: fp32 A tiles issued into the raw ring
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
         const int nt = (int)(tile % tiles_n);
         const int64_t rest = tile / tiles_n;
@@ -186,13 +191,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const int k = kb * TC_BK;
           uint64_t* abar;
           uint8_t* adst;
+          const bool gathered = kGather && k >= p.k1;   // built by the transform
           if (kBf16) {
-            const int r = it % RAW;
+            const int r = ra % RAW;
             abar = &raw_full_bar[r];
             adst = a_raw(r);
-            if (do_a) {
-              mbar_wait(&raw_empty_bar[r], ((it / RAW) & 1u) ^ 1u);
+            if (do_a && !gathered) {
+              mbar_wait(&raw_empty_bar[r], ((ra / RAW) & 1u) ^ 1u);
               mbar_arrive_expect_tx(abar, TC_A_BYTES);
+              ++ra;
             }
             if (do_w) {
               mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -208,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             mbar_wait(&empty_bar[s], ph ^ 1u);
             mbar_arrive_expect_tx(&full_bar[s], TC_A_BYTES + kNP * b_bytes);
           }
-          if (do_a) {
+          if (do_a && !gathered) {
             if (p.tap3_rows > 0) {
               // Downsample: W columns are [tap0 | tap1 | tap2]; taps 1,2 = the (M, 2*Cin) view of
               // the input, tap 0 = the same view shifted one output row up inside each graph
@@ -307,22 +314,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if ((kPasses == 3 || kBf16) && !kASplit) {
       constexpr int PER = TC_A_BYTES / 16 / TC_XF_THREADS;
       const int t = threadIdx.x - 320;
-      uint32_t it = 0;
+      uint32_t it = 0, ra = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
+        const int64_t rest = tile / tiles_n;
+        const int g = (int)(rest % p.groups);
+        const int64_t m0 = ((rest / p.groups) * kCluster + crank) * TC_BM;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
-          const int rs = kBf16 ? (int)(it % RAW) : s;
-          mbar_wait(kBf16 ? &raw_full_bar[rs] : &full_bar[s], kBf16 ? (it / RAW) & 1u : ph);
-          const float4* raw = reinterpret_cast<const float4*>(a_raw(rs));
+          const int k = kb * TC_BK;
+          const bool gathered = kGather && k >= p.k1;
           float4 v[PER];
+          int rs = s;
+          if (gathered) {
+            // Fused gather + max-relative (reference torch_vertex.py:21-29): this k-block of the second A
+            // source is max_t (y[j_t] - y[i]) over the row's neighbour list, read straight from y (the rows of
+            // one graph are a contiguous, L2-resident 64 KB block that this kernel streams anyway).  Identical
+            // arithmetic to mr_aggregate_staged_kernel, so the result is bit-identical to the unfused route.
+            // v[i] holds LOGICAL chunk q & 7 of row q >> 3 (the store below un-swizzles with r & 7).
+            const int kc = g * p.k2 + (k - p.k1);
 #pragma unroll
-          for (int i = 0; i < PER; ++i) v[i] = raw[t + TC_XF_THREADS * i];
+            for (int i = 0; i < PER; ++i) {
+              const int q = t + TC_XF_THREADS * i;
+              const int r = q >> 3;
+              const int lc = (q & 7) ^ (r & 7);                        // logical chunk this slot must hold
+              const int64_t row = m0 + r;
+              float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < p.m) {
+                const int64_t gb = (row / p.gat_n) * p.gat_n;
+                const float* col = p.gat_x + kc + lc * 4;
+                const float4 xi = __ldg(reinterpret_cast<const float4*>(col + row * p.gat_ld));
+                const int32_t* nb = p.gat_idx + row * p.gat_k;
+                best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                for (int tt = 0; tt < p.gat_k; ++tt) {
+                  const int j = __ldg(nb + tt);
+                  const float4 xj = __ldg(reinterpret_cast<const float4*>(col + (gb + j) * p.gat_ld));
+                  const float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z, dw = xj.w - xi.w;
+                  if (dx > best.x) best.x = dx;
+                  if (dy > best.y) best.y = dy;
+                  if (dz > best.z) best.z = dz;
+                  if (dw > best.w) best.w = dw;
+                }
+              }
+              v[i] = best;
+            }
+          } else {
+            rs = kBf16 ? (int)(ra % RAW) : s;
+            mbar_wait(kBf16 ? &raw_full_bar[rs] : &full_bar[s], kBf16 ? (ra / RAW) & 1u : ph);
+            const float4* raw = reinterpret_cast<const float4*>(a_raw(rs));
+#pragma unroll
+            for (int i = 0; i < PER; ++i) v[i] = raw[t + TC_XF_THREADS * i];
+          }
           if (kBf16) {
             // raw tile is in registers: its slot may be refilled.  The refill is an async-proxy (TMA) write
             // after generic-proxy reads: without the proxy fence the write can overtake the reads.
-            fence_proxy_async_smem();
-            mbar_arrive(&raw_empty_bar[rs]);
+            if (!gathered) {
+              fence_proxy_async_smem();
+              mbar_arrive(&raw_empty_bar[rs]);
+              ++ra;
+            }
             mbar_wait(&empty_bar[s], ph ^ 1u);          // operand stage s free (MMAs of k-block it - S retired)
             uint8_t* hi = a_hi(s);
             uint8_t* lo = a_lo(s);
@@ -610,7 +660,7 @@ int gemm_tc_supported(const grafp_gemm_args& a) {
     } else if ((a.lda1 * 4) % 16 != 0) {
       return 0;
     }
-    if (a.k2 && (a.lda2 * 4) % 16 != 0) return 0;
+    if (a.k2 && !a.a2_gather_idx && (a.lda2 * 4) % 16 != 0) return 0;
   }
   if (a.a1_split && a.tap3_nodes > 0) return 0;
   if ((a.ldw * 4) % 16 != 0 || a.ldw % 8 != 0) return 0;
@@ -649,7 +699,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
     } else if (int rc = tc_make_map_2d(&mA1, a.a1, a.m, (int64_t)a.groups * a.k1, a.lda1, TC_BM)) {
       return rc;
     }
-    if (a.k2 > 0) {
+    if (a.k2 > 0 && !a.a2_gather_idx) {
       if (int rc = tc_make_map_2d(&mA2, a.a2, a.m, (int64_t)a.groups * a.k2, a.lda2, TC_BM)) return rc;
     } else {
       mA2 = mA1;
@@ -674,6 +724,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
     return rc;
   }
   p.y_split = a.y_split ? 1 : 0;
+  p.gat_idx = a.a2_gather_idx; p.gat_x = a.a1; p.gat_ld = a.lda1; p.gat_n = a.a2_gather_nodes; p.gat_k = a.a2_gather_k;
   const bool asplit = a.a1_split != nullptr;
   p.k1 = a.k1; p.k2 = a.k2; p.n = a.n; p.bn = bn; p.n_total = n_total; p.groups = a.groups; p.m = a.m;
   p.scale = a.scale; p.shift = a.shift; p.residual = a.residual; p.ldr = a.ldr;
@@ -715,15 +766,18 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   grid *= cluster;
   using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   KernFn kern;
-  if (asplit)
-    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, true> : gemm_tc_kernel<3, 1, true, true>)
-                       : (cluster == 2 ? gemm_tc_kernel<1, 2, true, true> : gemm_tc_kernel<1, 1, true, true>);
+  if (a.a2_gather_idx)
+    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, false, true> : gemm_tc_kernel<3, 1, true, false, true>)
+                       : (cluster == 2 ? gemm_tc_kernel<1, 2, true, false, true> : gemm_tc_kernel<1, 1, true, false, true>);
+  else if (asplit)
+    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, true, false> : gemm_tc_kernel<3, 1, true, true, false>)
+                       : (cluster == 2 ? gemm_tc_kernel<1, 2, true, true, false> : gemm_tc_kernel<1, 1, true, true, false>);
   else if (bf16)
-    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, false> : gemm_tc_kernel<3, 1, true, false>)
-                       : (cluster == 2 ? gemm_tc_kernel<1, 2, true, false> : gemm_tc_kernel<1, 1, true, false>);
+    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, false, false> : gemm_tc_kernel<3, 1, true, false, false>)
+                       : (cluster == 2 ? gemm_tc_kernel<1, 2, true, false, false> : gemm_tc_kernel<1, 1, true, false, false>);
   else
-    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, false, false> : gemm_tc_kernel<3, 1, false, false>)
-                       : (cluster == 2 ? gemm_tc_kernel<1, 2, false, false> : gemm_tc_kernel<1, 1, false, false>);
+    kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, false, false, false> : gemm_tc_kernel<3, 1, false, false, false>)
+                       : (cluster == 2 ? gemm_tc_kernel<1, 2, false, false, false> : gemm_tc_kernel<1, 1, false, false, false>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

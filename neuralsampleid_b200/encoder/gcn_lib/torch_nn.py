@@ -102,9 +102,10 @@ class BasicConv(nn.Sequential):
         act = self[e["act"]] if e["act"] is not None else None
         return (hit[1],) + ((act.name, act.neg_slope) if act is not None else (None, 0.0))
 
-    def forward_nodes(self, x: torch.Tensor, x2: torch.Tensor = None, out_split: bool = False):
+    def forward_nodes(self, x: torch.Tensor, x2: torch.Tensor = None, out_split: bool = False, x2_gather=None):
         """x: (M, C) node-major.  If ``x2`` is given, the first layer consumes the virtual
-        interleave [x0, x2_0, x1, x2_1, ...] (MRConv2d) without materialising it.  ``out_split``:
+        interleave [x0, x2_0, x1, x2_1, ...] (MRConv2d) without materialising it; ``x2_gather`` = (idx, N)
+        instead has the kernel compute x2 = max-relative(x) on the fly (fused MRConv2d).  ``out_split``:
         the caller's consumer is a bf16 tensor-core GEMM, return an ops.SplitAct if this layer can
         produce one."""
         if self.training:
@@ -112,10 +113,12 @@ class BasicConv(nn.Sequential):
                                "neuralsampleid_b200.autograd")
         last = len(self._plan) - 1
         for i in range(len(self._plan)):
-            lin, act, slope = self.layer_params(i, interleaved_sources=(i == 0 and x2 is not None))
+            dual = i == 0 and (x2 is not None or x2_gather is not None)
+            lin, act, slope = self.layer_params(i, interleaved_sources=dual)
             k_total = lin.w.shape[1] * lin.groups
             split = out_split and i == last and not isinstance(x, ops.SplitAct) and ops.split_ok(lin, k_total)
-            x = ops.linear(x, lin, act, slope, a2=x2 if i == 0 else None, out_split=split)
+            x = ops.linear(x, lin, act, slope, a2=x2 if i == 0 else None, out_split=split,
+                           a2_gather=x2_gather if i == 0 else None)
         return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

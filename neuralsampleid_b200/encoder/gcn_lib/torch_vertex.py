@@ -25,6 +25,10 @@ class MRConv2d(nn.Module):
         self.nn = BasicConv([in_channels * 2, out_channels], act, norm, bias)
 
     def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int, out_split: bool = False):
+        lin = self.nn.layer_params(0, interleaved_sources=True)[0]
+        if ops.fused_mr_ok(lin, x.shape[1]):
+            # gather + max-relative computed inside the GEMM: the (M, C) aggregate never reaches HBM
+            return self.nn.forward_nodes(x, None, out_split, x2_gather=(nn_idx, N))
         m = ops.mr_aggregate(x, nn_idx, B, N)
         return self.nn.forward_nodes(x, m, out_split)
 

@@ -214,11 +214,23 @@ def split_ok(lin, k_total: int) -> bool:
     return k_total % (32 * lin.groups) == 0 and n % 32 == 0
 
 
+def fused_mr_ok(lin, c: int) -> bool:
+    """True when MRConv2d's gather + max-relative can run inside the GEMM over ``lin`` (the dual-source
+    BasicConv weights, C input channels per source): bf16 tensor-core engine, tcgen05-supported shape."""
+    # Opt-in (GRAFP_FUSED_MR=1): measured on B200 the in-kernel gather (four transform warps, dependent
+    # idx -> row loads from L2) makes the MRConv GEMMs 3-4x slower (5.6 vs 1.4 ms at stage 3), far more than the
+    # 1.3 ms/step of mr_aggregate it removes; a register-blocked variant that batches the loads spills.
+    if not os.environ.get("GRAFP_FUSED_MR"):
+        return False
+    return split_ok(lin, 2 * c) and (c // lin.groups) % 32 == 0 if lin.groups > 0 else False
+
+
 def linear(a1, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
-           tap3_nodes: int = 0, engine: Optional[int] = None, row_sumsq=None, out=None, out_split: bool = False):
+           tap3_nodes: int = 0, engine: Optional[int] = None, row_sumsq=None, out=None, out_split: bool = False,
+           a2_gather=None):
     """ops.gemm over a prepared ``_prep.Linear``."""
     return gemm(a1, lin.w, lin.scale, lin.shift, act, act_param, residual, a2, lin.groups, tap3_nodes,
-                engine, out, lin.w_split, lin.w_split_bf16, row_sumsq, out_split)
+                engine, out, lin.w_split, lin.w_split_bf16, row_sumsq, out_split, a2_gather)
 
 
 def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
@@ -227,8 +239,10 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
          groups: int = 1, tap3_nodes: int = 0, engine: Optional[int] = None,
          out: Optional[torch.Tensor] = None, w_split: Optional[torch.Tensor] = None,
          w_split_bf16: Optional[torch.Tensor] = None, row_sumsq: Optional[torch.Tensor] = None,
-         out_split: bool = False):
+         out_split: bool = False, a2_gather=None):
     """y = act(scale * [a1 | a2] @ w.T + shift) + residual  (per-group, see include/grafp.h).
+    ``a2_gather`` = (idx int32 (B, N, k), N): the second source is the max-relative aggregation of a1 over
+    those neighbour lists, computed inside the kernel (fused MRConv2d; bf16 tensor-core engines only).
 
     a1: (M, groups*k1) (or the (2M', Cin) node matrix in tap3 mode), a2: (M, groups*k2) or None,
     w: (groups*n, k1+k2).  ``a1`` may be a SplitAct; ``out_split`` returns one (bf16 tensor-core engines
@@ -257,6 +271,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
         if a2 is not None:
             a2 = _chk(a2, name="a2")
             k2 = a2.shape[1] // groups
+        elif a2_gather is not None:
+            k2 = k1
     if k1 + k2 != ktot:
         raise GrafpError("gemm: weight has %d columns, operands give %d" % (ktot, k1 + k2))
     dev = a1.device if a1 is not None else a1s.device
@@ -277,6 +293,11 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
         args.a1_split, args.lda1s = None, 0
     args.a2, args.lda2, args.k2 = (a2.data_ptr() if a2 is not None else None), \
         (a2.stride(0) if a2 is not None else 0), k2
+    if a2_gather is not None:
+        gidx = _chk(a2_gather[0], torch.int32, "a2_gather idx")
+        args.a2_gather_idx, args.a2_gather_nodes, args.a2_gather_k = gidx.data_ptr(), int(a2_gather[1]), gidx.shape[-1]
+    else:
+        args.a2_gather_idx, args.a2_gather_nodes, args.a2_gather_k = None, 0, 0
     args.w, args.ldw = w.data_ptr(), w.stride(0)
     args.w_split = w_split.data_ptr() if w_split is not None else None
     args.w_split_bf16 = w_split_bf16.data_ptr() if w_split_bf16 is not None else None

@@ -359,6 +359,38 @@ def test_gemm_split_bf16_activations_bit_exact(M, k, hid, n, groups, engine):
     assert torch.equal(y32, ys)
 
 
+@pytest.mark.parametrize("B,N,C,k,groups", [(5, 256, 64, 3, 1), (9, 128, 128, 3, 4), (7, 64, 256, 5, 4), (11, 32, 512, 3, 4),
+                                            (3, 64, 256, 9, 4)])
+@pytest.mark.parametrize("out_split", [False, True])
+def test_gemm_fused_max_relative_bit_exact(B, N, C, k, groups, out_split):
+    """Fused MRConv2d (grafp_gemm_args.a2_gather_idx): the max-relative aggregate is computed by the GEMM's
+    transform warps instead of being read -- BIT-identical to mr_aggregate + dual-source GEMM (ragged last
+    tile included: B*N is not a multiple of 128 for the small-N cases)."""
+    ops = _ops()
+    from neuralsampleid_b200 import _prep
+    x = synth.synth_normal((B * N, C), 70).to(DEV)
+    rng = np.random.Generator(np.random.PCG64(9))
+    idx = torch.from_numpy(rng.integers(0, N, size=(B, N, k), dtype=np.int64)).int().to(DEV)
+    idx[:, :, 0] = torch.arange(N, device=DEV)
+    n_out = 2 * C
+    w = (synth.synth_normal((n_out, 2 * C // groups), 71) / float(np.sqrt(2 * C // groups))).to(DEV)
+    scale = synth.synth_uniform((n_out,), 72, 0.5, 1.5).to(DEV)
+    shift = synth.synth_uniform((n_out,), 73, -0.5, 0.5).to(DEV)
+    lin = _prep.make_linear(w, scale, shift, groups, dual=True)
+    os.environ["GRAFP_FUSED_MR"] = "1"
+    try:
+        assert ops.fused_mr_ok(lin, C)
+    finally:
+        del os.environ["GRAFP_FUSED_MR"]
+    m = ops.mr_aggregate(x, idx, B, N)
+    want = ops.linear(x, lin, "relu", 0.0, a2=m, out_split=out_split)
+    got = ops.linear(x, lin, "relu", 0.0, out_split=out_split, a2_gather=(idx, N))
+    if out_split:
+        assert torch.equal(got.t, want.t)
+    else:
+        assert torch.equal(got, want)
+
+
 def test_gemm_split_bf16_needs_bf16_engine():
     ops = _ops()
     from neuralsampleid_b200 import _lib, _prep
