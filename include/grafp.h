@@ -149,6 +149,7 @@ typedef struct {
    * travel as the operand pair the bf16x3 engine computes with: a bf16 tensor (2, M, C), plane 0 =
    * bf16(v), plane 1 = bf16(v - bf16(v)).  Same bytes as fp32, bit-identical operands, and the
    * consuming GEMM needs no in-kernel conversion stage.
+   * With GRAFP_ENGINE_TC_BF16 (one MMA pass) the format is the hi plane alone: a plain bf16 (M, C) tensor.
    *   y_split   when non-NULL the output is written in this form (row stride ldys elements,
    *             plane stride m*ldys) INSTEAD of y (y may then be NULL)
    *   a1_split  when non-NULL the first A source is read in this form (row stride lda1s elements,

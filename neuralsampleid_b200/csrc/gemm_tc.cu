@@ -53,7 +53,7 @@ struct TcParams {
   float* row_sumsq;
   int act; float act_param;
   uint32_t tmem_cols;
-  int y_split;         // output as bf16 [hi ; lo] planes (tmY is then the 3-D bf16 map)
+  int y_split;         // 0: fp32 output; 2: bf16 [hi ; lo] planes; 1: bf16 hi plane only (1-pass engine)
   int raw;             // depth of the fp32 A ring (bf16 engines with an fp32 A operand)
   // fused max-relative aggregation: the second A source is not read but computed by the transform warps,
   // a2[m, c] = max_t (a1[graph(m) + idx[m, t], c] - a1[m, c])  (bf16 engines, fp32 A)
@@ -503,8 +503,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           for (int q = 0; q < 4; ++q) {
             const uint32_t off = (uint32_t)r * 64u + ((uint32_t)(q ^ ((r >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(sb + off) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
-            *reinterpret_cast<uint4*>(sb + TC_STORE_BYTES / 2 + off) =
-                make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+            if (p.y_split == 2)
+              *reinterpret_cast<uint4*>(sb + TC_STORE_BYTES / 2 + off) =
+                  make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
           }
         } else {
 #pragma unroll
@@ -517,7 +518,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (store_thread) {
           if (p.y_split) {
             tma_store_3d(&tmY, sb, (int)(col0 + c), m0, 0);
-            tma_store_3d(&tmY, sb + TC_STORE_BYTES / 2, (int)(col0 + c), m0, 1);
+            if (p.y_split == 2) tma_store_3d(&tmY, sb + TC_STORE_BYTES / 2, (int)(col0 + c), m0, 1);
           } else {
             tma_store_2d(&tmY, sb, (int)(col0 + c), m0);
           }
@@ -693,7 +694,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   } else {
     if (a.a1_split) {
       GRAFP_REQUIRE(bf16, "gemm_tc: a split-bf16 A operand needs a bf16 engine");
-      if (int rc = tc_make_map_3d_bf16(&mA1, a.a1_split, (int64_t)a.groups * a.k1, a.m, 2, a.lda1s,
+      if (int rc = tc_make_map_3d_bf16(&mA1, a.a1_split, (int64_t)a.groups * a.k1, a.m, passes == 3 ? 2 : 1, a.lda1s,
                                        a.m * a.lda1s, TC_BM))
         return rc;
     } else if (int rc = tc_make_map_2d(&mA1, a.a1, a.m, (int64_t)a.groups * a.k1, a.lda1, TC_BM)) {
@@ -719,11 +720,11 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
                                      a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
     return rc;
   if (a.y_split) {
-    if (int rc = tc_make_map_3d_bf16(&mY, a.y_split, n_total, a.m, 2, a.ldys, a.m * a.ldys, TC_BM)) return rc;
+    if (int rc = tc_make_map_3d_bf16(&mY, a.y_split, n_total, a.m, passes == 3 ? 2 : 1, a.ldys, a.m * a.ldys, TC_BM)) return rc;
   } else if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) {
     return rc;
   }
-  p.y_split = a.y_split ? 1 : 0;
+  p.y_split = a.y_split ? (passes == 3 ? 2 : 1) : 0;     // the 1-pass engine carries the hi plane only
   p.gat_idx = a.a2_gather_idx; p.gat_x = a.a1; p.gat_ld = a.lda1; p.gat_n = a.a2_gather_nodes; p.gat_k = a.a2_gather_k;
   const bool asplit = a.a1_split != nullptr;
   p.k1 = a.k1; p.k2 = a.k2; p.n = a.n; p.bn = bn; p.n_total = n_total; p.groups = a.groups; p.m = a.m;

@@ -198,8 +198,8 @@ class SplitAct:
         return self.t.device
 
     def float(self) -> torch.Tensor:
-        """fp32 value hi + lo (test / debugging helper)."""
-        return self.t[0].float() + self.t[1].float()
+        """fp32 value hi (+ lo) (test / debugging helper)."""
+        return self.t[0].float() + (self.t[1].float() if self.t.shape[0] > 1 else 0.0)
 
 
 def split_ok(lin, k_total: int) -> bool:
@@ -276,10 +276,16 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     if k1 + k2 != ktot:
         raise GrafpError("gemm: weight has %d columns, operands give %d" % (ktot, k1 + k2))
     dev = a1.device if a1 is not None else a1s.device
+    # the engine a split GEMM runs on (split_ok() admitted only bf16 tensor-core engines): the 1-pass bf16
+    # engine carries the hi plane only
+    split_engine = engine if engine is not None else (ENGINES[_engine_override] if _engine_override is not None else _engine)
+    planes = 1 if split_engine == _lib.ENGINE_TC_BF16 else 2
+    if a1s is not None and a1s.shape[0] < planes:
+        raise GrafpError("gemm: a hi-plane-only SplitAct can only feed the 1-pass bf16 engine")
     if out_split:
         if out is not None or row_sumsq is not None:
             raise GrafpError("gemm: out_split cannot be combined with out= / row_sumsq")
-        out = torch.empty((2, M, n_total), device=dev, dtype=torch.bfloat16)
+        out = torch.empty((planes, M, n_total), device=dev, dtype=torch.bfloat16)
     elif out is None:
         out = torch.empty((M, n_total), device=dev, dtype=torch.float32)
     elif out.shape != (M, n_total) or out.stride(1) != 1:
