@@ -279,9 +279,8 @@ def run_native(args):
     if not args.no_graph:
         try:
             from neuralsampleid_b200.graphed import GraphedEncoder
-            n_before = _lib.launch_count()
             graphed = GraphedEncoder(enc, hi - lo, 256, 8, warmup=2)
-            launches_per_step = (_lib.launch_count() - n_before) // 3        # 2 warm-ups + 1 capture
+            launches_per_step = graphed.kernel_nodes                          # counted during the capture
             graphed.input.copy_(x_dev)
             graph_note = "cuda graph replay (%d kernel nodes)" % launches_per_step
         except Exception as e:                                                # pragma: no cover

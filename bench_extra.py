@@ -45,6 +45,18 @@ def _model(dev, k):
     return model.to(dev)
 
 
+def _finish(world):
+    """End of a mode: flush and leave WITHOUT tearing NCCL down.  destroy_process_group() after a CUDA graph that
+    captured NCCL collectives (the graphed train step) hung all 8 ranks until the job's timeout."""
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def _timed(fn, steps, world, dev):
     if world > 1:
         dist.barrier()
@@ -96,8 +108,7 @@ def mode_train(args):
                           "loss_last": float(losses[-1]),
                           "config": "SimCLR(GraphEncoder t, k=5) fwd+bwd, NT-Xent (global negatives via NCCL "
                                     "all-gather), summed grad all-reduce, clip 1.0, Adam 8e-5"}))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 def mode_db(args):
@@ -131,8 +142,7 @@ def mode_db(args):
                           "h2d_bytes_per_segment": 64 * 128 * 4, "d2h_bytes_per_segment": 128 * 4,
                           "config": "SimCLR eval (peak extractor + GraphEncoder t k=3 + projector + L2 norm), CUDA graph "
                                     "replay per batch, pinned host in/out, contiguous segment ranges per rank"}))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 def mode_sweep(args):

@@ -36,7 +36,8 @@ extern "C" {
 /* activation codes (reference: act_layer, encoder/gcn_lib/torch_nn.py:9-25; ELU for the
  * projector, simclr/simclr.py:26) */
 enum { GRAFP_ACT_NONE = 0, GRAFP_ACT_RELU = 1, GRAFP_ACT_LEAKY = 2, GRAFP_ACT_GELU = 3,
-       GRAFP_ACT_ELU = 4 };
+       GRAFP_ACT_ELU = 4,
+       GRAFP_ACT_SIGMOID = 5 /* the re-ranker's output unit (downstream.py:55); fp32 SIMT GEMM engine only */ };
 
 /* GEMM engines */
 enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 bf16x3 (else 3xTF32) where the shape and the split
@@ -182,6 +183,19 @@ int grafp_split_bf16(const float* w, int64_t count, void* out_bf16_hi_lo, void* 
  * Cin in {4, 8, 16}; Cout = 4 * (a divisor of 256). */
 int grafp_stem_fwd(const float* x, const float* w, const float* scale, const float* shift, int B, int Cin,
                    int N, int Cout, int nchw, int act, float act_param, float* out, void* stream);
+
+/* (B, C, N) -> node-major (B*N, C) with a per-node row added: dst[b*N + n, c] = src[b, c, n] + pos[n, c]
+ * (pos may be NULL).  The re-ranker's positional embedding (downstream.py:66-70) fused with the layout change. */
+int grafp_nchw_to_nodes_add(const float* src, const float* pos, float* dst, int B, int C, int N, void* stream);
+
+/* ---- re-ranker attention -------------------------------------------------
+ * Per-head cross attention of nn.MultiheadAttention followed by CrossAttentionClassifier's mean over the
+ * query nodes (downstream.py:72-73), the mean taken before the output projection:
+ *   out[p, h*Dh + d] = mean_i sum_j softmax_j(scale * <Q[p,i,h,:], K[p,j,h,:]>) V[p,j,h,d]
+ * q (P*Nq, H*Dh) row stride ldq; k, v (P*Nk, H*Dh) row strides ldk, ldv (k and v may be column halves of
+ * one fused projection output); out (P, H*Dh) row stride ldo.  Exact fp32, one CTA per (pair, head). */
+int grafp_mha_pool_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                       int P, int Nq, int Nk, int H, int Dh, float scale, float* out, int64_t ldo, void* stream);
 
 /* mean over the nodes of each graph: x (B*N, C) -> out (B, C)   (graph_encoder.py:211) */
 int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream);

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgrafp_sm100a.so")
 
-ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_ELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16X3, ENGINE_TC_BF16 = 0, 1, 2, 3, 4, 5
 ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "3xtf32": ENGINE_TC_3XTF32,
            "tf32": ENGINE_TC_TF32, "bf16x3": ENGINE_TC_BF16X3, "bf16": ENGINE_TC_BF16}
@@ -53,6 +53,8 @@ SIGNATURES = {
     "grafp_split_tf32": [_P, _L, _P, _P],
     "grafp_split_bf16": [_P, _L, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
+    "grafp_nchw_to_nodes_add": [_P, _P, _P, _I, _I, _I, _P],
+    "grafp_mha_pool_fwd": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _P, _L, _P],
     "grafp_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P],
     "grafp_peak_extract_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "grafp_l2_normalize_rows": [_P, _L, _I, _F, _P, _P],

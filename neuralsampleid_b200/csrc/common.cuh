@@ -25,6 +25,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float p) {
     case GRAFP_ACT_LEAKY: return v > 0.0f ? v : v * p;
     case GRAFP_ACT_GELU:  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
     case GRAFP_ACT_ELU:   return v > 0.0f ? v : expm1f(v);
+    case GRAFP_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
     default:              return v;
   }
 }

@@ -25,7 +25,9 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
     GRAFP_REQUIRE(a.groups == 1 && a.k2 == 0 && a.k1 % 12 == 0, "gemm: tap3 needs groups=1, k2=0, k1=3*Cin");
     GRAFP_REQUIRE(a.m % a.tap3_nodes == 0, "gemm: tap3 m must be a multiple of tap3_nodes");
   }
-  GRAFP_REQUIRE(a.act >= GRAFP_ACT_NONE && a.act <= GRAFP_ACT_ELU, "gemm: unknown activation %d", a.act);
+  GRAFP_REQUIRE(a.act >= GRAFP_ACT_NONE && a.act <= GRAFP_ACT_SIGMOID, "gemm: unknown activation %d", a.act);
+  GRAFP_REQUIRE(a.act != GRAFP_ACT_SIGMOID || a.engine == GRAFP_ENGINE_SIMT || a.engine == GRAFP_ENGINE_AUTO,
+                "gemm: the sigmoid epilogue exists on the fp32 SIMT engine only");
   if (a.m == 0) return 0;
   cudaStream_t st = as_stream(stream);
   if (a.a2_gather_idx) {
@@ -64,6 +66,7 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
       GRAFP_REQUIRE(a.w_split_bf16, "gemm: the bf16 engines need w_split_bf16 (grafp_split_bf16)");
       return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_BF16X3 ? 3 : 1, 1, st);
     case GRAFP_ENGINE_AUTO:
+      if (a.act == GRAFP_ACT_SIGMOID) return gemm_simt_launch(a, st);
       if (a.w_split_bf16 && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, 1, st);
       if (a.w_split && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, 0, st);
       return gemm_simt_launch(a, st);

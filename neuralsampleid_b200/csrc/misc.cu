@@ -57,6 +57,25 @@ __global__ void transpose_batched_kernel(const float* __restrict__ src, float* _
   }
 }
 
+// (B, C, N) -> (B*N, C) with a per-node row added: dst[b, n, c] = src[b, c, n] + pos[n, c]
+__global__ void transpose_add_kernel(const float* __restrict__ src, const float* __restrict__ pos,
+                                     float* __restrict__ dst, int R, int S) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* s = src + (size_t)b * R * S;
+  float* d = dst + (size_t)b * R * S;
+  const int r0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = s0 + threadIdx.x;
+    if (r < R && c < S) tile[i][threadIdx.x] = s[(size_t)r * S + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = s0 + i, r = r0 + threadIdx.x;          // c: node, r: channel
+    if (r < R && c < S) d[(size_t)c * R + r] = tile[threadIdx.x][i] + (pos ? pos[(size_t)c * R + r] : 0.0f);
+  }
+}
+
 static int transpose_batched(const float* src, float* dst, int B, int R, int S, cudaStream_t st) {
   if (B == 0 || R == 0 || S == 0) return 0;
   for (int b0 = 0; b0 < B; b0 += 65535) {
@@ -276,6 +295,19 @@ int grafp_peak_extract_fwd(const float* spec, const float* w, const float* bias,
   peak_extract_kernel<<<B, 256, smem, as_stream(stream)>>>(spec, w, bias, n_mels, n_frames, F, pb,
                                                           pf, out);
   return check_launch("peak_extract");
+}
+
+int grafp_nchw_to_nodes_add(const float* src, const float* pos, float* dst, int B, int C, int N, void* stream) {
+  GRAFP_REQUIRE(B == 0 || (src && dst), "nchw_to_nodes_add: null pointer");
+  GRAFP_REQUIRE(B >= 0 && C > 0 && N > 0, "nchw_to_nodes_add: bad sizes");
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    int nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((N + 31) / 32, (C + 31) / 32, nb), block(32, 8);
+    transpose_add_kernel<<<grid, block, 0, as_stream(stream)>>>(src + (size_t)b0 * C * N, pos,
+                                                               dst + (size_t)b0 * C * N, C, N);
+    if (int rc = check_launch("transpose_add")) return rc;
+  }
+  return 0;
 }
 
 int grafp_stem_fwd(const float* x, const float* w, const float* scale, const float* shift, int B, int Cin,

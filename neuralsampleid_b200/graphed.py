@@ -35,9 +35,12 @@ class GraphedEncoder:
             for _ in range(warmup):                       # builds the prepared weights outside the capture
                 enc(self.input, return_pre_proj=return_pre_proj)
         torch.cuda.current_stream(dev).wait_stream(stream)
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.output = enc(self.input, return_pre_proj=return_pre_proj)
+        self.kernel_nodes = _lib.launch_count() - n0      # libgrafp kernels recorded in the graph
 
     def replay(self) -> None:
         self.graph.replay()

@@ -10,11 +10,11 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (ACT_ELU, ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ENGINES, GemmArgs,
+from ._lib import (ACT_ELU, ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ENGINES, GemmArgs,
                    GrafpError, check)
 
 _ACTS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leakyrelu": ACT_LEAKY,
-         "gelu": ACT_GELU, "elu": ACT_ELU}
+         "gelu": ACT_GELU, "elu": ACT_ELU, "sigmoid": ACT_SIGMOID}
 
 _engine = ENGINES[os.environ.get("GRAFP_ENGINE", "auto").lower()]
 # test/bench hook: a tensor-core engine name applied to every GEMM whose shape the tensor-core
@@ -355,6 +355,37 @@ def stem(x: torch.Tensor, lin, act=None, act_param: float = 0.0, B: int = None, 
     with torch.cuda.device(x.device):
         check(_lib.load().grafp_stem_fwd(_ptr(x), _ptr(lin.w), _ptr(lin.scale), _ptr(lin.shift), B, cin, N, cout,
                                          int(nchw), act_code(act), act_param, _ptr(out), _stream(x)), "stem_fwd")
+    return out
+
+
+def nchw_to_nodes_add(x: torch.Tensor, pos: Optional[torch.Tensor]) -> torch.Tensor:
+    """(B, C, N) -> (B*N, C) with pos (N, C) added to every graph's rows (pos may be None)."""
+    x = _chk(x, name="x")
+    B, Cc, N = x.shape
+    if pos is not None:
+        pos = _chk(pos, name="pos")
+        if tuple(pos.shape) != (N, Cc):
+            raise GrafpError("nchw_to_nodes_add: pos must be (N, C) = (%d, %d), got %s" % (N, Cc, tuple(pos.shape)))
+    out = torch.empty((B * N, Cc), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_nchw_to_nodes_add(_ptr(x), _ptr(pos), _ptr(out), B, Cc, N, _stream(x)),
+              "nchw_to_nodes_add")
+    return out
+
+
+def mha_pool(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, P: int, Nq: int, Nk: int, heads: int) -> torch.Tensor:
+    """mean over the Nq queries of per-head softmax(q k^T / sqrt(Dh)) v:  q (P*Nq, E), k / v (P*Nk, E) row-major
+    views with unit column stride (column slices of a fused projection are fine) -> (P, E)."""
+    E = q.shape[1]
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.stride(1) != 1 or t.shape[1] != E:
+            raise GrafpError("mha_pool: %s must be an fp32 CUDA (rows, E) view with unit column stride" % nm)
+    Dh = E // heads
+    out = torch.empty((P, E), device=q.device, dtype=torch.float32)
+    with torch.cuda.device(q.device):
+        check(_lib.load().grafp_mha_pool_fwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), P, Nq, Nk,
+                                             heads, Dh, 1.0 / float(Dh) ** 0.5, _ptr(out), out.stride(0), _stream(q)),
+              "mha_pool_fwd")
     return out
 
 

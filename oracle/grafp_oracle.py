@@ -353,6 +353,31 @@ def simclr_forward(p: Params, x_i: Tensor, x_j: Tensor, k: int = 3, size: str = 
     return outs[0][0], outs[1][0], outs[0][1], outs[1][1]
 
 
+def cross_attention_classifier(p: Params, x_i: Tensor, x_j: Tensor, num_heads: int = 4,
+                               prefix: str = "") -> Tensor:
+    """CrossAttentionClassifier.forward in eval mode, downstream.py:58-75: positional embedding, 
+    nn.MultiheadAttention(query = x_i, key = value = x_j, batch_first), mean over the nodes, fc (Linear, ReLU,
+    Dropout = identity, Linear, Sigmoid).  x_i, x_j: (B, C, N) -> (B, 1)."""
+    xi, xj = x_i.permute(0, 2, 1), x_j.permute(0, 2, 1)                    # (B, N, C)
+    if prefix + "positional_embedding" in p:
+        pos = p[prefix + "positional_embedding"][:, :xi.shape[1], :]
+        xi, xj = xi + pos, xj + pos
+    E = xi.shape[-1]
+    w, b = p[prefix + "attn.in_proj_weight"], p[prefix + "attn.in_proj_bias"]
+    q = F.linear(xi, w[:E], b[:E])
+    k = F.linear(xj, w[E:2 * E], b[E:2 * E])
+    v = F.linear(xj, w[2 * E:], b[2 * E:])
+    B, N, _ = q.shape
+    dh = E // num_heads
+    split = lambda t: t.reshape(B, N, num_heads, dh).transpose(1, 2)       # (B, H, N, dh)
+    att = torch.softmax((split(q) * (1.0 / float(dh) ** 0.5)) @ split(k).transpose(-1, -2), dim=-1)
+    o = (att @ split(v)).transpose(1, 2).reshape(B, N, E)
+    o = F.linear(o, p[prefix + "attn.out_proj.weight"], p[prefix + "attn.out_proj.bias"])
+    h = o.mean(dim=1)
+    h = torch.relu(F.linear(h, p[prefix + "fc.0.weight"], p[prefix + "fc.0.bias"]))
+    return torch.sigmoid(F.linear(h, p[prefix + "fc.3.weight"], p[prefix + "fc.3.bias"]))
+
+
 def ntxent_loop(z_i: Tensor, z_j: Tensor, tau: float) -> Tensor:
     """ntxent_loss restated row by row exactly as simclr/ntxent.py:18-29 (small cases)."""
     z = torch.stack((z_i, z_j), dim=1).view(2 * z_i.shape[0], z_i.shape[1])

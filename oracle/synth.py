@@ -97,6 +97,15 @@ def graphconv_state_spec(conv: str, cin: int, cout: int, signed_bn: bool = True)
     raise ValueError(conv)
 
 
+def reranker_state_spec(in_dim: int = 512, hidden: int = 128, num_nodes: int = 100) -> Spec:
+    """state_dict of CrossAttentionClassifier(in_dim, 4, hidden, num_nodes, True) (downstream.py:30-56)."""
+    return [("positional_embedding", (1, num_nodes, in_dim), "pos"),
+            ("attn.in_proj_weight", (3 * in_dim, in_dim), "w"), ("attn.in_proj_bias", (3 * in_dim,), "b"),
+            ("attn.out_proj.weight", (in_dim, in_dim), "w"), ("attn.out_proj.bias", (in_dim,), "b"),
+            ("fc.0.weight", (hidden, in_dim), "w"), ("fc.0.bias", (hidden,), "b"),
+            ("fc.3.weight", (1, hidden), "w"), ("fc.3.bias", (1,), "b")]
+
+
 def _uniform(rng: np.random.Generator, shape, lo: float, hi: float) -> np.ndarray:
     """Exact-arithmetic uniform floats: 24-bit integers / 2^24 in float64, affine, -> fp32."""
     n = int(np.prod(shape)) if len(shape) else 1
@@ -126,6 +135,8 @@ def synth_state(spec: Spec, seed: int = 1234) -> Dict[str, torch.Tensor]:
             a = _uniform(rng, shape, 0.5, 1.5)
         elif role == "bn_ws":                             # signed BatchNorm scale (max over edges then is
             a = _uniform(rng, shape, -1.2, 1.2)           # not a monotone function of the pre-activation)
+        elif role == "pos":
+            a = _uniform(rng, shape, -1.0, 1.0)
         elif role == "eps":
             a = _uniform(rng, shape, 0.1, 0.4)
         elif role == "count":
@@ -158,3 +169,12 @@ def state_sha256(sd: Dict[str, torch.Tensor]) -> str:
         h.update(name.encode())
         h.update(sd[name].detach().cpu().contiguous().numpy().tobytes())
     return h.hexdigest()
+
+
+def reranker_inputs(B: int, N: int, seed: int, in_dim: int = 512):
+    """(x_i, x_j) node matrices (B, in_dim, N) for the re-ranker: the first half are perturbed copies (matching
+    pairs), the second half unrelated.  Portable (same PCG64 streams everywhere), so fixtures store outputs only."""
+    x_i = synth_normal((B, in_dim, N), seed)
+    x_j = x_i + 0.5 * synth_normal((B, in_dim, N), seed + 1)
+    x_j[B // 2:] = synth_normal((B - B // 2, in_dim, N), seed + 2)
+    return x_i, x_j

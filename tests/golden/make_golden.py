@@ -95,6 +95,19 @@ def capture_graphconv(ref, conv, act, k, d, cin, cout, N, B, seed):
     return {"x": x.numpy(), "idx": edge[0].numpy().astype(np.int16), "y": y.numpy()}
 
 
+def capture_reranker(B, N, seed):
+    """CrossAttentionClassifier (downstream.py:30-79) in eval mode on (B, 512, N) node matrices."""
+    from refimport import import_reference_reranker
+    m = import_reference_reranker()(512, 4, 128, 100, True).eval()
+    sd = synth.synth_state(synth.reranker_state_spec(512, 128, 100), WEIGHT_SEED + 4)
+    assert sorted(sd.keys()) == sorted(m.state_dict().keys()), sorted(m.state_dict().keys())
+    m.load_state_dict(sd)
+    x_i, x_j = synth.reranker_inputs(B, N, seed)                           # half matching, half unrelated pairs
+    with torch.no_grad():
+        y = m(x_i, x_j)
+    return {"y": y.numpy(), "B": np.int64(B), "N": np.int64(N), "seed": np.int64(seed)}
+
+
 def capture_ntxent(ref, B, seed):
     z_i = torch.nn.functional.normalize(synth.synth_normal((B, 128), seed), dim=1)
     z_j = torch.nn.functional.normalize(z_i + 0.3 * synth.synth_normal((B, 128), seed + 1), dim=1)
@@ -167,6 +180,7 @@ def main():
     for conv, act in (("edge", "gelu"), ("edge", "relu"), ("sage", "relu"), ("gin", "leakyrelu")):
         np.savez_compressed(os.path.join(HERE, "graphconv_%s_%s.npz" % (conv, act)),
                             **capture_graphconv(ref, conv, act, 4, 2, 64, 128, 64, 3, 51))
+    np.savez_compressed(os.path.join(HERE, "reranker_b16_n32.npz"), **capture_reranker(16, 32, 61))
     np.savez_compressed(os.path.join(HERE, "ntxent_b16.npz"), **capture_ntxent(ref, 16, 41))
     np.savez_compressed(os.path.join(HERE, "simclr_eval_b4.npz"), **capture_simclr(ref, 3, 4, False))
     np.savez_compressed(os.path.join(HERE, "simclr_train_b8.npz"), **capture_simclr(ref, 5, 8, True))

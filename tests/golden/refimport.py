@@ -68,3 +68,21 @@ def import_reference():
         dense_knn_matrix=dense_knn_matrix, batched_index_select=batched_index_select,
         BasicConv=BasicConv, SimCLR=SimCLR, ntxent_loss=ntxent_loss, cfg=cfg)
     return ns
+
+
+def import_reference_reranker():
+    """CrossAttentionClassifier of the reference's downstream.py (lines 30-79).  The file itself cannot be imported
+    here (tensorboard / DGL / dataset imports at module level), so only the class definition is compiled, from the
+    reference source where it lies, into a namespace that provides torch / nn / F."""
+    import ast
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    path = os.path.join(REFERENCE_ROOT, "downstream.py")
+    tree = ast.parse(open(path).read(), path)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CrossAttentionClassifier"]
+    if not cls:
+        raise RuntimeError("CrossAttentionClassifier not found in %s" % path)
+    ns = {"torch": torch, "nn": nn, "F": F}
+    exec(compile(ast.Module(body=cls, type_ignores=[]), path, "exec"), ns)
+    return ns["CrossAttentionClassifier"]

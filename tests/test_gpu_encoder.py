@@ -229,6 +229,38 @@ def test_other_graph_convs_match_golden_and_oracle(golden_dir, conv, act):
         assert torch.allclose(a, b, rtol=3e-4, atol=3e-4), float((a - b).abs().max())
 
 
+def test_reranker_matches_golden_and_oracle(golden_dir):
+    """CrossAttentionClassifier (reference downstream.py:30-79): the five-kernel batch
+    evaluation against the vector minted from the reference class, and against the oracle for other shapes
+    (fewer nodes than the positional table, no positional embedding, 2 heads)."""
+    from neuralsampleid_b200.downstream import CrossAttentionClassifier
+    g = np.load(os.path.join(golden_dir, "reranker_b16_n32.npz"))
+    sd = synth.synth_state(synth.reranker_state_spec(512, 128, 100), 1238)
+    m = CrossAttentionClassifier(512, 4, 128, 100, True)
+    assert sorted(m.state_dict().keys()) == sorted(sd.keys())
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    x_i, x_j = synth.reranker_inputs(int(g["B"]), int(g["N"]), int(g["seed"]))
+    with torch.no_grad():
+        y = m(x_i.to(DEV), x_j.to(DEV)).cpu()
+    assert y.shape == (16, 1)
+    assert torch.allclose(y, torch.from_numpy(g["y"]), rtol=1e-4, atol=1e-5), float((y - torch.from_numpy(g["y"])).abs().max())
+    for in_dim, heads, hidden, nodes, pos, B, N in ((512, 4, 128, 100, True, 5, 20), (256, 2, 64, 40, False, 3, 40),
+                                                  (128, 4, 32, 64, True, 130, 32)):
+        sd2 = synth.synth_state([e for e in synth.reranker_state_spec(in_dim, hidden, nodes)
+                                 if pos or e[0] != "positional_embedding"], 77)
+        m2 = CrossAttentionClassifier(in_dim, heads, hidden, nodes, pos)
+        m2.load_state_dict(sd2)
+        m2 = m2.to(DEV).eval()
+        a, b = synth.reranker_inputs(B, N, 90, in_dim)
+        with torch.no_grad():
+            got = m2(a.to(DEV), b.to(DEV)).cpu()
+            want = O.cross_attention_classifier(sd2, a, b, heads)
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), float((got - want).abs().max())
+    with pytest.raises(RuntimeError):
+        m.train()(x_i.to(DEV), x_j.to(DEV))
+
+
 def test_grapher_module_api_matches_oracle():
     from neuralsampleid_b200.encoder.gcn_lib.torch_vertex import Grapher
     from neuralsampleid_b200.encoder.gcn_lib.torch_nn import batched_index_select

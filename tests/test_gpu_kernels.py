@@ -448,6 +448,44 @@ def test_gemm_empty_and_errors():
 # ------------------------------------------------------------------------------------------
 # small stages
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P,Nq,Nk,H,Dh", [(3, 32, 32, 4, 128), (2, 20, 20, 2, 64), (5, 7, 13, 1, 32), (1, 64, 64, 4, 128)])
+def test_mha_pool_matches_torch(P, Nq, Nk, H, Dh):
+    """grafp_mha_pool_fwd: per-head softmax attention + mean over the queries, k / v as column halves of one
+    fused projection output (strided views), against fp64 torch."""
+    ops = _ops()
+    E = H * Dh
+    q = synth.synth_normal((P * Nq, E), 80)
+    kv = synth.synth_normal((P * Nk, 2 * E), 81)
+    got = ops.mha_pool(q.to(DEV), kv.to(DEV)[:, :E], kv.to(DEV)[:, E:], P, Nq, Nk, H).cpu().double()
+    qq = q.double().view(P, Nq, H, Dh).transpose(1, 2)
+    kk = kv[:, :E].double().reshape(P, Nk, H, Dh).transpose(1, 2)
+    vv = kv[:, E:].double().reshape(P, Nk, H, Dh).transpose(1, 2)
+    att = torch.softmax(qq @ kk.transpose(-1, -2) / float(Dh) ** 0.5, dim=-1)
+    want = (att @ vv).mean(dim=2).reshape(P, E)                       # (P, H, Dh) -> (P, E)
+    assert got.shape == want.shape and float((got - want).abs().max()) < 1e-5
+    # positional add fused with the layout change
+    x = synth.synth_normal((P, 24, Nq), 82)
+    pos = synth.synth_normal((Nq, 24), 83)
+    nodes = ops.nchw_to_nodes_add(x.to(DEV), pos.to(DEV)).cpu()
+    assert torch.equal(nodes, (x.transpose(1, 2) + pos).reshape(P * Nq, 24))
+    assert torch.equal(ops.nchw_to_nodes_add(x.to(DEV), None).cpu(), x.transpose(1, 2).reshape(P * Nq, 24))
+
+
+def test_gemm_sigmoid_epilogue_simt_only():
+    ops = _ops()
+    from neuralsampleid_b200 import _lib, _prep
+    a = synth.synth_normal((70, 128), 84)
+    w = synth.synth_normal((1, 128), 85) / 11.0
+    b = synth.synth_uniform((1,), 86, -0.5, 0.5)
+    lin = _prep.make_linear(w.to(DEV), None, b.to(DEV))
+    got = ops.linear(a.to(DEV), lin, "sigmoid").cpu()
+    want = torch.sigmoid(a.double() @ w.double().T + b.double()).float()
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    w64 = (synth.synth_normal((64, 128), 87) / 11.0).to(DEV)
+    with pytest.raises(_lib.GrafpError):
+        ops.linear(a.to(DEV), _prep.make_linear(w64, None, None), "sigmoid", engine=_lib.ENGINES["bf16x3"])
+
+
 def test_node_mean_and_l2_normalize():
     ops = _ops()
     x = synth.synth_normal((6 * 32, 512), 30)

@@ -149,6 +149,16 @@ def test_state_spec_counts():
 # ----------------------------------------------------------------------------------- #
 # live reference (this container only)
 # ----------------------------------------------------------------------------------- #
+def test_oracle_reranker_matches_golden(golden_dir):
+    """CrossAttentionClassifier (downstream.py:30-79): oracle vs the vector minted from the reference class."""
+    g = np.load(os.path.join(golden_dir, "reranker_b16_n32.npz"))
+    sd = synth.synth_state(synth.reranker_state_spec(512, 128, 100), 1238)
+    x_i, x_j = synth.reranker_inputs(int(g["B"]), int(g["N"]), int(g["seed"]))
+    with torch.no_grad():
+        y = O.cross_attention_classifier(sd, x_i, x_j, 4)
+    assert y.shape == (16, 1) and torch.allclose(y, torch.from_numpy(g["y"]), rtol=1e-5, atol=1e-6)
+
+
 needs_ref = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
 
 
@@ -220,3 +230,20 @@ def test_oracle_vs_live_reference_other_graph_convs(conv, act):
         a = m(x)
         b = O.dy_graph_conv(sd, "gc", x, 4, 2, conv, act, False, None)
     assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+
+
+@needs_ref
+@pytest.mark.reference
+def test_oracle_vs_live_reference_reranker():
+    from refimport import import_reference_reranker
+    torch.manual_seed(4)
+    m = import_reference_reranker()(64, 4, 32, 50, True).eval()
+    x_i, x_j = torch.randn(3, 64, 20), torch.randn(3, 64, 20)
+    with torch.no_grad():
+        a = m(x_i, x_j)
+        b = O.cross_attention_classifier(dict(m.state_dict()), x_i, x_j, 4)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    m2 = import_reference_reranker()(64, 2, 32, 50, False).eval()               # no positional embedding
+    with torch.no_grad():
+        assert torch.allclose(m2(x_i, x_j), O.cross_attention_classifier(dict(m2.state_dict()), x_i, x_j, 2),
+                              rtol=1e-6, atol=1e-7)
