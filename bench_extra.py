@@ -5,6 +5,7 @@
   python bench_extra.py db     [--segments 1000000]          config 4: spectrogram segments -> 128-d fingerprints
   python bench_extra.py sweep                                 config 5: dynamic-graph stress sweep (kNN + aggregate)
   python bench_extra.py chunks                                generate.py call shape: chunks of 128 segments
+  python bench_extra.py search [--segments 1000000]           SURVEY 8f rank 4: exact L2 search of the fingerprint DB
 
 Each mode prints one JSON line (rank 0).  Synthetic data, random-init weights.
 """
@@ -191,16 +192,50 @@ def mode_chunks(args):
                           "graph_seg_s": 128 / (ms_graph * 1e-3)}))
 
 
+def mode_search(args):
+    """exact squared-L2 search of the fingerprint database (eval.py's index type 'l2')."""
+    from neuralsampleid_b200.db import FlatL2Index
+    from oracle.flat_l2 import flat_l2_search              # CPU baseline leg only
+    world, rank, dev = _setup()
+    n, nq, k, d = args.segments, args.queries, 20, 128
+    g = torch.Generator(device=dev).manual_seed(5)
+    db = torch.nn.functional.normalize(torch.randn((n, d), device=dev, generator=g), dim=1)
+    q = torch.nn.functional.normalize(db[torch.randint(0, n, (nq,), device=dev, generator=g)] +
+                                      0.05 * torch.randn((nq, d), device=dev, generator=g), dim=1)
+    index = FlatL2Index(d, dev)
+    index.add(db)
+    index.search(q, k)                                     # warm-up
+    steps = 5
+    ms = _timed(lambda: index.search(q, k), steps, world, dev) / steps
+    D, I = index.search(q, k)
+    t0 = time.perf_counter()
+    sample = 64
+    Dw, Iw = flat_l2_search(db.cpu().numpy(), q[:sample].cpu().numpy(), k)
+    cpu_s = time.perf_counter() - t0
+    agree = float((I[:sample].cpu().numpy() == Iw).mean())
+    if rank == 0:
+        print(json.dumps({"mode": "search", "metric": "exact L2 fingerprint search queries/s", "value": nq / (ms * 1e-3),
+                          "unit": "queries/s", "n_gpus": world, "database": n, "queries": nq, "k": k, "ms_per_search": ms,
+                          "pair_distances_per_s": nq * n / (ms * 1e-3),
+                          "cpu_baseline": {"value": sample / cpu_s, "unit": "queries/s", "kind": "port",
+                                           "sample": "%d queries, numpy float64 exact search" % sample},
+                          "id_agreement_with_exact": agree,
+                          "config": "FlatL2Index: bf16x3 tcgen05 GEMM per 65536-row chunk + threshold top-k scan + merge"}))
+    _finish(world)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["train", "db", "sweep", "chunks"])
+    ap.add_argument("mode", choices=["train", "db", "sweep", "chunks", "search"])
     ap.add_argument("--pairs", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--segments", type=int, default=1000000)
     ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--queries", type=int, default=2048)
     args = ap.parse_args()
     with torch.no_grad():
-        {"train": mode_train, "db": mode_db, "sweep": mode_sweep, "chunks": mode_chunks}[args.mode](args)
+        {"train": mode_train, "db": mode_db, "sweep": mode_sweep, "chunks": mode_chunks,
+         "search": mode_search}[args.mode](args)
 
 
 if __name__ == "__main__":

@@ -197,6 +197,23 @@ int grafp_nchw_to_nodes_add(const float* src, const float* pos, float* dst, int 
 int grafp_mha_pool_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                        int P, int Nq, int Nk, int H, int Dh, float scale, float* out, int64_t ldo, void* stream);
 
+/* ---- exact fingerprint search ----------------------------------------------
+ * The reference searches the (n, 128) fingerprint database with FAISS (eval.py:37-151, index.search(q, k_probe)
+ * at :306); index type 'l2' (IndexFlatL2) is the exact squared-L2 search these entry points reproduce on the
+ * GPU.  The matrix Y[q, j] = |d_j|^2 - 2 <q, d_j> is produced per database chunk by grafp_gemm_fwd (database rows
+ * as the weight operand, |d|^2 as `shift`, a1 = -2 q); then:
+ *   grafp_topk_rows_fwd   k smallest of each row of y (rows, cols) (row stride ldy) per column split:
+ *                         part_val / part_idx (rows, splits, k), indices = col_offset + column, unordered,
+ *                         index -1 = empty slot.  cols, ldy multiples of 4; 1 <= k <= 32.
+ *   grafp_topk_merge_fwd  merges `parts` partial lists per row (rows, parts, k) into (rows, k) sorted ascending
+ *                         (ties: lower index first), adding row_add[row] (|q|^2; may be NULL) to the values.
+ *   grafp_row_sumsq       out[m] = sum_c x[m, c]^2. */
+int grafp_topk_rows_fwd(const float* y, int64_t ldy, int rows, int64_t cols, int64_t col_offset, int k, int splits,
+                        float* part_val, int64_t* part_idx, void* stream);
+int grafp_topk_merge_fwd(const float* part_val, const int64_t* part_idx, int rows, int parts, int k,
+                         const float* row_add, float* out_val, int64_t* out_idx, void* stream);
+int grafp_row_sumsq(const float* x, int64_t M, int D, float* out, void* stream);
+
 /* mean over the nodes of each graph: x (B*N, C) -> out (B, C)   (graph_encoder.py:211) */
 int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream);
 

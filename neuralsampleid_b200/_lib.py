@@ -53,6 +53,9 @@ SIGNATURES = {
     "grafp_split_tf32": [_P, _L, _P, _P],
     "grafp_split_bf16": [_P, _L, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
+    "grafp_topk_rows_fwd": [_P, _L, _I, _L, _L, _I, _I, _P, _P, _P],
+    "grafp_topk_merge_fwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "grafp_row_sumsq": [_P, _L, _I, _P, _P],
     "grafp_nchw_to_nodes_add": [_P, _P, _P, _I, _I, _I, _P],
     "grafp_mha_pool_fwd": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _P, _L, _P],
     "grafp_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P],

@@ -1,0 +1,123 @@
+"""Fingerprint database: the reference's on-disk layout and an exact GPU search.
+
+Layout (test_fp.py:158-171, eval.py:154-196): ``{name}.mm`` float32 memmap (n, d), ``{name}_shape.npy``,
+``{name}_lookup.json``.  Search: the reference builds a FAISS index over the memmap and calls
+``index.search(q, k_probe)`` (eval.py:37-151, 306); ``FlatL2Index`` reproduces the exact variant
+(index type 'l2' = ``faiss.IndexFlatL2``: squared L2 distances ascending, int64 ids) on the GPU:
+
+    Y[q, j] = |d_j|^2 - 2 <q, d_j>      one tcgen05 GEMM per database chunk (database rows = weight operand,
+                                        |d|^2 = per-column shift, a1 = -2 q), fp32-parity bf16x3 engine
+    k smallest of every row             grafp_topk_rows_fwd (warp per (query, column split), threshold scan)
+    merge chunks / splits, + |q|^2      grafp_topk_merge_fwd
+
+FAISS is not in this image: the parity oracle is the exact float64 search (oracle/flat_l2.py)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import GrafpError, check
+from ._prep import make_linear
+
+
+def save_fingerprints(out_dir: str, name: str, emb: np.ndarray, lookup=None) -> None:
+    """Writes (n, d) float32 fingerprints in the reference's layout (test_fp.py:158-171)."""
+    os.makedirs(out_dir, exist_ok=True)
+    emb = np.ascontiguousarray(emb, dtype=np.float32)
+    mm = np.memmap(os.path.join(out_dir, name + ".mm"), dtype="float32", mode="w+", shape=emb.shape)
+    mm[:] = emb
+    mm.flush()
+    np.save(os.path.join(out_dir, name + "_shape.npy"), np.array(emb.shape))
+    if lookup is not None:
+        with open(os.path.join(out_dir, name + "_lookup.json"), "w") as f:
+            json.dump(lookup, f)
+
+
+def load_fingerprints(source_dir: str, name: str) -> Tuple[np.ndarray, np.ndarray]:
+    """load_memmap_data (eval.py:154-196): (memmap (n, d) float32 with NaN -> 0, shape)."""
+    shape = np.load(os.path.join(source_dir, name + "_shape.npy"))
+    data = np.memmap(os.path.join(source_dir, name + ".mm"), dtype="float32", mode="r+",
+                     shape=(int(shape[0]), int(shape[1])))
+    data[np.isnan(data)] = 0.0
+    return data, shape
+
+
+class FlatL2Index:
+    """Exact squared-L2 index with the ``faiss.IndexFlatL2`` calling convention used by eval.py:
+    ``add(x)``, ``search(q, k) -> (D, I)`` (float32 (nq, k) ascending, int64 (nq, k); -1 / inf when k > ntotal)."""
+
+    CHUNK = 65536          # database rows per GEMM (Y chunk = nq x 65536 fp32)
+    QBLOCK = 2048          # queries per pass
+
+    def __init__(self, d: int, device="cuda:0"):
+        self.d = int(d)
+        self.device = torch.device(device)
+        self.ntotal = 0
+        self._chunks = []          # (prepared Linear over the chunk rows padded to 32, valid rows, first id)
+
+    def add(self, x) -> None:
+        x = torch.as_tensor(np.asarray(x, dtype=np.float32) if not torch.is_tensor(x) else x)
+        if x.dim() != 2 or x.shape[1] != self.d:
+            raise ValueError("expected (n, %d) vectors" % self.d)
+        x = x.to(self.device, torch.float32).contiguous()
+        lib = _lib.load()
+        for c0 in range(0, x.shape[0], self.CHUNK):
+            rows = x[c0:c0 + self.CHUNK]
+            n = rows.shape[0]
+            npad = (n + 31) // 32 * 32                                 # tcgen05 tiles need n % 32 == 0
+            w = torch.zeros((npad, self.d), device=self.device, dtype=torch.float32)
+            w[:n] = rows
+            norms = torch.full((npad,), float("inf"), device=self.device, dtype=torch.float32)   # padding never wins
+            with torch.cuda.device(self.device):
+                check(lib.grafp_row_sumsq(C.c_void_p(w.data_ptr()), n, self.d, C.c_void_p(norms.data_ptr()),
+                                          ops._stream(w)), "row_sumsq")
+            self._chunks.append((make_linear(w, None, norms), n, self.ntotal))
+            self.ntotal += n
+
+    def search(self, q, k: int, engine: Optional[int] = None):
+        if not 1 <= k <= 32:
+            raise GrafpError("FlatL2Index.search: 1 <= k <= 32")
+        as_numpy = not torch.is_tensor(q)
+        q = torch.as_tensor(np.asarray(q, dtype=np.float32)) if as_numpy else q
+        q = q.to(self.device, torch.float32).contiguous()
+        nq = q.shape[0]
+        D = torch.full((nq, k), float("inf"), device=self.device, dtype=torch.float32)
+        I = torch.full((nq, k), -1, device=self.device, dtype=torch.int64)
+        lib = _lib.load()
+        P = C.c_void_p
+        for q0 in range(0, nq, self.QBLOCK):
+            qb = q[q0:q0 + self.QBLOCK]
+            nb = qb.shape[0]
+            if nb == 0 or not self._chunks:
+                continue
+            qn = torch.empty((nb,), device=self.device, dtype=torch.float32)
+            q2 = (qb * -2.0).contiguous()                               # exact scaling
+            splits = max(1, min(16, (148 * 8) // max(nb, 1)))           # enough warps to fill the GPU for few queries
+            parts = len(self._chunks) * splits
+            pv = torch.empty((nb, parts, k), device=self.device, dtype=torch.float32)
+            pi = torch.empty((nb, parts, k), device=self.device, dtype=torch.int64)
+            with torch.cuda.device(self.device):
+                st = ops._stream(qb)
+                check(lib.grafp_row_sumsq(P(qb.data_ptr()), nb, self.d, P(qn.data_ptr()), st), "row_sumsq")
+                for ci, (lin, n, first) in enumerate(self._chunks):
+                    y = ops.linear(q2, lin, engine=engine)              # (nb, npad) = |d|^2 - 2 q.d  (inf in the padding)
+                    sl_v, sl_i = pv[:, ci * splits:(ci + 1) * splits], pi[:, ci * splits:(ci + 1) * splits]
+                    # the partial buffers are (nb, parts, k): write this chunk's `splits` lists through a
+                    # temporary contiguous block, then place them
+                    tv = torch.empty((nb, splits, k), device=self.device, dtype=torch.float32)
+                    ti = torch.empty((nb, splits, k), device=self.device, dtype=torch.int64)
+                    check(lib.grafp_topk_rows_fwd(P(y.data_ptr()), y.stride(0), nb, y.shape[1], first, k, splits,
+                                                  P(tv.data_ptr()), P(ti.data_ptr()), st), "topk_rows")
+                    sl_v.copy_(tv)
+                    sl_i.copy_(ti)
+                check(lib.grafp_topk_merge_fwd(P(pv.data_ptr()), P(pi.data_ptr()), nb, parts, k, P(qn.data_ptr()),
+                                               P(D[q0:q0 + nb].data_ptr()), P(I[q0:q0 + nb].data_ptr()), st), "topk_merge")
+        if as_numpy:
+            return D.cpu().numpy(), I.cpu().numpy()
+        return D, I

@@ -560,3 +560,61 @@ def test_ntxent_sharded_rows_equal_global():
     d0 = ops.ntxent_bwd(z, lse, 0.05, one, 0, 20)
     d1 = ops.ntxent_bwd(z, lse, 0.05, one, 20, 2 * B - 20)
     assert torch.equal(torch.cat([d0, d1]), dz)
+
+
+# ------------------------------------------------------------------------------------------
+# exact fingerprint search
+# ------------------------------------------------------------------------------------------
+def _search_check(index, db, q, k, tol=2e-4):
+    from oracle.flat_l2 import flat_l2_search
+    D, I = index.search(q, k)
+    Dw, Iw = flat_l2_search(db, q, k)
+    assert D.shape == (q.shape[0], k) and I.shape == (q.shape[0], k) and I.dtype == np.int64
+    fin = np.isfinite(Dw)
+    assert np.array_equal(np.isfinite(D), fin) and bool((I[~fin] == -1).all())
+    assert np.allclose(D[fin], Dw[fin], rtol=0, atol=tol)
+    assert bool((np.diff(D, axis=1)[fin[:, 1:]] >= 0).all())                       # ascending
+    # ids agree except where the oracle's own distances are within the engine's error of each other
+    bad = (I != Iw) & fin
+    for r, c in zip(*np.nonzero(bad)):
+        alt = np.abs(Dw[r] - Dw[r, c]) < 2 * tol
+        assert I[r, c] in Iw[r][alt] or abs(float(D[r, c]) - float(Dw[r, min(c + 1, k - 1)])) < 2 * tol, (r, c)
+    return D, I
+
+
+def test_flat_l2_index_matches_exact_search():
+    from neuralsampleid_b200.db import FlatL2Index
+    rng = np.random.Generator(np.random.PCG64(11))
+    n, d, k = 150000, 128, 20                                  # three database chunks, the last one ragged
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    index = FlatL2Index(d, DEV)
+    index.add(db[:70000])
+    index.add(db[70000:])
+    assert index.ntotal == n
+    qi = rng.integers(0, n, size=300)
+    q = db[qi] + 0.05 * rng.standard_normal((300, d)).astype(np.float32)            # distorted copies of items
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    D, I = _search_check(index, db, q, k)
+    assert float((I[:, 0] == qi).mean()) > 0.99                                      # the source item ranks first
+    _search_check(index, db, q[:3], 5)                                              # few queries: 16 column splits
+    _search_check(index, db, (0.3 * rng.standard_normal((40, d))).astype(np.float32), 32, tol=1e-3)   # un-normalised, k = 32
+
+
+def test_flat_l2_index_small_and_duplicates():
+    from neuralsampleid_b200.db import FlatL2Index
+    rng = np.random.Generator(np.random.PCG64(12))
+    db = rng.standard_normal((7, 128)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    index = FlatL2Index(128, DEV)
+    index.add(db)
+    D, I = _search_check(index, db, db[:4], 10)                 # k > ntotal: -1 / inf padding
+    assert bool((I[:, 7:] == -1).all()) and bool(np.isinf(D[:, 7:]).all())
+    assert bool((I[:, 0] == np.arange(4)).all()) and float(np.abs(D[:, 0]).max()) < 1e-4
+    dup = np.repeat(db[:1], 50, axis=0)                          # exact duplicates: ties -> lower index first
+    index2 = FlatL2Index(128, DEV)
+    index2.add(np.concatenate([dup, db], axis=0))
+    D2, I2 = index2.search(db[:1], 8)
+    assert sorted(I2[0].tolist()) == list(range(8)) or bool((I2[0] < 51).all())
+    assert float(np.abs(D2).max()) < 1e-4
+    assert FlatL2Index(128, DEV).search(db[:2], 3)[1].tolist() == [[-1] * 3] * 2   # empty index

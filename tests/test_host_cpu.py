@@ -211,3 +211,22 @@ def test_shard_range_partitions_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_fingerprint_db_layout_roundtrip(tmp_path):
+    """The reference's on-disk fingerprint layout (test_fp.py:158-171 / eval.py:154-196) and the exact-search
+    oracle's conventions."""
+    import numpy as np
+    from neuralsampleid_b200.db import load_fingerprints, save_fingerprints
+    from oracle.flat_l2 import flat_l2_search
+    rng = np.random.Generator(np.random.PCG64(3))
+    emb = rng.standard_normal((37, 128)).astype(np.float32)
+    emb[5, 7] = np.nan
+    save_fingerprints(str(tmp_path), "db", emb, lookup=["a.wav"] * 37)
+    assert sorted(os.listdir(tmp_path)) == ["db.mm", "db_lookup.json", "db_shape.npy"]
+    data, shape = load_fingerprints(str(tmp_path), "db")
+    assert tuple(shape) == (37, 128) and data.dtype == np.float32 and data[5, 7] == 0.0     # NaN -> 0 (eval.py:192)
+    ok = ~np.isnan(emb)
+    assert np.array_equal(np.asarray(data)[ok], emb[ok])
+    D, I = flat_l2_search(np.asarray(data), np.asarray(data[:3]), 40)
+    assert I[:, 0].tolist() == [0, 1, 2] and (I[:, 37:] == -1).all() and np.isinf(D[:, 37:]).all()
