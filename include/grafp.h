@@ -214,6 +214,24 @@ int grafp_topk_merge_fwd(const float* part_val, const int64_t* part_idx, int row
                          const float* row_add, float* out_val, int64_t* out_idx, void* stream);
 int grafp_row_sumsq(const float* x, int64_t M, int D, float* out, void* stream);
 
+/* ---- log-mel front end ----------------------------------------------------
+ * modules/transformations.py:27-34: torchaudio MelSpectrogram(n_fft, win_length, hop_length, n_mels; power 2,
+ * centred, reflect padding, periodic Hann, HTK mel scale, no filterbank norm) + AmplitudeToDB(power); :96-104: the
+ * (T, n_mels) spectrogram cut into n_frames-long segments every `step` frames.  The DFT and the mel projection are
+ * two grafp_gemm_fwd calls (frames x [cos | -sin] basis, power x filterbank); these are the stages around them:
+ *   grafp_frame_window_fwd    out[t, n] = win[n] * wave[reflect(t*hop + n - n_fft/2)], T frames  -> (T, n_fft)
+ *   grafp_power_spectrum_fwd  p[t, k] = z[t, k]^2 + z[t, im_offset + k]^2 (k < bins), zero up to ldp
+ *   grafp_amplitude_to_db_fwd out = multiplier * log10(max(x, amin)) - db_offset
+ *   grafp_unfold_segments_fwd out[s, m, f] = db[(s*step + f) * ldm + m]                         -> (S, n_mels, n_frames) */
+int grafp_frame_window_fwd(const float* wave, int64_t L, const float* win, int n_fft, int hop, int64_t T,
+                           float* out, void* stream);
+int grafp_power_spectrum_fwd(const float* z, int64_t ldz, int64_t T, int bins, int im_offset, float* p, int64_t ldp,
+                             void* stream);
+int grafp_amplitude_to_db_fwd(const float* x, int64_t count, float multiplier, float amin, float db_offset, float* out,
+                              void* stream);
+int grafp_unfold_segments_fwd(const float* db, int64_t ldm, int64_t T, int n_mels, int n_frames, int step, int64_t S,
+                              float* out, void* stream);
+
 /* mean over the nodes of each graph: x (B*N, C) -> out (B, C)   (graph_encoder.py:211) */
 int grafp_node_mean(const float* x, int B, int N, int C, float* out, void* stream);
 

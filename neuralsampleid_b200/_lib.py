@@ -53,6 +53,10 @@ SIGNATURES = {
     "grafp_split_tf32": [_P, _L, _P, _P],
     "grafp_split_bf16": [_P, _L, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
+    "grafp_frame_window_fwd": [_P, _L, _P, _I, _I, _L, _P, _P],
+    "grafp_power_spectrum_fwd": [_P, _L, _L, _I, _I, _P, _L, _P],
+    "grafp_amplitude_to_db_fwd": [_P, _L, _F, _F, _F, _P, _P],
+    "grafp_unfold_segments_fwd": [_P, _L, _L, _I, _I, _I, _L, _P, _P],
     "grafp_topk_rows_fwd": [_P, _L, _I, _L, _L, _I, _I, _P, _P, _P],
     "grafp_topk_merge_fwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "grafp_row_sumsq": [_P, _L, _I, _P, _P],

@@ -178,3 +178,13 @@ def reranker_inputs(B: int, N: int, seed: int, in_dim: int = 512):
     x_j = x_i + 0.5 * synth_normal((B, in_dim, N), seed + 1)
     x_j[B // 2:] = synth_normal((B - B // 2, in_dim, N), seed + 2)
     return x_i, x_j
+
+
+def synth_wave(n_samples: int, seed: int) -> torch.Tensor:
+    """Portable mono test waveform (exactly reproducible everywhere: integer noise stream + integer-pattern square
+    waves, no transcendental functions): broadband noise, a 444 Hz and a 2 kHz square tone with a slow gate."""
+    n = torch.arange(n_samples)
+    sq1 = (((n // 18) % 2) * 2 - 1).float()              # 16000 / 36 = 444.4 Hz
+    sq2 = (((n // 4) % 2) * 2 - 1).float()               # 2 kHz
+    gate = ((n // 4096) % 3 != 1).float()
+    return 0.3 * synth_normal((n_samples,), seed) + 0.4 * sq1 * gate + 0.1 * sq2

@@ -108,6 +108,20 @@ def capture_reranker(B, N, seed):
     return {"y": y.numpy(), "B": np.int64(B), "N": np.int64(N), "seed": np.int64(seed)}
 
 
+def capture_logmel(n_samples, seed):
+    """The reference's front end exactly as modules/transformations.py:27-34 builds it (torchaudio transforms with the
+    grafp.yaml parameters) and its eval-branch segmentation (:96-104)."""
+    from torchaudio.transforms import AmplitudeToDB, MelSpectrogram
+    logmelspec = torch.nn.Sequential(MelSpectrogram(sample_rate=16000, win_length=1024, hop_length=512, n_fft=1024,
+                                                    n_mels=64), AmplitudeToDB())
+    wave = synth.synth_wave(n_samples, seed)
+    with torch.no_grad():
+        X = logmelspec(wave)                                            # (n_mels, T)
+        seg = X.transpose(1, 0).unfold(0, size=128, step=int(128 * (1 - 0.875)))
+    return {"db": X.numpy(), "n_segments": np.int64(seg.shape[0]), "seg_last": seg[-1].numpy(),
+            "n_samples": np.int64(n_samples), "seed": np.int64(seed)}
+
+
 def capture_ntxent(ref, B, seed):
     z_i = torch.nn.functional.normalize(synth.synth_normal((B, 128), seed), dim=1)
     z_j = torch.nn.functional.normalize(z_i + 0.3 * synth.synth_normal((B, 128), seed + 1), dim=1)
@@ -181,6 +195,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, "graphconv_%s_%s.npz" % (conv, act)),
                             **capture_graphconv(ref, conv, act, 4, 2, 64, 128, 64, 3, 51))
     np.savez_compressed(os.path.join(HERE, "reranker_b16_n32.npz"), **capture_reranker(16, 32, 61))
+    np.savez_compressed(os.path.join(HERE, "logmel_5s.npz"), **capture_logmel(81920, 71))
     np.savez_compressed(os.path.join(HERE, "ntxent_b16.npz"), **capture_ntxent(ref, 16, 41))
     np.savez_compressed(os.path.join(HERE, "simclr_eval_b4.npz"), **capture_simclr(ref, 3, 4, False))
     np.savez_compressed(os.path.join(HERE, "simclr_train_b8.npz"), **capture_simclr(ref, 5, 8, True))

@@ -261,6 +261,43 @@ def test_reranker_matches_golden_and_oracle(golden_dir):
         m.train()(x_i.to(DEV), x_j.to(DEV))
 
 
+def test_logmel_front_end_matches_oracle_and_golden(golden_dir):
+    """waveform -> dB log-mel -> overlapping segments on the GPU (DFT and mel projection on the fp32
+    GEMM engine) against the oracle (torchaudio's algorithm) and the torchaudio-minted vector; then the segments go
+    straight into SimCLR (the consumer in the reference)."""
+    from neuralsampleid_b200.frontend import LogMelSpectrogram
+    from oracle import logmel
+    cfg = dict(CFG, fs=16000, win_len=1024, hop_len=512, n_fft=1024, overlap=0.875)
+    fe = LogMelSpectrogram(cfg).to(DEV)
+    g = np.load(os.path.join(golden_dir, "logmel_5s.npz"))
+    wave = synth.synth_wave(int(g["n_samples"]), int(g["seed"]))
+    X = fe(wave.to(DEV)).cpu()
+    want = torch.from_numpy(g["db"])
+    assert X.shape == want.shape
+    assert float((X - want).abs().max()) < 5e-3, float((X - want).abs().max())     # dB
+    seg = fe.segments(wave.to(DEV))
+    assert seg.shape == (int(g["n_segments"]), 64, 128)
+    assert float((seg[-1].cpu() - torch.from_numpy(g["seg_last"])).abs().max()) < 5e-3
+    want_seg = logmel.segment_spectrogram(logmel.log_mel_spectrogram(wave, 16000, 1024, 1024, 512, 64), 128, 0.875)
+    assert float((seg.cpu() - want_seg).abs().max()) < 5e-3
+    # other sizes: ragged length, a waveform shorter than one segment (reference's except branch)
+    w2 = synth.synth_wave(30011, 5)
+    got = fe(w2.to(DEV)).cpu()
+    ref2 = logmel.log_mel_spectrogram(w2, 16000, 1024, 1024, 512, 64)
+    assert got.shape == ref2.shape and float((got - ref2).abs().max()) < 5e-3
+    assert fe.segments(w2.to(DEV)).shape == (ref2.shape[1], 64)
+    # wave -> segments -> fingerprints through the drop-in SimCLR
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    from neuralsampleid_b200.simclr.simclr import SimCLR
+    model = SimCLR(CFG, encoder=GraphEncoder(cfg=CFG, in_channels=CFG["n_filters"], k=3))
+    model.load_state_dict(synth.synth_state(synth.simclr_state_spec(CFG, "t"), 1236))
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        _, _, z, _ = model(seg, seg)
+    assert z.shape == (seg.shape[0], 128) and bool(torch.isfinite(z).all())
+    assert float((z.norm(dim=1) - 1).abs().max()) < 1e-5
+
+
 def test_grapher_module_api_matches_oracle():
     from neuralsampleid_b200.encoder.gcn_lib.torch_vertex import Grapher
     from neuralsampleid_b200.encoder.gcn_lib.torch_nn import batched_index_select

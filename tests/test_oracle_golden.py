@@ -159,6 +159,28 @@ def test_oracle_reranker_matches_golden(golden_dir):
     assert y.shape == (16, 1) and torch.allclose(y, torch.from_numpy(g["y"]), rtol=1e-5, atol=1e-6)
 
 
+def test_oracle_logmel_matches_golden_and_torchaudio(golden_dir):
+    """Log-mel front end (modules/transformations.py:27-34, 96-104): the oracle against the vector minted with the
+    torchaudio transforms the reference instantiates, and against the installed torchaudio when it is importable."""
+    from oracle import logmel
+    g = np.load(os.path.join(golden_dir, "logmel_5s.npz"))
+    wave = synth.synth_wave(int(g["n_samples"]), int(g["seed"]))
+    X = logmel.log_mel_spectrogram(wave, 16000, 1024, 1024, 512, 64)
+    assert X.shape == g["db"].shape
+    assert float((X - torch.from_numpy(g["db"])).abs().max()) < 1e-3          # dB; FFT back ends differ in the last bits
+    seg = logmel.segment_spectrogram(X, 128, 0.875)
+    assert seg.shape == (int(g["n_segments"]), 64, 128)
+    assert float((seg[-1] - torch.from_numpy(g["seg_last"])).abs().max()) < 1e-3
+    assert logmel.segment_spectrogram(X[:, :100], 128, 0.875).shape == (100, 64)     # too short: reference's except branch
+    try:
+        from torchaudio.transforms import AmplitudeToDB, MelSpectrogram
+    except Exception:
+        return
+    ref = torch.nn.Sequential(MelSpectrogram(sample_rate=16000, win_length=1024, hop_length=512, n_fft=1024, n_mels=64),
+                              AmplitudeToDB())
+    assert float((ref(wave) - X).abs().max()) < 1e-4
+
+
 needs_ref = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
 
 
