@@ -382,7 +382,7 @@ def run_native(args):
     value = seg_per_step * args.steps / (ms_total * 1e-3)
     e2e_value = seg_per_step * args.steps / (ms_e2e * 1e-3)
     pk = peaks()
-    traffic = ncu_traffic(Bl_for_traffic := (hi - lo))
+    traffic = ncu_traffic(hi - lo)
 
     # dominant kernel class (by C-ABI entry point) and its roofline
     by_entry = {}

@@ -41,7 +41,7 @@ class MRConv2d(nn.Module):
         return ops.nodes_to_nchw(out, B, N).unsqueeze(-1)
 
 
-def _concat_halves(conv_seq, tag_cache, act_mod):
+def _concat_halves(conv_seq, tag_cache):
     """Prepared operands of a BasicConv layer whose input is a PLAIN channel concat [a | b] (EdgeConv2d,
     GraphSAGE.nn2): with groups=4 the first two groups read only `a`, the last two only `b`, so the layer
     is two independent 2-group GEMMs writing the two column halves of the output.
@@ -89,11 +89,11 @@ class EdgeConv2d(_NodeGraphConv):
         self._cache = {}
 
     def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int, out_split: bool = False):
-        (lin_a, lin_b), act, slope = _concat_halves(self.nn, self._cache, None)
+        (lin_a, lin_b), act, slope = _concat_halves(self.nn, self._cache)
         h = lin_a.w.shape[0]
         out = torch.empty((x.shape[0], 2 * h), device=x.device, dtype=torch.float32)
         ops.linear(x, lin_a, act, slope, out=out[:, :h])                       # groups 0-1: functions of x_i only
-        raw = Linear_raw(lin_b)
+        raw = _without_epilogue(lin_b)
         p = ops.linear(x, raw)                                                 # P = W x (no bias / BN / act)
         ops.nbr_reduce(p, nn_idx, B, N, ops.NBR_EDGE_MAX, lin_b.scale, lin_b.shift, act, slope, out=out[:, h:])
         return out
@@ -112,7 +112,7 @@ class GraphSAGE(_NodeGraphConv):
     def forward_nodes(self, x: torch.Tensor, nn_idx: torch.Tensor, B: int, N: int, out_split: bool = False):
         q = self.nn1.forward_nodes(x)
         xj = ops.nbr_reduce(q, nn_idx, B, N, ops.NBR_MAX)
-        (lin_a, lin_b), act, slope = _concat_halves(self.nn2, self._cache, None)
+        (lin_a, lin_b), act, slope = _concat_halves(self.nn2, self._cache)
         h = lin_a.w.shape[0]
         out = torch.empty((x.shape[0], 2 * h), device=x.device, dtype=torch.float32)
         ops.linear(x, lin_a, act, slope, out=out[:, :h])
@@ -133,7 +133,7 @@ class GINConv2d(_NodeGraphConv):
         return self.nn.forward_nodes(h)
 
 
-def Linear_raw(lin):
+def _without_epilogue(lin):
     """The same prepared weights without the epilogue (scale / shift dropped)."""
     from ..._prep import Linear
     return Linear(lin.w, None, None, lin.groups, lin.w_split, lin.w_split_bf16)

@@ -222,7 +222,7 @@ def fused_mr_ok(lin, c: int) -> bool:
     # 1.3 ms/step of mr_aggregate it removes; a register-blocked variant that batches the loads spills.
     if not os.environ.get("GRAFP_FUSED_MR"):
         return False
-    return split_ok(lin, 2 * c) and (c // lin.groups) % 32 == 0 if lin.groups > 0 else False
+    return lin.groups > 0 and split_ok(lin, 2 * c) and (c // lin.groups) % 32 == 0
 
 
 def linear(a1, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
