@@ -152,7 +152,8 @@ typedef struct {
    * consuming GEMM needs no in-kernel conversion stage.
    * With GRAFP_ENGINE_TC_BF16 (one MMA pass) the format is the hi plane alone: a plain bf16 (M, C) tensor.
    *   y_split   when non-NULL the output is written in this form (row stride ldys elements,
-   *             plane stride m*ldys) INSTEAD of y (y may then be NULL)
+   *             plane stride m*ldys); y may then be NULL (split only) or non-NULL (both forms are written:
+   *             a tensor that is a residual / kNN input AND the next GEMM's operand)
    *   a1_split  when non-NULL the first A source is read in this form (row stride lda1s elements,
    *             plane stride m*lda1s) instead of a1 (a1 may then be NULL); needs k2 == 0, no tap3 */
   void* y_split; int64_t ldys;

@@ -74,11 +74,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                                                            // were 40 % of all issued instructions in the kNN)
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the box.
+// Bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the box.  The bound is
+// wall-clock (4 s on %globaltimer, polled only on the slow path): with the suspend-time hint one try_wait may
+// sleep for milliseconds, so a spin count no longer bounds anything.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { printf("grafp: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    ++spins;
+    if (spins == 64u) {
+      t0 = global_timer_ns();
+    } else if (spins > 64u && (spins & 63u) == 0u && global_timer_ns() - t0 > 4000000000ull) {
+      printf("grafp: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
   }
 }
 // 1-D bulk async copy global -> shared, completion on an mbarrier (TMA engine, UBLKCP).

@@ -54,6 +54,7 @@ struct TcParams {
   int act; float act_param;
   uint32_t tmem_cols;
   int y_split;         // 0: fp32 output; 2: bf16 [hi ; lo] planes; 1: bf16 hi plane only (1-pass engine)
+  int y_both;          // with y_split: ALSO write the fp32 output (tmY fp32 map + tmYs split map, two staging tiles)
   int raw;             // depth of the fp32 A ring (bf16 engines with an fp32 A operand)
   // fused max-relative aggregation: the second A source is not read but computed by the transform warps,
   // a2[m, c] = max_t (a1[graph(m) + idx[m, t], c] - a1[m, c])  (bf16 engines, fp32 A)
@@ -100,6 +101,7 @@ template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
+               const __grid_constant__ CUtensorMap tmYs,
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
@@ -122,12 +124,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const uint32_t b_bytes = (uint32_t)p.bn * kOpRow;
   const uint32_t stage_bytes = kNP * (kAop + b_bytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* store_buf = smem;                                  // 2 x 16 KB staging tiles
+  uint8_t* store_buf = smem;                                  // 2 (4 in dual-output mode) x 16 KB staging tiles
+  const uint32_t n_store = p.y_both ? 4u : 2u;
   // tf32: operand stages [A raw = hi | A_lo (3x) | B_hi | B_lo (3x)]
   // bf16: a separate ring of p.raw fp32 A tiles (freed as soon as the transform has read them, so the
   //       HBM-latency-bound A loads run up to p.raw k-blocks ahead of the MMA), then operand stages
   //       [A_hi | A_lo (3x) | B_hi | B_lo (3x)]
-  uint8_t* raw0 = smem + 2 * TC_STORE_BYTES;
+  uint8_t* raw0 = smem + n_store * TC_STORE_BYTES;
   const int RAW = p.raw;
   uint8_t* stage0 = raw0 + ((kBf16 && !kASplit) ? RAW * TC_A_BYTES : 0);
   auto a_raw = [&](int s) { return kBf16 ? raw0 + (size_t)s * TC_A_BYTES : stage0 + (size_t)s * stage_bytes; };
@@ -150,6 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmYs);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&xf_bar[s], TC_XF_THREADS);
@@ -429,6 +433,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int r = quad * 32 + lane;              // row inside the tile
     const bool store_thread = (et == 0);
     uint8_t* sb = store_buf + half * TC_STORE_BYTES;
+    uint8_t* sb32 = store_buf + (2 + half) * TC_STORE_BYTES;   // dual-output mode: the fp32 tile beside the split tiles
     uint32_t ti = 0;
     for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
       const int nt = (int)(tile % tiles_n);
@@ -507,18 +512,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               *reinterpret_cast<uint4*>(sb + TC_STORE_BYTES / 2 + off) =
                   make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
           }
-        } else {
+        }
+        if (!p.y_split || p.y_both) {
+          uint8_t* dst = p.y_both ? sb32 : sb;
 #pragma unroll
           for (int q = 0; q < 8; ++q)                     // 128B swizzle: 16-byte chunk q -> q ^ (row & 7)
-            *reinterpret_cast<float4*>(sb + r * 128 + ((q ^ (r & 7)) << 4)) =
+            *reinterpret_cast<float4*>(dst + r * 128 + ((q ^ (r & 7)) << 4)) =
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         fence_proxy_async_smem();
         named_bar_sync(1 + half, 128);
         if (store_thread) {
           if (p.y_split) {
-            tma_store_3d(&tmY, sb, (int)(col0 + c), m0, 0);
-            if (p.y_split == 2) tma_store_3d(&tmY, sb + TC_STORE_BYTES / 2, (int)(col0 + c), m0, 1);
+            tma_store_3d(&tmYs, sb, (int)(col0 + c), m0, 0);
+            if (p.y_split == 2) tma_store_3d(&tmYs, sb + TC_STORE_BYTES / 2, (int)(col0 + c), m0, 1);
+            if (p.y_both) tma_store_2d(&tmY, sb32, (int)(col0 + c), m0);
           } else {
             tma_store_2d(&tmY, sb, (int)(col0 + c), m0);
           }
@@ -667,9 +675,9 @@ int gemm_tc_supported(const grafp_gemm_args& a) {
   if ((a.ldw * 4) % 16 != 0 || a.ldw % 8 != 0) return 0;
   if (a.y_split) {
     if (a.ldys % 8 != 0 || (reinterpret_cast<uintptr_t>(a.y_split) & 15) || a.row_sumsq) return 0;
-  } else if (a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15)) {
-    return 0;
   }
+  if (a.y && (a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15))) return 0;
+  if (!a.y && !a.y_split) return 0;
   if (a.residual && (a.ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15))) return 0;
   return 1;
 }
@@ -679,7 +687,7 @@ int gemm_tc_supported(const grafp_gemm_args& a) {
 int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t st) {
   const int bn = pick_bn(a.n);
   const int n_total = a.groups * a.n;
-  CUtensorMap mA1, mA2, mW, mY;
+  CUtensorMap mA1, mA2, mW, mY, mYs;
   TcParams p;
   p.tap3_rows = 0; p.tap3_cin = 0;
   if (a.tap3_nodes > 0) {
@@ -719,11 +727,16 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   } else if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
                                      a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
     return rc;
+  const bool y_both = a.y_split && a.y;                    // dual output: fp32 and split
   if (a.y_split) {
-    if (int rc = tc_make_map_3d_bf16(&mY, a.y_split, n_total, a.m, passes == 3 ? 2 : 1, a.ldys, a.m * a.ldys, TC_BM)) return rc;
-  } else if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) {
-    return rc;
+    if (int rc = tc_make_map_3d_bf16(&mYs, a.y_split, n_total, a.m, passes == 3 ? 2 : 1, a.ldys, a.m * a.ldys, TC_BM)) return rc;
   }
+  if (a.y) {
+    if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) return rc;
+  }
+  if (!a.y) mY = mYs;
+  if (!a.y_split) mYs = mY;
+  p.y_both = y_both ? 1 : 0;
   p.y_split = a.y_split ? (passes == 3 ? 2 : 1) : 0;     // the 1-pass engine carries the hi plane only
   p.gat_idx = a.a2_gather_idx; p.gat_x = a.a1; p.gat_ld = a.lda1; p.gat_n = a.a2_gather_nodes; p.gat_k = a.a2_gather_k;
   const bool asplit = a.a1_split != nullptr;
@@ -740,7 +753,8 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   // Shared-memory plan.  The fp32 A ring covers the HBM latency (a memory-bound shape needs ~75 KB in flight
   // per SM to stream at the HBM rate), the operand stages only the transform -> MMA hand-off: narrow tiles
   // (small stages) get a deep ring and three operand stages, 256-wide tiles keep three ring slots.
-  const size_t budget = 220 * 1024 - 1024 - 2 * TC_STORE_BYTES;      // 227 KB minus ~6 KB static
+  const size_t n_store = y_both ? 4 : 2;
+  const size_t budget = 220 * 1024 - 1024 - n_store * TC_STORE_BYTES;      // 227 KB minus ~6 KB static
   int raw = 0, stages;
   if (bf16 && !asplit) {
     static int raw_env = -1;
@@ -753,7 +767,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
     if (raw_env >= 2 && raw_env <= TC_RAW_MAX) raw = raw_env;
   }
   p.raw = raw > 0 ? raw : 1;
-  const size_t fixed_bytes = 2 * TC_STORE_BYTES + (size_t)raw * TC_A_BYTES;
+  const size_t fixed_bytes = n_store * TC_STORE_BYTES + (size_t)raw * TC_A_BYTES;
   const int nkb = (a.k1 + a.k2) / TC_BK;
   stages = (int)((220 * 1024 - fixed_bytes - 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -765,7 +779,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   int grid = sm_count() / cluster;
   if (units < grid) grid = (int)units;
   grid *= cluster;
-  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   KernFn kern;
   if (a.a2_gather_idx)
     kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, false, true> : gemm_tc_kernel<3, 1, true, false, true>)
@@ -792,7 +806,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA1, mA2, mW, mY, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA1, mA2, mW, mY, mYs, p);
   if (le != cudaSuccess) return fail("gemm_tc launch: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc");
 }

@@ -222,7 +222,10 @@ class Grapher(nn.Module):
         return hit[1]
 
     def forward_nodes(self, x: torch.Tensor, B: int, N: int, nn_idx: torch.Tensor = None,
-                      taps: dict = None) -> torch.Tensor:
+                      taps: dict = None, want_split: bool = False):
+        """``want_split``: also return the output as an ops.SplitAct (written by the same fc2 epilogue) for a
+        consumer GEMM -- the following FFN's fc1 -- when fc2 runs on a bf16 tensor-core engine: returns
+        (out, SplitAct or None)."""
         if self.training:
             raise RuntimeError("Grapher.forward_nodes is the eval path; training goes through "
                                "neuralsampleid_b200.autograd")
@@ -237,6 +240,10 @@ class Grapher(nn.Module):
         fc2 = self._folded("fc2")
         # the MRConv output feeds only fc2: split-bf16 on the bf16 tensor-core engines (ops.SplitAct)
         g = self.graph_conv.forward_nodes(y, B, N, nn_idx, out_split=ops.split_ok(fc2, 2 * self.channels))
+        if want_split:
+            if isinstance(g, ops.SplitAct) and ops.split_ok(fc2, 2 * self.channels):
+                return ops.linear(g, fc2, residual=x, out_split="both")
+            return ops.linear(g, fc2, residual=x), None
         return ops.linear(g, fc2, residual=x)
 
     def forward(self, x):

@@ -98,7 +98,18 @@ class FFN(_Cached):
         return self._memo(name, (conv.weight, conv.bias) + _bn_tensors(bn),
                           lambda: make_linear(*fold_conv_bn(conv.weight, conv.bias, bn)))
 
-    def forward_nodes(self, x: torch.Tensor) -> torch.Tensor:
+    def wants_split_input(self, channels: int) -> bool:
+        """True when fc1 gains from a pre-split A operand written by the producer (measured on B200: the C >= 256
+        stages, whose fc1 is MMA / shared-memory bound: 494 -> 433 us and 826 -> 673 us per layer; at C <= 128 the
+        extra 268 MB write of the split copy costs more than the conversion stage it removes)."""
+        import os
+        if os.environ.get("GRAFP_NO_DUAL_OUT"):
+            return False
+        return channels >= 256 and ops.split_ok(self._folded("fc1"), channels) and _ffn_slab_rows(1) <= 0
+
+    def forward_nodes(self, x: torch.Tensor, x_split=None) -> torch.Tensor:
+        """``x_split``: the same tensor as an ops.SplitAct (from the producing GEMM's dual-output epilogue); fc1 then
+        reads it instead of converting x in shared memory.  The shortcut always adds the fp32 x."""
         if self.training:
             raise RuntimeError("FFN.forward_nodes is the eval path; training goes through "
                                "neuralsampleid_b200.autograd")
@@ -109,7 +120,8 @@ class FFN(_Cached):
             # the hidden tensor feeds only fc2: on the bf16 tensor-core engines it travels as the
             # split-bf16 operand pair (same bytes, bit-identical operands, no conversion stage in fc2)
             split = ops.split_ok(fc1, x.shape[1]) and ops.split_ok(fc2, hid)
-            h = ops.linear(x, fc1, self.act.name, self.act.neg_slope, out_split=split)
+            a = x_split if (x_split is not None and split) else x
+            h = ops.linear(a, fc1, self.act.name, self.act.neg_slope, out_split=split)
             return ops.linear(h, fc2, residual=x)
         # Optional (off by default, see _ffn_slab_rows): row slabs sized so the hidden activations of
         # one slab stay L2-resident between the two GEMMs.
@@ -223,10 +235,13 @@ class GraphEncoder(_Cached):
             fi = forced_idx[blk] if forced_idx is not None else None
             if t is not None:
                 t["in"] = h
-            h = entry[0].forward_nodes(h, B, N, fi, t)
+            if entry[1].wants_split_input(h.shape[1]):
+                h, h_split = entry[0].forward_nodes(h, B, N, fi, t, want_split=True)
+            else:
+                h, h_split = entry[0].forward_nodes(h, B, N, fi, t), None
             if t is not None:
                 t["grapher"] = h
-            h = entry[1].forward_nodes(h)
+            h = entry[1].forward_nodes(h, h_split)
             if t is not None:
                 t["out"] = h
                 taps.append(t)

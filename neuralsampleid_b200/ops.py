@@ -245,8 +245,9 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     those neighbour lists, computed inside the kernel (fused MRConv2d; bf16 tensor-core engines only).
 
     a1: (M, groups*k1) (or the (2M', Cin) node matrix in tap3 mode), a2: (M, groups*k2) or None,
-    w: (groups*n, k1+k2).  ``a1`` may be a SplitAct; ``out_split`` returns one (bf16 tensor-core engines
-    only: the library refuses anything else)."""
+    w: (groups*n, k1+k2).  ``a1`` may be a SplitAct; ``out_split=True`` returns one, ``out_split="both"`` returns
+    (fp32 tensor, SplitAct) written by the same epilogue (bf16 tensor-core engines only: the library refuses
+    anything else)."""
     a1s = None
     if isinstance(a1, SplitAct):
         a1s = _chk(a1.t, torch.bfloat16, "a1 (split)")
@@ -282,10 +283,14 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     planes = 1 if split_engine == _lib.ENGINE_TC_BF16 else 2
     if a1s is not None and a1s.shape[0] < planes:
         raise GrafpError("gemm: a hi-plane-only SplitAct can only feed the 1-pass bf16 engine")
+    both = out_split == "both"                       # fp32 output AND its split copy, from one epilogue
+    out32 = None
     if out_split:
         if out is not None or row_sumsq is not None:
             raise GrafpError("gemm: out_split cannot be combined with out= / row_sumsq")
         out = torch.empty((planes, M, n_total), device=dev, dtype=torch.bfloat16)
+        if both:
+            out32 = torch.empty((M, n_total), device=dev, dtype=torch.float32)
     elif out is None:
         out = torch.empty((M, n_total), device=dev, dtype=torch.float32)
     elif out.shape != (M, n_total) or out.stride(1) != 1:
@@ -315,7 +320,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     else:
         args.residual, args.ldr = None, 0
     if out_split:
-        args.y, args.ldy = None, 0
+        args.y, args.ldy = (out32.data_ptr(), out32.stride(0)) if both else (None, 0)
         args.y_split, args.ldys = out.data_ptr(), out.stride(1)
     else:
         args.y, args.ldy = out.data_ptr(), out.stride(0)
@@ -333,6 +338,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
             args.engine = ov
     with torch.cuda.device(dev):
         check(_lib.load().grafp_gemm_fwd(C.byref(args), _stream(out)), "gemm_fwd")
+    if both:
+        return out32, SplitAct(out)
     return SplitAct(out) if out_split else out
 
 

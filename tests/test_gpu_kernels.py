@@ -358,6 +358,12 @@ def test_gemm_split_bf16_activations_bit_exact(M, k, hid, n, groups, engine):
     y32 = ops.linear(h32, l2, None, 0.0, res, engine=eng)
     ys = ops.linear(hs, l2, None, 0.0, res, engine=eng)
     assert torch.equal(y32, ys)
+    # dual output: one epilogue writes the fp32 tensor and its split copy (residual stream that is also the next
+    # GEMM's operand); both bit-identical to the single-output launches
+    yb32, ybs = ops.linear(hs, l2, None, 0.0, res, engine=eng, out_split="both")
+    assert torch.equal(yb32, y32)
+    yh = y32.bfloat16()
+    assert torch.equal(ybs.t[0], yh) and (planes == 1 or torch.equal(ybs.t[1], (y32 - yh.float()).bfloat16()))
 
 
 @pytest.mark.parametrize("B,N,C,k,groups", [(5, 256, 64, 3, 1), (9, 128, 128, 3, 4), (7, 64, 256, 5, 4), (11, 32, 512, 3, 4),
