@@ -195,7 +195,6 @@ def mode_chunks(args):
 def mode_search(args):
     """exact squared-L2 search of the fingerprint database (eval.py's index type 'l2')."""
     from neuralsampleid_b200.db import FlatL2Index
-    from oracle.flat_l2 import flat_l2_search              # CPU baseline leg only
     world, rank, dev = _setup()
     n, nq, k, d = args.segments, args.queries, 20, 128
     g = torch.Generator(device=dev).manual_seed(5)
@@ -210,7 +209,10 @@ def mode_search(args):
     D, I = index.search(q, k)
     t0 = time.perf_counter()
     sample = 64
-    Dw, Iw = flat_l2_search(db.cpu().numpy(), q[:sample].cpu().numpy(), k)
+    import numpy as np                                     # CPU baseline: plain numpy exact search (float64)
+    dbn, qn = db.cpu().numpy().astype(np.float64), q[:sample].cpu().numpy().astype(np.float64)
+    dist = (qn * qn).sum(1)[:, None] - 2.0 * (qn @ dbn.T) + (dbn * dbn).sum(1)[None, :]
+    Iw = np.argsort(dist, axis=1, kind="stable")[:, :k]
     cpu_s = time.perf_counter() - t0
     agree = float((I[:sample].cpu().numpy() == Iw).mean())
     if rank == 0:
