@@ -230,3 +230,26 @@ def test_fingerprint_db_layout_roundtrip(tmp_path):
     assert np.array_equal(np.asarray(data)[ok], emb[ok])
     D, I = flat_l2_search(np.asarray(data), np.asarray(data[:3]), 40)
     assert I[:, 0].tolist() == [0, 1, 2] and (I[:, 37:] == -1).all() and np.isinf(D[:, 37:]).all()
+
+
+def test_gemm_args_struct_layout_matches_header(tmp_path):
+    """The ctypes mirror of grafp_gemm_args must have the C struct's field offsets and size (compiled from
+    include/grafp.h with the host compiler): guards the binding against ABI drift."""
+    import ctypes as C
+    import shutil
+    from neuralsampleid_b200._lib import GemmArgs
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no host C compiler")
+    fields = [f[0] for f in GemmArgs._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grafp.h"', 'int main(void) {']
+    lines += ['  printf("%s %%zu\\n", offsetof(grafp_gemm_args, %s));' % (f, f) for f in fields]
+    lines += ['  printf("sizeof %zu\\n", sizeof(grafp_gemm_args));', '  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for f in fields:
+        assert int(out[f]) == getattr(GemmArgs, f).offset, f
+    assert int(out["sizeof"]) == C.sizeof(GemmArgs)
