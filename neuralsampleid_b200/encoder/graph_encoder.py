@@ -105,7 +105,8 @@ class FFN(_Cached):
         import os
         if os.environ.get("GRAFP_NO_DUAL_OUT"):
             return False
-        return channels >= 256 and ops.split_ok(self._folded("fc1"), channels) and _ffn_slab_rows(1) <= 0
+        min_c = int(os.environ.get("GRAFP_DUAL_MIN_C", "256"))
+        return channels >= min_c and ops.split_ok(self._folded("fc1"), channels) and _ffn_slab_rows(1) <= 0
 
     def forward_nodes(self, x: torch.Tensor, x_split=None) -> torch.Tensor:
         """``x_split``: the same tensor as an ops.SplitAct (from the producing GEMM's dual-output epilogue); fc1 then
