@@ -214,6 +214,10 @@ int grafp_topk_rows_fwd(const float* y, int64_t ldy, int rows, int64_t cols, int
 int grafp_topk_merge_fwd(const float* part_val, const int64_t* part_idx, int rows, int parts, int k,
                          const float* row_add, float* out_val, int64_t* out_idx, void* stream);
 int grafp_row_sumsq(const float* x, int64_t M, int D, float* out, void* stream);
+/* Song-level match score (eval.py:322-331): out[c] = mean_{t < len} <q[t, :], db[cand[c] + t, :]>, len = min(sl,
+ * n - cand[c]) (0 for cand[c] outside [0, n)).  q (sl, D), db (n, D) row-major, cand (nc) int64. */
+int grafp_sequence_score_fwd(const float* q, int sl, int D, const float* db, int64_t n, const int64_t* cand, int nc,
+                             float* out, void* stream);
 
 /* ---- log-mel front end ----------------------------------------------------
  * modules/transformations.py:27-34: torchaudio MelSpectrogram(n_fft, win_length, hop_length, n_mels; power 2,

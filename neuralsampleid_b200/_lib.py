@@ -60,6 +60,7 @@ SIGNATURES = {
     "grafp_topk_rows_fwd": [_P, _L, _I, _L, _L, _I, _I, _P, _P, _P],
     "grafp_topk_merge_fwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "grafp_row_sumsq": [_P, _L, _I, _P, _P],
+    "grafp_sequence_score_fwd": [_P, _I, _I, _P, _L, _P, _I, _P, _P],
     "grafp_nchw_to_nodes_add": [_P, _P, _P, _I, _I, _I, _P],
     "grafp_mha_pool_fwd": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _P, _L, _P],
     "grafp_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P],

@@ -136,6 +136,30 @@ __global__ void row_sumsq_kernel(const float* __restrict__ x, int64_t M, int D, 
   if (lane == 0) out[row] = s;
 }
 
+// Song-level match score of eval.py:322-331: for every candidate start id, the mean over the query sequence of the
+// inner products with the database rows that follow it:  out[c] = mean_{t < len} <q[t], db[cand[c] + t]>,
+// len = min(sl, n - cand[c]).  One warp per candidate (the reference does this in a Python loop per candidate).
+__global__ void __launch_bounds__(256)
+sequence_score_kernel(const float* __restrict__ q, int sl, int D, const float* __restrict__ db, int64_t n,
+                      const long long* __restrict__ cand, int nc, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= nc) return;
+  const long long cid = cand[c];
+  float acc = 0.0f;
+  int len = 0;
+  if (cid >= 0 && cid < n) {
+    len = (int)((n - cid < (long long)sl) ? (n - cid) : (long long)sl);
+    for (int t = 0; t < len; ++t) {
+      const float* qr = q + (int64_t)t * D;
+      const float* dr = db + (cid + t) * D;
+      for (int d = lane; d < D; d += 32) acc = fmaf(qr[d], dr[d], acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[c] = len > 0 ? acc / (float)len : 0.0f;
+}
+
 }  // namespace grafp
 
 using namespace grafp;
@@ -166,6 +190,16 @@ int grafp_topk_merge_fwd(const float* part_val, const int64_t* part_idx, int row
       part_val, reinterpret_cast<const long long*>(part_idx), rows, parts, k, row_add, out_val,
       reinterpret_cast<long long*>(out_idx));
   return check_launch("topk_merge");
+}
+
+int grafp_sequence_score_fwd(const float* q, int sl, int D, const float* db, int64_t n, const int64_t* cand, int nc,
+                             float* out, void* stream) {
+  GRAFP_REQUIRE(nc <= 0 || (q && db && cand && out), "sequence_score: null pointer");
+  GRAFP_REQUIRE(sl > 0 && D > 0 && n >= 0 && nc >= 0, "sequence_score: bad sizes");
+  if (nc == 0) return 0;
+  sequence_score_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, as_stream(stream)>>>(
+      q, sl, D, db, n, reinterpret_cast<const long long*>(cand), nc, out);
+  return check_launch("sequence_score");
 }
 
 int grafp_row_sumsq(const float* x, int64_t M, int D, float* out, void* stream) {

@@ -60,12 +60,16 @@ class FlatL2Index:
         self.device = torch.device(device)
         self.ntotal = 0
         self._chunks = []          # (prepared Linear over the chunk rows padded to 32, valid rows, first id)
+        self._rows = []            # the added blocks as given (device), for reconstruct / sequence scores
+        self._flat = None
 
     def add(self, x) -> None:
         x = torch.as_tensor(np.asarray(x, dtype=np.float32) if not torch.is_tensor(x) else x)
         if x.dim() != 2 or x.shape[1] != self.d:
             raise ValueError("expected (n, %d) vectors" % self.d)
         x = x.to(self.device, torch.float32).contiguous()
+        self._rows.append(x)
+        self._flat = None
         lib = _lib.load()
         for c0 in range(0, x.shape[0], self.CHUNK):
             rows = x[c0:c0 + self.CHUNK]
@@ -121,3 +125,45 @@ class FlatL2Index:
         if as_numpy:
             return D.cpu().numpy(), I.cpu().numpy()
         return D, I
+
+    def vectors(self) -> torch.Tensor:
+        """The indexed vectors as one (ntotal, d) device tensor (what eval.py keeps as ``fake_recon_index``)."""
+        if self._flat is None:
+            self._flat = (torch.cat(self._rows) if len(self._rows) != 1 else self._rows[0]) if self._rows else \
+                torch.empty((0, self.d), device=self.device, dtype=torch.float32)
+        return self._flat
+
+    def sequence_scores(self, q, cand) -> torch.Tensor:
+        """Song-level match scores of eval.py:322-331 for a query sequence q (sl, d) and candidate start ids cand
+        (nc,) int64: mean over the sequence of <q[t], db[cand + t]> (shorter at the end of the database)."""
+        q = torch.as_tensor(q).to(self.device, torch.float32).contiguous()
+        cand = torch.as_tensor(cand).to(self.device, torch.int64).contiguous()
+        db = self.vectors()
+        out = torch.empty((cand.numel(),), device=self.device, dtype=torch.float32)
+        P = C.c_void_p
+        with torch.cuda.device(self.device):
+            check(_lib.load().grafp_sequence_score_fwd(P(q.data_ptr()), q.shape[0], self.d, P(db.data_ptr()), db.shape[0],
+                                                       P(cand.data_ptr()), cand.numel(), P(out.data_ptr()),
+                                                       ops._stream(q)), "sequence_score")
+        return out
+
+
+def song_level_ranking(index: FlatL2Index, q, k_probe: int, file_of: np.ndarray, query_file: int = -1,
+                       first_valid: int = 0):
+    """eval.py:300-336 for one query sequence: segment-level top-k_probe search, every returned id is a candidate start,
+    each candidate adds its sequence score to the histogram bin of the file it belongs to (ids below ``first_valid`` --
+    the dummy database -- and the query's own file are skipped); returns (file ids sorted by score descending, scores).
+    ``file_of`` (ntotal,) int array: file index of every database row."""
+    _, I = index.search(q, k_probe)
+    I = I.cpu().numpy() if torch.is_tensor(I) else I
+    cand = I[np.where(I >= 0)].flatten()
+    keep = (cand >= first_valid) & (file_of[cand] != query_file)
+    cand = cand[keep]
+    if cand.size == 0:
+        return np.zeros((0,), dtype=np.int64), np.zeros((0,), dtype=np.float64)
+    scores = index.sequence_scores(q, cand).cpu().numpy().astype(np.float64)
+    files = file_of[cand]
+    uniq, inv = np.unique(files, return_inverse=True)
+    hist = np.bincount(inv, weights=scores, minlength=uniq.size)
+    order = np.argsort(-hist, kind="stable")
+    return uniq[order], hist[order]

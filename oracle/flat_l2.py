@@ -20,3 +20,22 @@ def flat_l2_search(db: np.ndarray, q: np.ndarray, k: int):
         order = np.concatenate([order, -np.ones((q.shape[0], pad), dtype=order.dtype)], axis=1)
         D = np.concatenate([D, np.full((q.shape[0], pad), np.inf)], axis=1)
     return D, order.astype(np.int64)
+
+
+def song_level_ranking(db: np.ndarray, q: np.ndarray, k_probe: int, file_of: np.ndarray, query_file: int = -1,
+                       first_valid: int = 0):
+    """eval.py:300-336 restated for one query sequence with integer file ids (the reference keys its histogram by the
+    lookup string): candidates = every id of the segment-level top-k_probe lists; score = np.mean(np.sum(q_match *
+    candidate_seq, axis=1)); hist[file] += score; ranking by descending score."""
+    _, I = flat_l2_search(db, q, k_probe)
+    cand = I[np.where(I >= 0)].flatten()
+    hist = {}
+    sl = q.shape[0]
+    for cid in cand:
+        if cid < first_valid or file_of[cid] == query_file:
+            continue
+        seq = db[cid:cid + sl].astype(np.float64)
+        qm = q[:seq.shape[0]].astype(np.float64)
+        hist[int(file_of[cid])] = hist.get(int(file_of[cid]), 0.0) + float(np.mean(np.sum(qm * seq, axis=1)))
+    files = sorted(hist, key=hist.get, reverse=True)
+    return np.array(files, dtype=np.int64), np.array([hist[f] for f in files])

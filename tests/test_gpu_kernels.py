@@ -625,3 +625,36 @@ def test_flat_l2_index_small_and_duplicates():
     assert sorted(I2[0].tolist()) == list(range(8)) or bool((I2[0] < 51).all())
     assert float(np.abs(D2).max()) < 1e-4
     assert FlatL2Index(128, DEV).search(db[:2], 3)[1].tolist() == [[-1] * 3] * 2   # empty index
+
+
+def test_song_level_ranking_matches_oracle():
+    """eval.py:300-336: segment-level search -> candidate sequences -> per-file score histogram."""
+    from neuralsampleid_b200.db import FlatL2Index, song_level_ranking
+    from oracle import flat_l2
+    rng = np.random.Generator(np.random.PCG64(21))
+    n_files, per, d = 40, 60, 128
+    db = rng.standard_normal((n_files * per, d)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    file_of = np.repeat(np.arange(n_files), per)
+    index = FlatL2Index(d, DEV)
+    index.add(db)
+    for start, sl in ((7 * per + 11, 9), (n_files * per - 5, 5), (3, 19)):          # incl. a sequence running off the end
+        q = db[start:start + sl] + 0.08 * rng.standard_normal((min(sl, db.shape[0] - start), d)).astype(np.float32)
+        q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+        files, scores = song_level_ranking(index, q, 20, file_of, query_file=-1, first_valid=per)   # file 0 = dummy DB
+        wf, ws = flat_l2.song_level_ranking(db, q, 20, file_of, -1, per)
+        # the winning file and its score (a k_probe-boundary near-tie between the engines can move a weak candidate in
+        # or out, never the true match)
+        assert files[0] == wf[0] and (start < per or files[0] == file_of[start])
+        assert abs(float(scores[0]) - float(ws[0])) < 1e-3
+        # the scoring kernel itself, on the oracle's own candidate list: deterministic, tight
+        _, Iw = flat_l2.flat_l2_search(db, q, 20)
+        cand = Iw[np.where(Iw >= 0)].flatten()
+        got = index.sequence_scores(q, cand).cpu().numpy()
+        want = np.array([np.mean(np.sum(q[:db[c:c + q.shape[0]].shape[0]].astype(np.float64) *
+                                        db[c:c + q.shape[0]].astype(np.float64), axis=1)) for c in cand])
+        assert np.allclose(got, want, rtol=0, atol=2e-6)
+    sc = index.sequence_scores(db[100:104], np.array([100, -1, db.shape[0] - 2, db.shape[0] + 5]))
+    assert abs(float(sc[0]) - 1.0) < 1e-5 and float(sc[1]) == 0.0 and float(sc[3]) == 0.0
+    want2 = float(np.mean(np.sum(db[100:102].astype(np.float64) * db[-2:].astype(np.float64), axis=1)))
+    assert abs(float(sc[2]) - want2) < 1e-5
