@@ -253,3 +253,48 @@ def test_gemm_args_struct_layout_matches_header(tmp_path):
     for f in fields:
         assert int(out[f]) == getattr(GemmArgs, f).offset, f
     assert int(out["sizeof"]) == C.sizeof(GemmArgs)
+
+
+# ------------------------------------------------------------------------------------------
+# the kNN epilogue's two-pass threshold selection, modelled in numpy (csrc/knn_tc.cu)
+# ------------------------------------------------------------------------------------------
+def _threshold_select_model(dist_row, kk, groups=16, list_cap=None):
+    """Pass 1: minimum of each of `groups` column groups, tau = kk-th smallest group minimum.  Pass 2: every column
+    with dist <= tau, in column order (overflow -> None = the kernel's full-scan fallback).  Final: stable insertion
+    of the candidates by (distance, earlier column first)."""
+    n = dist_row.shape[0]
+    gsz = n // groups
+    gm = dist_row.reshape(groups, gsz).min(axis=1)
+    tau = np.sort(gm)[kk - 1]
+    cand = np.nonzero(dist_row <= tau)[0]
+    if list_cap is not None and cand.size >= list_cap:
+        return None
+    order = np.argsort(dist_row[cand], kind="stable")[:kk]
+    return cand[order]
+
+
+def test_knn_threshold_selection_is_exact_property():
+    """The candidate set {dist <= tau} always contains the kk smallest columns (tau is an upper bound of the kk-th
+    smallest distance because kk different groups each hold a column <= tau), so selection over the candidates equals
+    the full stable sort -- including exact ties and duplicated columns -- whenever the list does not overflow."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 2 ** 32 - 1), st.sampled_from([128, 256]), st.integers(1, 16),
+           st.sampled_from(["normal", "quantised", "constant", "few_values"]))
+    def check(seed, n, kk, kind):
+        rng = np.random.Generator(np.random.PCG64(seed))
+        if kind == "normal":
+            d = rng.standard_normal(n).astype(np.float32)
+        elif kind == "quantised":
+            d = np.round(rng.standard_normal(n) * 4).astype(np.float32) / 4          # many exact ties
+        elif kind == "constant":
+            d = np.zeros(n, dtype=np.float32)
+        else:
+            d = rng.choice(np.array([0.0, 0.5, 2.0], dtype=np.float32), size=n)
+        want = np.argsort(d, kind="stable")[:kk]
+        got = _threshold_select_model(d, kk)
+        assert got is not None and np.array_equal(got, want)
+        capped = _threshold_select_model(d, kk, list_cap=kk + 8 if kk > 4 else 12)
+        assert capped is None or np.array_equal(capped, want)                       # overflow -> fallback, never wrong
+    check()
