@@ -298,3 +298,21 @@ def test_knn_threshold_selection_is_exact_property():
         capped = _threshold_select_model(d, kk, list_cap=kk + 8 if kk > 4 else 12)
         assert capped is None or np.array_equal(capped, want)                       # overflow -> fallback, never wrong
     check()
+
+
+def test_bench_reference_arm_and_traffic_file():
+    """bench.py contract pieces that run without a GPU: the `--impl reference` line (CPU arm) and the committed ncu
+    traffic file that feeds `roofline.traffic`."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "GraphEncoder forward segments/s"
+    assert line["unit"] == "segments/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    sys.path.insert(0, ROOT)
+    import bench
+    t = bench.ncu_traffic(4096)
+    assert t["gemm"] > 6e10 and t["knn"] > 3e9 and t["aggregate"] > 5e9 and "ncu" in t["note"]
