@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 3
+#define GRAFP_ABI_VERSION 4
 
 /* activation codes (reference: act_layer, encoder/gcn_lib/torch_nn.py:9-25; ELU for the
  * projector, simclr/simclr.py:26) */
@@ -40,15 +40,18 @@ enum { GRAFP_ACT_NONE = 0, GRAFP_ACT_RELU = 1, GRAFP_ACT_LEAKY = 2, GRAFP_ACT_GE
        GRAFP_ACT_SIGMOID = 5 /* the re-ranker's output unit (downstream.py:55); fp32 SIMT GEMM engine only */ };
 
 /* GEMM engines */
-enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 bf16x3 (else 3xTF32) where the shape and the split
-                                      weights allow, else SIMT                            */
+enum { GRAFP_ENGINE_AUTO = 0,      /* tcgen05 f16x3 (else bf16x3, else 3xTF32) where the shape and
+                                      the split weights allow, else SIMT                  */
        GRAFP_ENGINE_SIMT = 1,      /* fp32 FFMA tiles (exact fp32)                       */
        GRAFP_ENGINE_TC_3XTF32 = 2, /* tcgen05 kind::tf32, hi/lo split, ~2e-6 per product */
        GRAFP_ENGINE_TC_TF32 = 3,   /* tcgen05 kind::tf32 single pass (not parity grade)  */
        GRAFP_ENGINE_TC_BF16X3 = 4, /* tcgen05 kind::f16 bf16 hi/lo split, 3 passes at twice the
                                       tf32 rate, <= 3*2^-18 per product: the fp32-parity engine */
-       GRAFP_ENGINE_TC_BF16 = 5    /* tcgen05 kind::f16 plain bf16 operands, fp32 accumulate
-                                      (reduced precision, reported separately)            */ };
+       GRAFP_ENGINE_TC_BF16 = 5,   /* tcgen05 kind::f16 plain bf16 operands, fp32 accumulate
+                                      (reduced precision, reported separately)            */
+       GRAFP_ENGINE_TC_F16X3 = 6   /* tcgen05 kind::f16 IEEE-half hi/lo split, 3 passes at the bf16
+                                      rate, ~3*2^-24 per product (operands up to 2*65504): the
+                                      fp32-parity engine (ABI 4)                          */ };
 
 int grafp_abi_version(void);
 const char* grafp_last_error(void);
@@ -166,6 +169,12 @@ typedef struct {
    * grafp_knn_fwd emits).  Same arithmetic as grafp_mr_aggregate_fwd, bit-identical results; the
    * (M, C) max-relative tensor never reaches HBM. */
   const int32_t* a2_gather_idx; int32_t a2_gather_nodes; int32_t a2_gather_k;
+  /* ---- f16x3 engine (ABI 4) ---------------------------------------------------------------------
+   * w_split_f16: fp16 (2*groups*n, k1+k2), row stride ldw elements: the [hi ; lo] IEEE-half split of
+   * w * 2^s made by grafp_split_f16 (s chosen by the caller so that max|w| * 2^s stays well inside the
+   * half range and the lo parts are normal numbers); w_f16_unscale = 2^-s is folded into the epilogue
+   * scale.  With this engine y_split / a1_split carry fp16 planes instead of bf16 ones (same layout). */
+  const void* w_split_f16; float w_f16_unscale;
 } grafp_gemm_args;
 int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream);
 /* 1 if the tcgen05 engine takes this problem (k1, k2 multiples of 32, n multiple of 16, no tap3) */
@@ -175,6 +184,9 @@ int grafp_gemm_tc_supported(const grafp_gemm_args* args);
 int grafp_split_tf32(const float* w, int64_t count, float* out_hi_lo, void* stream);
 /* bf16 operand split: out (bf16)[0:count] = bf16(w), out[count:2*count] = bf16(w - bf16(w)) */
 int grafp_split_bf16(const float* w, int64_t count, void* out_bf16_hi_lo, void* stream);
+/* fp16 operand split of w * prescale (prescale = 2^s): out (half)[0:count] = f16(w*2^s),
+ * out[count:2*count] = f16(w*2^s - f16(w*2^s)); values are clamped to the finite half range */
+int grafp_split_f16(const float* w, int64_t count, float prescale, void* out_f16_hi_lo, void* stream);
 
 /* Stem: Conv2d(Cin -> Cout, 1x1, no bias) + BatchNorm2d + activation on a tiny input width
  * (encoder/graph_encoder.py:151-153, 201-202), fused with the layout change: reads the reference's

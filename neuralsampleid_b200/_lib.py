@@ -14,8 +14,9 @@ LIB_PATH = os.path.join(HERE, "libgrafp_sm100a.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16X3, ENGINE_TC_BF16 = 0, 1, 2, 3, 4, 5
+ENGINE_TC_F16X3 = 6
 ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "3xtf32": ENGINE_TC_3XTF32,
-           "tf32": ENGINE_TC_TF32, "bf16x3": ENGINE_TC_BF16X3, "bf16": ENGINE_TC_BF16}
+           "tf32": ENGINE_TC_TF32, "bf16x3": ENGINE_TC_BF16X3, "bf16": ENGINE_TC_BF16, "f16x3": ENGINE_TC_F16X3}
 
 
 class GrafpError(RuntimeError):
@@ -35,7 +36,8 @@ class GemmArgs(C.Structure):
                 ("tap3_nodes", C.c_int32), ("engine", C.c_int32),
                 ("y_split", C.c_void_p), ("ldys", C.c_int64),
                 ("a1_split", C.c_void_p), ("lda1s", C.c_int64),
-                ("a2_gather_idx", C.c_void_p), ("a2_gather_nodes", C.c_int32), ("a2_gather_k", C.c_int32)]
+                ("a2_gather_idx", C.c_void_p), ("a2_gather_nodes", C.c_int32), ("a2_gather_k", C.c_int32),
+                ("w_split_f16", C.c_void_p), ("w_f16_unscale", C.c_float)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -52,6 +54,7 @@ SIGNATURES = {
     "grafp_gemm_tc_supported": [C.POINTER(GemmArgs)],
     "grafp_split_tf32": [_P, _L, _P, _P],
     "grafp_split_bf16": [_P, _L, _P, _P],
+    "grafp_split_f16": [_P, _L, _F, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
     "grafp_frame_window_fwd": [_P, _L, _P, _I, _I, _L, _P, _P],
     "grafp_power_spectrum_fwd": [_P, _L, _L, _I, _I, _P, _L, _P],

@@ -50,11 +50,13 @@ def tap3_weight(weight: torch.Tensor) -> torch.Tensor:
 class Linear:
     """Prepared operands of one fused GEMM layer: weight (groups*n, k), optional stacked tf32
     [hi ; lo] split for the tcgen05 3xTF32 engine, per-channel scale / shift."""
-    __slots__ = ("w", "w_split", "w_split_bf16", "scale", "shift", "groups")
+    __slots__ = ("w", "w_split", "w_split_bf16", "w_split_f16", "f16_unscale", "scale", "shift", "groups")
 
-    def __init__(self, w, scale, shift, groups=1, w_split=None, w_split_bf16=None):
+    def __init__(self, w, scale, shift, groups=1, w_split=None, w_split_bf16=None, w_split_f16=None,
+                 f16_unscale=0.0):
         self.w, self.scale, self.shift, self.groups = w, scale, shift, groups
         self.w_split, self.w_split_bf16 = w_split, w_split_bf16
+        self.w_split_f16, self.f16_unscale = w_split_f16, f16_unscale
 
 
 @torch.no_grad()
@@ -82,4 +84,6 @@ def make_linear(w: torch.Tensor, scale, shift, groups: int = 1, dual: bool = Fal
         # both operand splits are tiny (weights): keep them so any engine can be selected later
         lin.w_split = ops.split_tf32(w)
         lin.w_split_bf16 = ops.split_bf16(w)
+        pre = ops.f16_prescale(w)
+        lin.w_split_f16, lin.f16_unscale = ops.split_f16(w, pre), 1.0 / pre
     return lin

@@ -18,7 +18,7 @@ from typing import Dict, List, Optional
 import torch
 from torch import nn
 
-from . import ops
+from . import _prep, ops
 from ._prep import tap3_weight
 
 
@@ -29,11 +29,11 @@ class _Layer:
 
 
 def _w_split(w2d: torch.Tensor, groups: int, k_parts: int):
-    """(tf32 split, bf16 split) of a GEMM operand when its shape suits the tcgen05 engines."""
+    """Split copies (keyword arguments of ops.gemm) of a GEMM operand when its shape suits the tcgen05 engines."""
     n_total, k = w2d.shape
     if (k // k_parts) % 32 == 0 and (n_total // groups) % 32 == 0:
         return ops.tc_splits(w2d)
-    return None, None
+    return {}
 
 
 def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: torch.Tensor, kind: str,
@@ -42,7 +42,7 @@ def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: t
               groups: int = 1, tap3_nodes: int = 0) -> torch.Tensor:
     w2d = w2d.contiguous()
     raw = ops.gemm(a1, w2d, None, None, None, 0.0, None, a2, groups, tap3_nodes, None, None,
-                   *_w_split(w2d, groups, 2 if a2 is not None else 1))
+                   **_w_split(w2d, groups, 2 if a2 is not None else 1))
     M, C = raw.shape
     if bn is not None:
         stats = ops.col_stats(raw)
@@ -50,6 +50,9 @@ def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: t
                                bias.detach() if bias is not None else None, bn.eps, bn.momentum,
                                bn.running_mean, bn.running_var)
         bn.num_batches_tracked += 1
+        # running_mean / running_var were just updated through raw pointers (torch's version counters do not see
+        # it): invalidate the eval path's folded (scale, shift) caches, which are keyed on _prep.sig()
+        _prep.bump_epoch()
     else:
         ssmi = torch.zeros((4, C), device=raw.device, dtype=torch.float32)
         ssmi[0].fill_(1.0)
@@ -119,17 +122,17 @@ def layer_bwd(L: _Layer, dout: torch.Tensor, grads: Dict, need_input: bool = Tru
         cin = L.k1 // 3
         wT = L.w2d.t().contiguous()                                   # (3*Cin, Cout)
         sp = _w_split(wT, 1, 1)
-        dA = ops.gemm(draw, wT, w_split=sp[0], w_split_bf16=sp[1])
+        dA = ops.gemm(draw, wT, **sp)
         return ops.tap3_bwd_input(dA, L.tap3_nodes, cin), None
     wg = L.w2d.view(L.groups, n, L.k1 + L.k2)
     wT1 = wg[:, :, :L.k1].transpose(1, 2).reshape(L.groups * L.k1, n).contiguous()
     sp = _w_split(wT1, L.groups, 1)
-    da1 = ops.gemm(draw, wT1, residual=add_to, groups=L.groups, w_split=sp[0], w_split_bf16=sp[1])
+    da1 = ops.gemm(draw, wT1, residual=add_to, groups=L.groups, **sp)
     da2 = None
     if L.k2:
         wT2 = wg[:, :, L.k1:].transpose(1, 2).reshape(L.groups * L.k2, n).contiguous()
         sp = _w_split(wT2, L.groups, 1)
-        da2 = ops.gemm(draw, wT2, groups=L.groups, w_split=sp[0], w_split_bf16=sp[1])
+        da2 = ops.gemm(draw, wT2, groups=L.groups, **sp)
     return da1, da2
 
 

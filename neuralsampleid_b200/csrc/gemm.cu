@@ -4,7 +4,7 @@
 namespace grafp {
 int gemm_simt_launch(const grafp_gemm_args& a, cudaStream_t st);
 int gemm_tc_supported(const grafp_gemm_args& a);
-int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t st);
+int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t st);
 }  // namespace grafp
 
 using namespace grafp;
@@ -30,24 +30,29 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
                 "gemm: the sigmoid epilogue exists on the fp32 SIMT engine only");
   if (a.m == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  // 16-bit operand format of the split engines: 2 = fp16 (f16x3), 1 = bf16
+  const bool f16_ok = a.w_split_f16 && a.w_f16_unscale > 0.0f;
   if (a.a2_gather_idx) {
     GRAFP_REQUIRE(!a.a2 && !a.a1_split && a.a1 && a.k2 == a.k1 && a.tap3_nodes == 0,
                   "gemm: a2_gather needs fp32 a1, a2 == NULL, k2 == k1, no tap3");
     GRAFP_REQUIRE(a.a2_gather_nodes > 0 && a.a2_gather_k > 0 && a.m % a.a2_gather_nodes == 0,
                   "gemm: a2_gather needs m to be a multiple of a2_gather_nodes");
-    GRAFP_REQUIRE(a.engine == GRAFP_ENGINE_AUTO || a.engine == GRAFP_ENGINE_TC_BF16X3 ||
-                      a.engine == GRAFP_ENGINE_TC_BF16,
+    GRAFP_REQUIRE(a.engine == GRAFP_ENGINE_TC_BF16X3 || a.engine == GRAFP_ENGINE_TC_BF16,
                   "gemm: a2_gather needs a bf16 tensor-core engine (engine=%d)", a.engine);
     GRAFP_REQUIRE(a.w_split_bf16 && gemm_tc_supported(a), "gemm: a2_gather needs w_split_bf16 and a tcgen05-supported shape");
     return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_BF16 ? 1 : 3, 1, st);
   }
   if (a.a1_split || a.y_split) {
-    // split-bf16 activations exist only on the bf16 tensor-core engines: fail loudly, never convert
+    // split 16-bit activations exist only on the 16-bit tensor-core engines: fail loudly, never convert
     GRAFP_REQUIRE(a.engine == GRAFP_ENGINE_AUTO || a.engine == GRAFP_ENGINE_TC_BF16X3 ||
-                      a.engine == GRAFP_ENGINE_TC_BF16,
-                  "gemm: split-bf16 activations need a bf16 tensor-core engine (engine=%d)", a.engine);
-    GRAFP_REQUIRE(a.w_split_bf16 && gemm_tc_supported(a),
-                  "gemm: split-bf16 activations need w_split_bf16 and a tcgen05-supported shape");
+                      a.engine == GRAFP_ENGINE_TC_BF16 || a.engine == GRAFP_ENGINE_TC_F16X3,
+                  "gemm: split activations need a 16-bit tensor-core engine (engine=%d)", a.engine);
+    GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: split activations need a tcgen05-supported shape");
+    if (a.engine == GRAFP_ENGINE_TC_F16X3 || (a.engine == GRAFP_ENGINE_AUTO && f16_ok)) {
+      GRAFP_REQUIRE(f16_ok, "gemm: the f16x3 engine needs w_split_f16 (grafp_split_f16) and w_f16_unscale");
+      return gemm_tc_launch(a, 3, 2, st);
+    }
+    GRAFP_REQUIRE(a.w_split_bf16, "gemm: split-bf16 activations need w_split_bf16");
     return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_BF16 ? 1 : 3, 1, st);
   }
   switch (a.engine) {
@@ -65,8 +70,13 @@ extern "C" int grafp_gemm_fwd(const grafp_gemm_args* args, void* stream) {
       GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
       GRAFP_REQUIRE(a.w_split_bf16, "gemm: the bf16 engines need w_split_bf16 (grafp_split_bf16)");
       return gemm_tc_launch(a, a.engine == GRAFP_ENGINE_TC_BF16X3 ? 3 : 1, 1, st);
+    case GRAFP_ENGINE_TC_F16X3:
+      GRAFP_REQUIRE(gemm_tc_supported(a), "gemm: shape not supported by the tcgen05 engine");
+      GRAFP_REQUIRE(f16_ok, "gemm: the f16x3 engine needs w_split_f16 (grafp_split_f16) and w_f16_unscale");
+      return gemm_tc_launch(a, 3, 2, st);
     case GRAFP_ENGINE_AUTO:
       if (a.act == GRAFP_ACT_SIGMOID) return gemm_simt_launch(a, st);
+      if (f16_ok && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, 2, st);
       if (a.w_split_bf16 && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, 1, st);
       if (a.w_split && gemm_tc_supported(a)) return gemm_tc_launch(a, 3, 0, st);
       return gemm_simt_launch(a, st);

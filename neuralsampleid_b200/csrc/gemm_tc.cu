@@ -27,6 +27,7 @@
 // empty[s] (MMA commit -> TMA), tmem_full[b] (MMA commit -> epilogue), tmem_empty[b].
 #include <stdlib.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace grafp {
@@ -52,6 +53,7 @@ struct TcParams {
   const float* residual; int64_t ldr;
   float* row_sumsq;
   int act; float act_param;
+  float unscale;       // multiplies the epilogue scale: undoes the host's power-of-two weight pre-scaling (f16x3)
   uint32_t tmem_cols;
   int y_split;         // 0: fp32 output; 2: bf16 [hi ; lo] planes; 1: bf16 hi plane only (1-pass engine)
   int y_both;          // with y_split: ALSO write the fp32 output (tmY fp32 map + tmYs split map, two staging tiles)
@@ -79,6 +81,26 @@ __device__ __forceinline__ void epi_apply(float (&v)[32], const float* scale, co
   }
 }
 
+
+// 16-bit operand packing of the split engines: element 0 in the low half.  kF16: IEEE half with a
+// saturating conversion (a value beyond 65504 becomes hi = 65504, lo = the rest, instead of inf);
+// else bfloat16.
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if (kF16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <bool kF16>
+__device__ __forceinline__ float2 unpack16(uint32_t v) {
+  if (kF16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+
 // kCluster == 2: CTA pairs (thread-block cluster 2x1) work on two vertically adjacent 128-row tiles
 // of the same column tile; each CTA fetches HALF of the weight tile and TMA-multicasts it into both
 // CTAs' shared memory, halving the per-SM weight traffic out of L2 (the limiter of the 1-CTA form).
@@ -97,7 +119,12 @@ __device__ __forceinline__ void epi_apply(float (&v)[32], const float* scale, co
 // into the operand stage, there is no fp32 ring and no transform, the MMA waits on full[s] alone.
 // kGather: fused max-relative aggregation of the second A source (opt-in, see TcParams::gat_idx); a separate
 // instantiation so the default kernels carry none of its registers or code.
-template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather>
+// kF16 (with kBf16, which selects the 16-bit kind::f16 operand path): the operand pair is IEEE fp16 instead of
+// bfloat16 -- "f16x3": hi carries 11 significant bits, lo the next 11, so a = a1 + a2 to 2^-24 |a| (an absolute
+// floor of 2^-25 where lo is subnormal) and the dropped a2*w2 term is 2^-24: fp32-class products at the bf16 MMA
+// rate.  The weights are pre-scaled by a power of two on the host (p.unscale undoes it in the epilogue) so that
+// their lo parts stay normal numbers.
+template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather, bool kF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -256,7 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = kBf16 ? umma_idesc_bf16(TC_BM, p.bn) : umma_idesc_tf32(TC_BM, p.bn);
+      const uint32_t idesc = kBf16 ? (kF16 ? umma_idesc_f16(TC_BM, p.bn) : umma_idesc_bf16(TC_BM, p.bn))
+                                   : umma_idesc_tf32(TC_BM, p.bn);
       uint32_t it = 0, ti = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
         const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
@@ -387,19 +415,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               const int lc = (q & 7) ^ (r & 7);                          // logical 4-float chunk 0..7
               const uint32_t dst = (uint32_t)r * 64u + ((uint32_t)((lc >> 1) ^ ((r >> 1) & 3)) << 4) +
                                    ((uint32_t)(lc & 1) << 3);
-              const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[i].x, v[i].y);
-              const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[i].z, v[i].w);
               uint2 hv;
-              hv.x = *reinterpret_cast<const uint32_t*>(&h01);
-              hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+              hv.x = pack16<kF16>(v[i].x, v[i].y);
+              hv.y = pack16<kF16>(v[i].z, v[i].w);
               *reinterpret_cast<uint2*>(hi + dst) = hv;
               if (kPasses == 3) {
-                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[i].x - f01.x, v[i].y - f01.y);
-                const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[i].z - f23.x, v[i].w - f23.y);
+                const float2 f01 = unpack16<kF16>(hv.x), f23 = unpack16<kF16>(hv.y);
                 uint2 lv;
-                lv.x = *reinterpret_cast<const uint32_t*>(&l01);
-                lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                lv.x = pack16<kF16>(v[i].x - f01.x, v[i].y - f01.y);
+                lv.y = pack16<kF16>(v[i].z - f23.x, v[i].w - f23.y);
                 *reinterpret_cast<uint2*>(lo + dst) = lv;
               }
             }
@@ -450,7 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       float* ssc = s_scale[ti & 1u];
       float* ssh = s_shift[ti & 1u];
       if (e256 < p.bn) {
-        ssc[e256] = p.scale ? __ldg(p.scale + col0 + e256) : 1.0f;
+        ssc[e256] = (p.scale ? __ldg(p.scale + col0 + e256) : 1.0f) * p.unscale;
         ssh[e256] = p.shift ? __ldg(p.shift + col0 + e256) : 0.0f;
       }
       const float* res_row = (p.residual && row_ok) ? p.residual + row * p.ldr + col0 : nullptr;
@@ -498,11 +522,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint32_t hp[16], lp[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-            const float2 f = __bfloat1622float2(h);
-            const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * q] - f.x, v[2 * q + 1] - f.y);
-            hp[q] = *reinterpret_cast<const uint32_t*>(&h);
-            lp[q] = *reinterpret_cast<const uint32_t*>(&l);
+            hp[q] = pack16<kF16>(v[2 * q], v[2 * q + 1]);
+            const float2 f = unpack16<kF16>(hp[q]);
+            lp[q] = pack16<kF16>(v[2 * q] - f.x, v[2 * q + 1] - f.y);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -683,8 +705,11 @@ int gemm_tc_supported(const grafp_gemm_args& a) {
 }
 
 // tf32 engines: passes == 3 reads a.w_split = stacked fp32 [W_hi ; W_lo] (2 * groups * n rows).
-// bf16 engines: a.w_split_bf16 = stacked bf16 [w1 ; w2]; passes == 1 uses only w1.
-int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t st) {
+// bf16 engines (fmt 1): a.w_split_bf16 = stacked bf16 [w1 ; w2]; passes == 1 uses only w1.
+// f16x3 (fmt 2): a.w_split_f16 = stacked fp16 split of w * 2^s, a.w_f16_unscale = 2^-s.
+int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t st) {
+  const int bf16 = fmt != 0;
+  const bool f16 = fmt == 2;
   const int bn = pick_bn(a.n);
   const int n_total = a.groups * a.n;
   CUtensorMap mA1, mA2, mW, mY, mYs;
@@ -721,7 +746,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   // bn <= 128 10-30 % slower than independent CTAs -- the pair's lock-step costs more than the L2 traffic saved)
   const int cluster = (mc_env == 2 && tiles_m >= 2 && bn >= 256 && sm_count() % 2 == 0) ? 2 : 1;
   if (bf16) {
-    if (int rc = tc_make_map_2d_bf16(&mW, a.w_split_bf16, (int64_t)n_total * 2, a.k1 + a.k2, a.ldw,
+    if (int rc = tc_make_map_2d_bf16(&mW, f16 ? a.w_split_f16 : a.w_split_bf16, (int64_t)n_total * 2, a.k1 + a.k2, a.ldw,
                                      cluster == 2 ? bn / 2 : bn))
       return rc;
   } else if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
@@ -744,6 +769,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   p.scale = a.scale; p.shift = a.shift; p.residual = a.residual; p.ldr = a.ldr;
   p.row_sumsq = a.row_sumsq;
   p.act = a.act; p.act_param = a.act_param;
+  p.unscale = f16 ? a.w_f16_unscale : 1.0f;
   uint32_t cols = 32;
   while ((int)cols < 2 * bn) cols <<= 1;
   p.tmem_cols = cols;
@@ -781,7 +807,11 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int bf16, cudaStream_t 
   grid *= cluster;
   using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   KernFn kern;
-  if (a.a2_gather_idx)
+  if (f16) {
+    GRAFP_REQUIRE(passes == 3 && !a.a2_gather_idx, "gemm_tc: the fp16 operand format exists as the 3-pass f16x3 engine only");
+    if (asplit) kern = cluster == 2 ? gemm_tc_kernel<3, 2, true, true, false, true> : gemm_tc_kernel<3, 1, true, true, false, true>;
+    else kern = cluster == 2 ? gemm_tc_kernel<3, 2, true, false, false, true> : gemm_tc_kernel<3, 1, true, false, false, true>;
+  } else if (a.a2_gather_idx)
     kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, false, true> : gemm_tc_kernel<3, 1, true, false, true>)
                        : (cluster == 2 ? gemm_tc_kernel<1, 2, true, false, true> : gemm_tc_kernel<1, 1, true, false, true>);
   else if (asplit)
@@ -833,9 +863,30 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __
   }
 }
 
+// w1 = f16(w * prescale), w2 = f16(w * prescale - w1): out is fp16 (2*rows, cols) = [w1 ; w2]
+__global__ void split_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t n, float prescale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = w[i] * prescale;
+    const float c = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    const __half h = __float2half_rn(c);
+    out[i] = h;
+    out[n + i] = __float2half_rn(fminf(fmaxf(v - __half2float(h), -65504.0f), 65504.0f));
+  }
+}
+
 }  // namespace grafp
 
 using namespace grafp;
+
+extern "C" int grafp_split_f16(const float* w, int64_t count, float prescale, void* out_f16_hi_lo, void* stream) {
+  GRAFP_REQUIRE(count >= 0 && (count == 0 || (w && out_f16_hi_lo)), "split_f16: bad arguments");
+  GRAFP_REQUIRE(prescale > 0.0f, "split_f16: prescale must be positive");
+  if (count == 0) return 0;
+  split_f16_kernel<<<(unsigned)((count + 255) / 256), 256, 0, as_stream(stream)>>>(
+      w, static_cast<__half*>(out_f16_hi_lo), count, prescale);
+  return check_launch("split_f16");
+}
 
 extern "C" int grafp_split_bf16(const float* w, int64_t count, void* out_bf16_hi_lo, void* stream) {
   GRAFP_REQUIRE(count >= 0 && (count == 0 || (w && out_bf16_hi_lo)), "split_bf16: bad arguments");

@@ -46,7 +46,7 @@ struct KnnTcParams {
   int kbk;                // k-block width in fp32 elements: 32 (128-byte rows, 128B swizzle) or 16 (64B)
   int thresh;             // two-pass threshold selection (needs k*d <= column groups of a graph)
   int stages;
-  const float* rinv; const float* sq;   // prepass outputs, or (rinv == nullptr) sq = raw sum of squares
+  const float* rinv; const float* sq;   // prepass outputs (rinv holds the normalize DENOMINATOR), or (rinv == nullptr) sq = raw sum of squares
   int normalize;
   int32_t* idx; float* dist;
   uint32_t tmem_cols;
@@ -70,30 +70,20 @@ knn_rownorm_kernel(const float* __restrict__ x, int64_t M, int C, int normalize,
       s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
     }
   for (int o = lanes_per_row >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  float ri = 1.0f, q = s;
+  float ri = 1.0f, q = s;          // ri: the F.normalize denominator max(||x||, 1e-12) (1 when not normalising)
   if (normalize) {
-    ri = __frcp_rn(fmaxf(sqrtf(s), 1e-12f));
+    ri = fmaxf(sqrtf(s), 1e-12f);
     float t = 0.0f;
     if (ok)
       for (int c = sl * 4; c < C; c += lanes_per_row * 4) {
         const float4 v = *reinterpret_cast<const float4*>(xr + c);
-        const float a0 = v.x * ri, a1 = v.y * ri, a2 = v.z * ri, a3 = v.w * ri;
+        const float a0 = __fdiv_rn(v.x, ri), a1 = __fdiv_rn(v.y, ri), a2 = __fdiv_rn(v.z, ri), a3 = __fdiv_rn(v.w, ri);
         t = fmaf(a0, a0, t); t = fmaf(a1, a1, t); t = fmaf(a2, a2, t); t = fmaf(a3, a3, t);
       }
     for (int o = lanes_per_row >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     q = t;
   }
   if (ok && sl == 0) { rinv[row] = ri; sq[row] = q; }
-}
-
-// (rinv, sq) of one node: from the prepass arrays, or derived from the raw sum of squares that the
-// producing GEMM's epilogue accumulated
-__device__ __forceinline__ float2 knn_node_norm(const KnnTcParams& p, int64_t node) {
-  if (p.rinv) return make_float2(__ldg(p.rinv + node), __ldg(p.sq + node));
-  const float s = __ldg(p.sq + node);
-  if (!p.normalize) return make_float2(1.0f, s);
-  const float ri = __frcp_rn(fmaxf(sqrtf(s), 1e-12f));
-  return make_float2(ri, s * ri * ri);
 }
 
 template <int KMAX>
@@ -214,11 +204,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
     float ri_next[8];
     load_raw(blockIdx.x, ri_next);
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      float ri[8];
+      // F.normalize divides (torch_edge.py:281): x / den is reproduced as the correctly rounded quotient from the
+      // reciprocal and one residual correction (q = x*r; q += (x - q*den)*r), not as the 1-ulp-off product x*r
+      float ri[8], dn[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float s0 = ri_next[i];                   // rinv itself (prepass) or the raw sum of squares
-        ri[i] = p.rinv ? s0 : (p.normalize ? __frcp_rn(fmaxf(sqrtf(s0), 1e-12f)) : 1.0f);
+        const float s0 = ri_next[i];                   // the denominator itself (prepass) or the raw sum of squares
+        dn[i] = p.rinv ? s0 : (p.normalize ? fmaxf(sqrtf(s0), 1e-12f) : 1.0f);
+        ri[i] = __frcp_rn(dn[i]);
       }
       load_raw(tile + gridDim.x, ri_next);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -235,8 +228,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
             for (int i = 0; i < 4; ++i) v[i] = bh[t + KT_XF_THREADS * (half4 * 4 + i)];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float rr = ri[half4 * 4 + i];
-              const float x0 = v[i].x * rr, x1 = v[i].y * rr, x2 = v[i].z * rr, x3 = v[i].w * rr;
+              const float rr = ri[half4 * 4 + i], dd = dn[half4 * 4 + i];
+              float x0 = v[i].x * rr, x1 = v[i].y * rr, x2 = v[i].z * rr, x3 = v[i].w * rr;
+              x0 = fmaf(fmaf(-x0, dd, v[i].x), rr, x0);
+              x1 = fmaf(fmaf(-x1, dd, v[i].y), rr, x1);
+              x2 = fmaf(fmaf(-x2, dd, v[i].z), rr, x2);
+              x3 = fmaf(fmaf(-x3, dd, v[i].w), rr, x3);
               float4 h, l;
               h.x = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
               h.y = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);

@@ -136,7 +136,7 @@ class GINConv2d(_NodeGraphConv):
 def _without_epilogue(lin):
     """The same prepared weights without the epilogue (scale / shift dropped)."""
     from ..._prep import Linear
-    return Linear(lin.w, None, None, lin.groups, lin.w_split, lin.w_split_bf16)
+    return Linear(lin.w, None, None, lin.groups, lin.w_split, lin.w_split_bf16, lin.w_split_f16, lin.f16_unscale)
 
 
 class GraphConv2d(nn.Module):

@@ -23,10 +23,19 @@ _engine_override = None
 
 
 def set_engine(name: str) -> None:
-    """Selects the GEMM engine: 'auto' (tcgen05 bf16x3 where shapes allow, else fp32 SIMT), 'simt',
-    '3xtf32', 'tf32', 'bf16x3', 'bf16'.  Prepared weights are re-split on the next call."""
+    """Selects the GEMM engine: 'auto' (tcgen05 f16x3 where shapes allow, else fp32 SIMT), 'simt',
+    '3xtf32', 'tf32', 'f16x3', 'bf16x3', 'bf16'.  An explicit tensor-core engine applies to every GEMM
+    whose shape the tcgen05 kernels take; the others (stem, odd widths) keep the exact SIMT kernel.  The
+    kNN Gram tiles always use 3xTF32 on the tensor-core engines.  Prepared weights carry every split."""
     global _engine
     _engine = ENGINES[name.lower()]
+
+
+_SPLIT16 = (_lib.ENGINE_AUTO, _lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16, _lib.ENGINE_TC_F16X3)
+
+
+def _effective_engine() -> int:
+    return ENGINES[_engine_override] if _engine_override is not None else _engine
 
 
 def get_engine() -> int:
@@ -84,7 +93,10 @@ def knn(x: torch.Tensor, B: int, N: int, k: int, dilation: int = 1, normalize: b
     idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
     dist = torch.empty((B, N, k), device=x.device, dtype=torch.float32) if return_dist else None
     eng = _engine if engine is None else engine
-    eng = {_lib.ENGINE_TC_TF32: _lib.ENGINE_TC_3XTF32}.get(eng, eng)
+    # the Gram tiles always run 3xTF32: every tensor-core GEMM engine maps onto it (shapes the tcgen05 kNN
+    # does not take fall back to the exact SIMT kernel under AUTO)
+    if eng in (_lib.ENGINE_TC_TF32, _lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16, _lib.ENGINE_TC_F16X3):
+        eng = _lib.ENGINE_AUTO
     lib = _lib.load()
     ws_bytes = int(lib.grafp_knn_workspace_bytes(B, N, Cc, k, dilation)) if eng != _lib.ENGINE_SIMT else 0
     ws = torch.empty((ws_bytes // 4,), device=x.device, dtype=torch.float32) if ws_bytes else None
@@ -172,18 +184,50 @@ def split_bf16(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def tc_splits(w: torch.Tensor):
-    """The split copies of a weight the engines in use need: (tf32 split | None, bf16 split | None)."""
-    e = _engine
-    want_tf32 = e in (_lib.ENGINE_TC_3XTF32,)
-    want_bf16 = e in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16)
-    return (split_tf32(w) if want_tf32 else None), (split_bf16(w) if want_bf16 else None)
+def f16_prescale(w: torch.Tensor) -> float:
+    """Power of two 2^s that brings max|w| to [2^9, 2^10): the fp16 lo parts of the f16x3 engine are then normal
+    numbers for every weight above 2^-4 of the largest, and hi stays 64x under the half overflow."""
+    amax = float(w.abs().max()) if w.numel() else 0.0
+    if not (amax > 0.0) or amax != amax or amax == float("inf"):
+        return 1.0
+    import math
+    s = 9 - math.floor(math.log2(amax))
+    return float(2.0 ** max(-14, min(24, s)))
+
+
+def split_f16(w: torch.Tensor, prescale: float) -> torch.Tensor:
+    """(n, k) fp32 -> fp16 (2n, k) stacked [f16(w * prescale) ; f16(w * prescale - hi)] for the f16x3 engine."""
+    w = _chk(w, name="w")
+    out = torch.empty((2 * w.shape[0], w.shape[1]), device=w.device, dtype=torch.float16)
+    with torch.cuda.device(w.device):
+        check(_lib.load().grafp_split_f16(_ptr(w), w.numel(), float(prescale), _ptr(out), _stream(w)), "split_f16")
+    return out
+
+
+TRAIN_F16_PRESCALE = 256.0
+
+
+def tc_splits(w: torch.Tensor) -> dict:
+    """The split copies of a weight that the engine in use needs, as keyword arguments of ``gemm``.  This is the
+    per-step path of the train mode (weights change every step), so the f16x3 pre-scale is the fixed 2^8 instead
+    of a data-dependent one (no host synchronisation, CUDA-graph capturable): lo parts stay normal numbers for
+    |w| >= 1e-3, weights saturate beyond |w| = 511."""
+    e = _effective_engine()
+    out = {}
+    if e == _lib.ENGINE_TC_3XTF32:
+        out["w_split"] = split_tf32(w)
+    if e in (_lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16):
+        out["w_split_bf16"] = split_bf16(w)
+    if e in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_F16X3):
+        out["w_split_f16"] = split_f16(w, TRAIN_F16_PRESCALE)
+        out["f16_unscale"] = 1.0 / TRAIN_F16_PRESCALE
+    return out
 
 
 class SplitAct:
-    """An activation in the split-bf16 format of include/grafp.h (ABI 2): bf16 (2, M, C), plane 0 =
-    bf16(v), plane 1 = bf16(v - bf16(v)) -- the operand pair the bf16x3 engine computes with.  Only a
-    GEMM may consume it (``ops.gemm`` / ``ops.linear`` as ``a1``)."""
+    """An activation in the split 16-bit format of include/grafp.h (ABI 2 / 4): a bf16 (bf16 engines) or fp16
+    (f16x3 engine) tensor (2, M, C), plane 0 = r(v), plane 1 = r(v - r(v)) -- the operand pair the 3-pass engine
+    computes with.  Only a GEMM on the same engine may consume it (``ops.gemm`` / ``ops.linear`` as ``a1``)."""
     __slots__ = ("t",)
 
     def __init__(self, t: torch.Tensor):
@@ -202,13 +246,20 @@ class SplitAct:
         return self.t[0].float() + (self.t[1].float() if self.t.shape[0] > 1 else 0.0)
 
 
+def split_dtype(engine: Optional[int] = None):
+    """Element type of SplitAct planes under ``engine`` (default: the engine in effect)."""
+    eng = _effective_engine() if engine is None else engine
+    return torch.float16 if eng in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_F16X3) else torch.bfloat16
+
+
 def split_ok(lin, k_total: int) -> bool:
-    """True when the GEMM over ``lin`` (k_total input columns) runs on a bf16 tensor-core engine, i.e.
+    """True when the GEMM over ``lin`` (k_total input columns) runs on a 16-bit-operand tensor-core engine, i.e.
     may produce or consume a SplitAct."""
-    eng = ENGINES[_engine_override] if _engine_override is not None else _engine
-    if eng not in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16):
+    eng = _effective_engine()
+    if eng not in _SPLIT16:
         return False
-    if lin.w_split_bf16 is None or os.environ.get("GRAFP_NO_SPLIT_ACT"):
+    have = lin.w_split_f16 if eng in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_F16X3) else lin.w_split_bf16
+    if have is None or os.environ.get("GRAFP_NO_SPLIT_ACT"):
         return False
     n = lin.w.shape[0] // lin.groups
     return k_total % (32 * lin.groups) == 0 and n % 32 == 0
@@ -220,7 +271,7 @@ def fused_mr_ok(lin, c: int) -> bool:
     # Opt-in (GRAFP_FUSED_MR=1): measured on B200 the in-kernel gather (four transform warps, dependent
     # idx -> row loads from L2) makes the MRConv GEMMs 3-4x slower (5.6 vs 1.4 ms at stage 3), far more than the
     # 1.3 ms/step of mr_aggregate it removes; a register-blocked variant that batches the loads spills.
-    if not os.environ.get("GRAFP_FUSED_MR"):
+    if not os.environ.get("GRAFP_FUSED_MR") or _effective_engine() not in (_lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_BF16):
         return False
     return lin.groups > 0 and split_ok(lin, 2 * c) and (c // lin.groups) % 32 == 0
 
@@ -230,7 +281,8 @@ def linear(a1, lin, act=None, act_param: float = 0.0, residual=None, a2=None,
            a2_gather=None):
     """ops.gemm over a prepared ``_prep.Linear``."""
     return gemm(a1, lin.w, lin.scale, lin.shift, act, act_param, residual, a2, lin.groups, tap3_nodes,
-                engine, out, lin.w_split, lin.w_split_bf16, row_sumsq, out_split, a2_gather)
+                engine, out, lin.w_split, lin.w_split_bf16, row_sumsq, out_split, a2_gather,
+                lin.w_split_f16, lin.f16_unscale)
 
 
 def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None,
@@ -239,7 +291,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
          groups: int = 1, tap3_nodes: int = 0, engine: Optional[int] = None,
          out: Optional[torch.Tensor] = None, w_split: Optional[torch.Tensor] = None,
          w_split_bf16: Optional[torch.Tensor] = None, row_sumsq: Optional[torch.Tensor] = None,
-         out_split: bool = False, a2_gather=None):
+         out_split: bool = False, a2_gather=None, w_split_f16: Optional[torch.Tensor] = None,
+         f16_unscale: float = 0.0):
     """y = act(scale * [a1 | a2] @ w.T + shift) + residual  (per-group, see include/grafp.h).
     ``a2_gather`` = (idx int32 (B, N, k), N): the second source is the max-relative aggregation of a1 over
     those neighbour lists, computed inside the kernel (fused MRConv2d; bf16 tensor-core engines only).
@@ -249,8 +302,12 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     (fp32 tensor, SplitAct) written by the same epilogue (bf16 tensor-core engines only: the library refuses
     anything else)."""
     a1s = None
+    # the engine this call resolves to (an explicit tensor-core engine only applies where the tcgen05 kernels
+    # take the shape: decided below, once the arguments are assembled)
+    eng_req = engine if engine is not None else _effective_engine()
+    sdt = split_dtype(eng_req)
     if isinstance(a1, SplitAct):
-        a1s = _chk(a1.t, torch.bfloat16, "a1 (split)")
+        a1s = _chk(a1.t, sdt, "a1 (split)")
         a1 = None
     else:
         a1 = _chk(a1, name="a1")
@@ -279,8 +336,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     dev = a1.device if a1 is not None else a1s.device
     # the engine a split GEMM runs on (split_ok() admitted only bf16 tensor-core engines): the 1-pass bf16
     # engine carries the hi plane only
-    split_engine = engine if engine is not None else (ENGINES[_engine_override] if _engine_override is not None else _engine)
-    planes = 1 if split_engine == _lib.ENGINE_TC_BF16 else 2
+    planes = 1 if eng_req == _lib.ENGINE_TC_BF16 else 2
     if a1s is not None and a1s.shape[0] < planes:
         raise GrafpError("gemm: a hi-plane-only SplitAct can only feed the 1-pass bf16 engine")
     both = out_split == "both"                       # fp32 output AND its split copy, from one epilogue
@@ -288,7 +344,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     if out_split:
         if out is not None or row_sumsq is not None:
             raise GrafpError("gemm: out_split cannot be combined with out= / row_sumsq")
-        out = torch.empty((planes, M, n_total), device=dev, dtype=torch.bfloat16)
+        out = torch.empty((planes, M, n_total), device=dev, dtype=sdt)
         if both:
             out32 = torch.empty((M, n_total), device=dev, dtype=torch.float32)
     elif out is None:
@@ -312,6 +368,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     args.w, args.ldw = w.data_ptr(), w.stride(0)
     args.w_split = w_split.data_ptr() if w_split is not None else None
     args.w_split_bf16 = w_split_bf16.data_ptr() if w_split_bf16 is not None else None
+    args.w_split_f16 = w_split_f16.data_ptr() if w_split_f16 is not None else None
+    args.w_f16_unscale = float(f16_unscale) if w_split_f16 is not None else 0.0
     args.scale = scale.data_ptr() if scale is not None else None
     args.shift = shift.data_ptr() if shift is not None else None
     if residual is not None:
@@ -329,13 +387,16 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     args.m, args.n, args.groups = M, n, groups
     args.act, args.act_param = act_code(act) if not isinstance(act, int) else act, act_param
     args.tap3_nodes = tap3_nodes
-    args.engine = _engine if engine is None else engine
-    if engine is None and _engine_override is not None:
-        ov = ENGINES[_engine_override]
-        if ov == _lib.ENGINE_SIMT:
-            args.engine = ov
-        elif w_split is not None and _lib.load().grafp_gemm_tc_supported(C.byref(args)):
-            args.engine = ov
+    args.engine = eng_req
+    if engine is None and eng_req not in (_lib.ENGINE_AUTO, _lib.ENGINE_SIMT) and a1s is None and not out_split \
+            and a2_gather is None:
+        # a tensor-core engine selected globally (set_engine / GRAFP_ENGINE): shapes, or unprepared weights, that
+        # the tcgen05 kernels do not take run the exact SIMT kernel, as under AUTO.  An engine passed per call
+        # (engine=) is taken literally and fails loudly instead.
+        need = {_lib.ENGINE_TC_3XTF32: w_split, _lib.ENGINE_TC_TF32: w, _lib.ENGINE_TC_BF16X3: w_split_bf16,
+                _lib.ENGINE_TC_BF16: w_split_bf16, _lib.ENGINE_TC_F16X3: w_split_f16}[eng_req]
+        if need is None or not _lib.load().grafp_gemm_tc_supported(C.byref(args)):
+            args.engine = _lib.ENGINE_SIMT
     with torch.cuda.device(dev):
         check(_lib.load().grafp_gemm_fwd(C.byref(args), _stream(out)), "gemm_fwd")
     if both:

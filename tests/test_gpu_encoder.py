@@ -117,7 +117,7 @@ def test_encoder_matches_reference_golden(golden_dir, fname, k):
     assert float(_rel(got_f.cpu(), torch.from_numpy(g["emb"])).max()) < REL_TOL
 
 
-@pytest.mark.parametrize("engine", ["simt", "3xtf32", "bf16x3"])
+@pytest.mark.parametrize("engine", ["simt", "3xtf32", "bf16x3", "f16x3"])
 def test_encoder_engines_agree(engine):
     from neuralsampleid_b200 import ops
     enc, sd = _encoder(3)
@@ -135,6 +135,57 @@ def test_encoder_engines_agree(engine):
         ops._engine_override = None
         ops._engine = old
     assert float(_rel(got.cpu(), want).max()) < REL_TOL
+
+
+@pytest.mark.parametrize("engine", ["auto", "simt", "3xtf32", "tf32", "bf16x3", "bf16", "f16x3"])
+def test_forward_under_every_set_engine_value(engine):
+    """ops.set_engine(name) (the public switch, also GRAFP_ENGINE) must give a working forward for every
+    documented value: the kNN maps every tensor-core GEMM engine onto its 3xTF32 Gram tiles and GEMM shapes the
+    tcgen05 kernels do not take (the stem) run the exact SIMT kernel."""
+    from neuralsampleid_b200 import ops
+    enc, sd = _encoder(3)
+    x = synth.synth_uniform((5, 8, 256), 72)
+    want, blocks = _oracle_run(sd, x, 3)
+    forced = [t["idx"].int().to(DEV) for t in blocks]
+    old = ops.get_engine()
+    try:
+        ops.set_engine(engine)
+        with torch.no_grad():
+            got = enc(x.to(DEV), forced_idx=forced)
+            free = enc(x.to(DEV))
+    finally:
+        ops._engine = old
+    assert free.shape == (5, 1024) and bool(torch.isfinite(free).all())
+    assert float(_rel(got.cpu(), want).max()) < (3e-2 if engine in ("tf32", "bf16") else REL_TOL)
+
+
+def test_eval_after_train_forward_refolds_batchnorm():
+    """A train-mode forward updates the BatchNorm running statistics through raw pointers; the eval path's folded
+    (scale, shift) caches must notice even when no optimizer step follows (frozen encoder, BN recalibration, a
+    NaN-skipped step): eval -> train forward -> eval equals a fresh module loaded with the same state."""
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    enc, sd = _encoder(3)
+    x = synth.synth_uniform((4, 8, 256), 73).to(DEV)
+    with torch.no_grad():
+        before = enc(x)
+    enc.train()
+    enc(synth.synth_uniform((6, 8, 256), 74).to(DEV))         # BN batch statistics -> running stats move
+    enc.eval()
+    with torch.no_grad():
+        after = enc(x)
+    fresh = GraphEncoder(cfg=CFG, in_channels=8, k=3)
+    fresh.load_state_dict({k: v.cpu() for k, v in enc.state_dict().items()})
+    fresh = fresh.to(DEV).eval()
+    with torch.no_grad():
+        want = fresh(x)
+    assert not torch.equal(before, after)
+    assert torch.equal(after, want)
+    # and against the oracle on the updated state (teacher-forced graphs)
+    sd2 = {k: v.cpu() for k, v in enc.state_dict().items()}
+    ref, blocks = _oracle_run(sd2, x.cpu(), 3)
+    with torch.no_grad():
+        got = enc(x, forced_idx=[t["idx"].int().to(DEV) for t in blocks])
+    assert float(_rel(got.cpu(), ref).max()) < REL_TOL
 
 
 def test_encoder_bf16_engine_reported_separately():

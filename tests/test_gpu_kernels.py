@@ -287,7 +287,7 @@ GEMM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("engine", ["simt", "3xtf32", "tf32", "bf16x3", "bf16", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "3xtf32", "tf32", "bf16x3", "bf16", "f16x3", "auto"])
 @pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: "m%d_k%d+%d_n%d_g%d_%s%s%s" % (
     c[0], c[1], c[2], c[3], c[4], c[5], "_res" if c[6] else "", "_tap3" if c[7] else ""))
 def test_gemm_engines(case, engine):
@@ -311,7 +311,7 @@ def test_gemm_engines(case, engine):
     # rows per graph tile 128 evenly
     tc_ok = lin.w_split is not None and n % 32 == 0 and \
         (not tap3 or ((k1 // 3) % 32 == 0 and (128 % tap3 == 0 or tap3 % 128 == 0)))
-    if engine in ("3xtf32", "tf32", "bf16x3", "bf16") and not tc_ok:
+    if engine in ("3xtf32", "tf32", "bf16x3", "bf16", "f16x3") and not tc_ok:
         with pytest.raises(_lib.GrafpError):
             ops.linear(a1.to(DEV), lin, act, 0.2, res.to(DEV) if use_res else None,
                        a2.to(DEV) if k2 else None, tap3, eng)
@@ -325,11 +325,15 @@ def test_gemm_engines(case, engine):
     # k=2048, 3.0e-5 at k=4096) -> 5e-5.  Single-pass TF32: 2e-3.
     # bf16x3 (the default tensor-core engine): <= 3 * 2^-18 per product + the same accumulator bias -> 5e-5.
     # Plain bf16 operands: 1e-2.
+    # f16x3 (the default tensor-core engine since ABI 4): ~3 * 2^-24 per product, so only the accumulator bias
+    # is left: 4e-6 + 1.2e-8 per k element (measured: see profiles/r2*_parity.json).
     tol = {"tf32": 2e-3, "bf16": 1e-2, "simt": 1e-5}.get(engine, 5e-5)
+    if engine in ("f16x3", "auto") and tc_ok:
+        tol = 4e-6 + 1.2e-8 * (k1 + k2)
     assert err < tol, "engine %s rel err %.3g" % (engine, err)
 
 
-@pytest.mark.parametrize("engine", ["bf16x3", "bf16", "auto"])
+@pytest.mark.parametrize("engine", ["bf16x3", "bf16", "f16x3", "auto"])
 @pytest.mark.parametrize("M,k,hid,n,groups", [(640, 64, 256, 64, 1), (300, 256, 1024, 256, 1), (130, 512, 2048, 512, 1),
                                               (1000, 64, 128, 64, 4), (128 * 5 + 7, 128, 512, 128, 1)])
 def test_gemm_split_bf16_activations_bit_exact(M, k, hid, n, groups, engine):
@@ -351,9 +355,10 @@ def test_gemm_split_bf16_activations_bit_exact(M, k, hid, n, groups, engine):
     h32 = ops.linear(a, l1, "relu", 0.0, engine=eng)
     hs = ops.linear(a, l1, "relu", 0.0, engine=eng, out_split=True)
     planes = 1 if engine == "bf16" else 2                 # the 1-pass engine carries the hi plane only
-    assert isinstance(hs, ops.SplitAct) and hs.t.shape == (planes, M, groups * hid) and hs.t.dtype == torch.bfloat16
-    hi = h32.bfloat16()
-    lo = (h32 - hi.float()).bfloat16()
+    dt = torch.float16 if engine in ("f16x3", "auto") else torch.bfloat16    # fp16 planes on the f16x3 engine
+    assert isinstance(hs, ops.SplitAct) and hs.t.shape == (planes, M, groups * hid) and hs.t.dtype == dt
+    hi = h32.to(dt)
+    lo = (h32 - hi.float()).to(dt)
     assert torch.equal(hs.t[0], hi) and (planes == 1 or torch.equal(hs.t[1], lo))
     y32 = ops.linear(h32, l2, None, 0.0, res, engine=eng)
     ys = ops.linear(hs, l2, None, 0.0, res, engine=eng)
@@ -362,8 +367,8 @@ def test_gemm_split_bf16_activations_bit_exact(M, k, hid, n, groups, engine):
     # GEMM's operand); both bit-identical to the single-output launches
     yb32, ybs = ops.linear(hs, l2, None, 0.0, res, engine=eng, out_split="both")
     assert torch.equal(yb32, y32)
-    yh = y32.bfloat16()
-    assert torch.equal(ybs.t[0], yh) and (planes == 1 or torch.equal(ybs.t[1], (y32 - yh.float()).bfloat16()))
+    yh = y32.to(dt)
+    assert torch.equal(ybs.t[0], yh) and (planes == 1 or torch.equal(ybs.t[1], (y32 - yh.float()).to(dt)))
 
 
 @pytest.mark.parametrize("B,N,C,k,groups", [(5, 256, 64, 3, 1), (9, 128, 128, 3, 4), (7, 64, 256, 5, 4), (11, 32, 512, 3, 4),
@@ -385,13 +390,15 @@ def test_gemm_fused_max_relative_bit_exact(B, N, C, k, groups, out_split):
     shift = synth.synth_uniform((n_out,), 73, -0.5, 0.5).to(DEV)
     lin = _prep.make_linear(w, scale, shift, groups, dual=True)
     os.environ["GRAFP_FUSED_MR"] = "1"
+    ops._engine_override = "bf16x3"             # the fused gather exists on the bf16 engines only
     try:
         assert ops.fused_mr_ok(lin, C)
+        m = ops.mr_aggregate(x, idx, B, N)
+        want = ops.linear(x, lin, "relu", 0.0, a2=m, out_split=out_split)
+        got = ops.linear(x, lin, "relu", 0.0, out_split=out_split, a2_gather=(idx, N))
     finally:
         del os.environ["GRAFP_FUSED_MR"]
-    m = ops.mr_aggregate(x, idx, B, N)
-    want = ops.linear(x, lin, "relu", 0.0, a2=m, out_split=out_split)
-    got = ops.linear(x, lin, "relu", 0.0, out_split=out_split, a2_gather=(idx, N))
+        ops._engine_override = None
     if out_split:
         assert torch.equal(got.t, want.t)
     else:

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in sorted(declared):
         assert hasattr(handle, name), "library does not export %s" % name
     assert declared == set(lib.exported_symbols()), declared ^ set(lib.exported_symbols())
-    assert handle.grafp_abi_version() == 3
+    assert handle.grafp_abi_version() == 4
 
 
 def test_library_is_sm100a_with_tcgen05_and_tma(lib):
