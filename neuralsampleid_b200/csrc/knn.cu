@@ -190,11 +190,18 @@ int knn_tc_supported(int B, int N, int C, int kk);
 size_t knn_tc_workspace_bytes(int B, int N);
 int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int normalize,
                   const float* row_sumsq, int32_t* idx, float* dist, float* workspace, cudaStream_t st);
+// large graphs / long lists (knn_big.cu): N in {256, 512, ..., 2048}, k*d <= 64
+int knn_big_supported(int B, int N, int C, int kk);
+size_t knn_big_workspace_bytes(int B, int N);
+int knn_big_launch(const float* x, int B, int N, int C, int kk, int d, int k, int normalize, int32_t* idx,
+                   float* dist, void* workspace, cudaStream_t st);
 }  // namespace grafp
 
 extern "C" size_t grafp_knn_workspace_bytes(int B, int N, int C, int k, int dilation) {
   if (B <= 0 || N <= 0 || C <= 0 || k <= 0 || dilation <= 0) return 0;
-  return knn_tc_supported(B, N, C, k * dilation) ? knn_tc_workspace_bytes(B, N) : 0;
+  if (knn_tc_supported(B, N, C, k * dilation)) return knn_tc_workspace_bytes(B, N);
+  if (knn_big_supported(B, N, C, k * dilation)) return knn_big_workspace_bytes(B, N);
+  return 0;
 }
 
 extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dilation,
@@ -210,13 +217,18 @@ extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dil
   cudaStream_t st = as_stream(stream);
   const bool tc_ok = knn_tc_supported(B, N, C, kk) && workspace &&
                      workspace_bytes >= knn_tc_workspace_bytes(B, N);
+  const bool big_ok = !tc_ok && knn_big_supported(B, N, C, kk) && workspace &&
+                      workspace_bytes >= knn_big_workspace_bytes(B, N);
   if (engine == GRAFP_ENGINE_TC_3XTF32) {
-    GRAFP_REQUIRE(tc_ok, "knn: tcgen05 engine needs N in {16..128 | 128, 256}, C %% 32 == 0, k*d <= 16 "
-                         "and a workspace of grafp_knn_workspace_bytes()");
+    GRAFP_REQUIRE(tc_ok || big_ok, "knn: the tcgen05 engines need (N in {16..128 | 128, 256}, C %% 32 == 0, k*d <= 16) or "
+                                   "(N in {256, 512, ..., 2048}, C %% 16 == 0, k*d <= 64), and a workspace of "
+                                   "grafp_knn_workspace_bytes()");
   }
   if ((engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_TC_3XTF32) && tc_ok)
     return knn_tc_launch(x, B, N, C, kk, dilation, k, normalize, row_sumsq, idx_out, dist_out,
                          static_cast<float*>(workspace), st);
+  if ((engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_TC_3XTF32) && big_ok)
+    return knn_big_launch(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out, workspace, st);
   GRAFP_REQUIRE(engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_SIMT, "knn: unknown engine %d", engine);
   if (N <= 16) return knn_launch<1>(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out, st);
   if (N <= 32) return knn_launch<2>(x, B, N, C, kk, dilation, k, normalize, idx_out, dist_out, st);

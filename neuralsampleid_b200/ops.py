@@ -106,6 +106,14 @@ def knn(x: torch.Tensor, B: int, N: int, k: int, dilation: int = 1, normalize: b
     return (idx, dist) if return_dist else idx
 
 
+def knn_engine(B: int, N: int, Cc: int, k: int, dilation: int = 1) -> str:
+    """Which kernel family ``knn`` runs for this shape under the default engine: "tcgen05" (knn_tc.cu / knn_big.cu:
+    the library asks for a workspace) or "simt" (the exact fp32 kernel)."""
+    if _engine == _lib.ENGINE_SIMT:
+        return "simt"
+    return "tcgen05" if int(_lib.load().grafp_knn_workspace_bytes(B, N, Cc, k, dilation)) > 0 else "simt"
+
+
 def mr_aggregate(x: torch.Tensor, idx: torch.Tensor, B: int, N: int, want_arg: bool = False):
     """m[n, c] = max_k (x[idx[n, k], c] - x[n, c]);  optional uint8 arg-max ranks."""
     x = _chk(x, name="x")

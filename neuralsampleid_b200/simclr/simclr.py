@@ -44,7 +44,10 @@ class SimCLR(nn.Module):
             if self.encoder.training:
                 raise RuntimeError("call .eval() for inference (BatchNorm statistics)")
             nodes, N = self.peak_extractor.forward_nodes(x)
-            h = self.encoder.forward_nodes(nodes, x.shape[0], N)
+            taps = [] if getattr(self, "_taps", None) is not None else None      # parity-test hook
+            h = self.encoder.forward_nodes(nodes, x.shape[0], N, forced_idx=forced_idx, taps=taps)
+            if taps is not None:
+                self._taps.append(taps)
             return h, self._project(h)
         from ..autograd import simclr_view_train
         return simclr_view_train(self, x, forced_idx)

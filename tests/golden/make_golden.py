@@ -145,9 +145,19 @@ def capture_simclr(ref, k, B, training):
     s_j = s_i + 0.1 * synth.synth_normal((B, cfg["n_mels"], cfg["n_frames"]), 22)
     out = {"weights_sha256": np.array(synth.state_sha256(sd))}
     if not training:
+        # per-block neighbour lists of both views (the encoder runs twice: view i, then view j)
+        calls = []
+        for m in enc.backbone:
+            if not hasattr(m, "conv"):
+                m[0].graph_conv.dilated_knn_graph.register_forward_hook(
+                    lambda mod, inp, res: calls.append(res[0].detach().clone()))
         with torch.no_grad():
             h_i, h_j, z_i, z_j = model(s_i, s_j)
-        out.update(h_i=h_i.numpy(), z_i=z_i.numpy(), z_j=z_j.numpy())
+        nb = len(calls) // 2
+        for b in range(nb):
+            out["idx_i_%d" % b] = calls[b].numpy().astype(np.int16)
+            out["idx_j_%d" % b] = calls[nb + b].numpy().astype(np.int16)
+        out.update(h_i=h_i.numpy(), h_j=h_j.numpy(), z_i=z_i.numpy(), z_j=z_j.numpy())
         return out
     h_i, h_j, z_i, z_j = model(s_i, s_j)
     loss = ref.ntxent_loss(z_i, z_j, cfg)
@@ -181,6 +191,9 @@ def capture_simclr(ref, k, B, training):
 def main():
     torch.set_num_threads(1)          # single-thread reductions: reproducible fixtures
     ref = import_reference()
+    if "--only-simclr-eval" in sys.argv:      # re-mint one fixture without touching the others
+        np.savez_compressed(os.path.join(HERE, "simclr_eval_b4.npz"), **capture_simclr(ref, 3, 4, False))
+        return
     g, relpos = capture_encoder(ref, k=3, B=4, x_seed=11)
     np.savez_compressed(os.path.join(HERE, "encoder_t_k3.npz"), **g)
     np.savez_compressed(os.path.join(HERE, "relative_pos_checksums.npz"),

@@ -22,7 +22,7 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 REL_TOL = 1e-3
-TIE_TOL = 1e-5
+TIE_TOL = 4e-6        # documented-tie window: adjacent reference distances within a few fp32 ulp at distance ~1
 CFG = dict(n_mels=64, n_frames=128, patch_bins=4, patch_frames=8, n_filters=8, tau=0.05,
            d=128, h=1024, u=32, dim=2048, arch="grafp", bsz_train=256, lr=8.0e-5)
 
@@ -82,7 +82,7 @@ def test_encoder_teacher_forced_and_free_running(k):
     assert tr.bad == 0, tr.log
     rel = _rel(got.cpu(), want)
     assert float(rel[tr.alive].max()) < REL_TOL
-    assert int(tr.alive.sum()) >= B // 3, "too many diverged segments: %s" % (tr.log,)
+    assert int(tr.alive.sum()) >= (2 * B) // 3, "too many diverged segments: %s" % (tr.log,)
 
 
 @pytest.mark.parametrize("fname,k", [("encoder_t_k3.npz", 3), ("encoder_t_k5.npz", 5)])
@@ -393,18 +393,77 @@ def test_simclr_eval_matches_golden(golden_dir):
     model = model.to(DEV).eval()
     s_i = synth.synth_normal((4, 64, 128), 21)
     s_j = s_i + 0.1 * synth.synth_normal((4, 64, 128), 22)
+    nb = 12
+    gold = [[torch.from_numpy(g["idx_%s_%d" % (v, b)].astype(np.int64)) for b in range(nb)] for v in "ij"]
+    # (1) the reference's own graphs forced: EVERY row of h and z agrees to REL_TOL
+    model._forced_idx = [[t.int().to(DEV) for t in gold[0]], [t.int().to(DEV) for t in gold[1]]]
     with torch.no_grad():
         h_i, h_j, z_i, z_j = model(s_i.to(DEV), s_j.to(DEV))
+    model._forced_idx = None
     assert h_i.shape == (4, 1024) and z_i.shape == (4, 128)
     assert torch.allclose(z_i.norm(dim=1).cpu(), torch.ones(4), atol=1e-5)
-    # no per-layer taps in this fixture: rows either agree to fp32 round-off or are tie-flip
-    # cascades (small); most rows must be tight
-    tight = 0
-    for got, want in ((h_i, g["h_i"]), (z_i, g["z_i"]), (z_j, g["z_j"])):
+    for got, want in ((h_i, g["h_i"]), (h_j, g["h_j"]), (z_i, g["z_i"]), (z_j, g["z_j"])):
         rel = _rel(got.cpu(), torch.from_numpy(want))
-        assert float(rel.max()) < 5e-2, rel
-        tight += int((rel < REL_TOL).sum())
-    assert tight >= 6, tight
+        assert float(rel.max()) < REL_TOL, rel
+    # (2) free running: per view, every block's neighbour lists equal the reference's except on documented ties
+    # (tie masks from the oracle's distances); segments whose graphs all matched agree to REL_TOL
+    model._taps = []
+    with torch.no_grad():
+        h_i, h_j, z_i, z_j = model(s_i.to(DEV), s_j.to(DEV))
+    taps, model._taps = model._taps, None
+    enc_sd = {n[len("encoder."):]: t for n, t in sd.items() if n.startswith("encoder.")}
+    alive_total = 0
+    for v, (spec, h, z, hname, zname) in enumerate(((s_i, h_i, z_i, "h_i", "z_i"), (s_j, h_j, z_j, "h_j", "z_j"))):
+        with torch.no_grad():
+            nodes = O.peak_extractor(sd, spec)
+            _, blocks = _oracle_run(enc_sd, nodes, 3)
+        tr = O.CascadeTracker(4)
+        for b in range(nb):
+            tr.update(b, taps[v][b]["idx"].cpu(), gold[v][b], blocks[b]["dist"], 3, TIE_TOL)
+        assert tr.bad == 0, (v, tr.log)
+        if tr.alive.any():
+            assert float(_rel(h.cpu(), torch.from_numpy(g[hname]))[tr.alive].max()) < REL_TOL
+            assert float(_rel(z.cpu(), torch.from_numpy(g[zname]))[tr.alive].max()) < REL_TOL
+        alive_total += int(tr.alive.sum())
+    assert alive_total >= 5, alive_total       # of 8 (measured on B200: see the flip-rate test below)
+
+
+def test_knn_flip_rate_is_reported_and_bounded():
+    """How often does a neighbour list differ from the oracle's, and at which reference gap?  512 segments, k = 3, every
+    block.  Teacher-forced (the oracle's graphs drive the features, this path's kNN runs on its own fc1 output) the
+    per-block fraction of differing rows is bounded and every differing row is a documented tie (adjacent reference
+    distances within TIE_TOL = 4e-6, i.e. a few fp32 ulp at distance ~1); free-running, no segment leaves the
+    reference trajectory off a documented tie and most segments never leave it.  Measured on B200 (f16x3 GEMMs +
+    3xTF32 Gram tiles; profiles/r2a_parity.json): <= 11 of 32768 rows per block (3.4e-4), 458 / 512 segments identical
+    through all 12 blocks -- the same as the exact-fp32 SIMT engines (461 / 512): the residue is fp32 round-off
+    against the reference's own matmul, not the tensor-core path."""
+    enc, sd = _encoder(3)
+    B = 512
+    x = synth.synth_uniform((B, 8, 256), 4242)
+    want, blocks = _oracle_run(sd, x, 3)
+    ops = __import__("neuralsampleid_b200.ops", fromlist=["ops"])
+    forced = [t["idx"].int().to(DEV) for t in blocks]
+    with torch.no_grad():
+        tf, fr = [], []
+        emb_f = enc(x.to(DEV), forced_idx=forced, taps=tf)
+        emb = enc(x.to(DEV), taps=fr)
+    report = []
+    for i, (t, o) in enumerate(zip(tf, blocks)):
+        N = o["idx"].shape[1]
+        idx = ops.knn(t["fc1"], B, N, 3, 1).cpu().long()
+        diff = (idx != o["idx"]).any(-1)
+        tie = O.knn_tie_rows(o["dist"], 3, TIE_TOL)
+        report.append((i, int(diff.sum()), diff.numel()))
+        assert not (diff & ~tie).any(), "block %d: %d off-tie rows" % (i, int((diff & ~tie).sum()))
+        assert float(diff.float().mean()) < 1e-3, "block %d flip rate %.2e" % (i, float(diff.float().mean()))
+    tr = O.CascadeTracker(B)
+    for i, (t, o) in enumerate(zip(fr, blocks)):
+        tr.update(i, t["idx"].cpu(), o["idx"], o["dist"], 3, TIE_TOL)
+    print("flip report (block, differing rows, rows):", report, "free-running alive %d / %d" % (int(tr.alive.sum()), B))
+    assert tr.bad == 0, tr.log
+    assert int(tr.alive.sum()) >= int(0.8 * B), int(tr.alive.sum())
+    assert float(_rel(emb_f.cpu(), want).max()) < REL_TOL
+    assert float(_rel(emb.cpu(), want)[tr.alive].max()) < REL_TOL
 
 
 def test_full_size_batch_properties():
