@@ -147,31 +147,60 @@ def mode_db(args):
 
 
 def mode_sweep(args):
+    """BASELINE configs[4] / SURVEY 8(d) config 5: k in {9,16,32} x N in {256,512,1024,2048}, C = 64, dilation 2,
+    B * N = 2^20 nodes.  Per point: kNN ms (+ its ratio to the 3-pass TF32 tensor ceiling of 2 N^2 C flops per graph),
+    aggregate ms + GB/s on algorithmic bytes, which kNN kernel family ran, and index parity of the first graphs against
+    the CPU oracle (rows that differ off documented ties: must be 0)."""
     from neuralsampleid_b200 import ops
+    from oracle import grafp_oracle as O
     world, rank, dev = _setup()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0 * 1e12          # dense tf32 = half the bf16 rate
+    hbm = peaks.get("hbm_gbs", 6650.0)
     rows = []
+    nodes = 1 << args.log2_nodes
     for N in (256, 512, 1024, 2048):
         for k in (9, 16, 32):
             for d in (2,):
-                B = (1 << 20) // N // 4               # 2^18 nodes per call (keeps every case < 1 s)
+                B = nodes // N
                 x = torch.randn((B * N, 64), device=dev, generator=torch.Generator(device=dev).manual_seed(4))
                 idx = ops.knn(x, B, N, k, d)
                 ops.mr_aggregate(x, idx, B, N)
                 torch.cuda.synchronize()
+                reps = 3
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 ev[0].record()
-                idx = ops.knn(x, B, N, k, d)
+                for _ in range(reps):
+                    idx = ops.knn(x, B, N, k, d)
                 ev[1].record()
-                m = ops.mr_aggregate(x, idx, B, N)
+                for _ in range(reps):
+                    m = ops.mr_aggregate(x, idx, B, N)
                 ev[2].record()
                 torch.cuda.synchronize()
-                t_knn, t_agg = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+                t_knn, t_agg = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
                 agg_bytes = B * (2 * N * 64 * 4 + 4 * N * k)
+                ceil_ms = 3.0 * 2.0 * N * N * 64 * B / tf32_peak * 1e3
+                # index parity of the first graphs against the oracle
+                gchk = 2
+                xs = x[:gchk * N].cpu().view(gchk, N, 64).transpose(1, 2).unsqueeze(-1).contiguous()
+                edge, dist = O.dilated_knn_graph(xs, k, d)
+                tie = O.knn_tie_rows(dist, k * d, 4e-6)
+                diff = (idx[:gchk].cpu().long() != edge[0]).any(-1)
                 rows.append({"N": N, "k": k, "d": d, "graphs": B, "knn_ms": round(t_knn, 3), "agg_ms": round(t_agg, 3),
+                             "knn_x_of_3xtf32_ceiling": round(t_knn / ceil_ms, 2), "knn_ceiling_ms": round(ceil_ms, 3),
                              "agg_GBps": round(agg_bytes / (t_agg * 1e-3) / 1e9, 1),
-                             "knn_engine": "tcgen05" if (N <= 256 and k * d <= 16) else "fp32 simt"})
+                             "agg_frac_of_hbm": round(agg_bytes / (t_agg * 1e-3) / 1e9 / hbm, 3),
+                             "knn_engine": ops.knn_engine(B, N, 64, k, d),
+                             "idx_parity": {"rows_checked": int(diff.numel()), "rows_differing": int(diff.sum()),
+                                            "off_tie_rows": int((diff & ~tie).sum())}})
+                del x, idx, m
     if rank == 0:
-        print(json.dumps({"mode": "sweep", "metric": "dynamic-graph stress sweep (C=64, dilation 2)", "rows": rows}))
+        print(json.dumps({"mode": "sweep", "metric": "dynamic-graph stress sweep (C=64, dilation 2)", "nodes": nodes,
+                          "rows": rows}))
 
 
 def mode_chunks(args):
@@ -234,6 +263,7 @@ def main():
     ap.add_argument("--segments", type=int, default=1000000)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--queries", type=int, default=2048)
+    ap.add_argument("--log2-nodes", type=int, default=20, help="sweep: B * N = 2^this nodes per point")
     args = ap.parse_args()
     with torch.no_grad():
         {"train": mode_train, "db": mode_db, "sweep": mode_sweep, "chunks": mode_chunks,

@@ -55,6 +55,99 @@ __device__ __forceinline__ uint32_t bf16_up_bits(float x) {
   return (x >= 0.0f) ? (b + 0xFFFFu) & 0xFFFF0000u : b & 0xFFFF0000u;
 }
 
+// ---- final exact selection: one warp per row --------------------------------------------------------------
+// A candidate is ordered by the 64-bit key (order-preserving image of the fp32 distance, local column index):
+// ascending keys = ascending (distance, lowest index first), the library's tie convention.
+__device__ __forceinline__ uint64_t knn_key(float2 e) {
+  const uint32_t b = __float_as_uint(e.x + 0.0f);                 // -0 -> +0
+  const uint32_t s = b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+  return ((uint64_t)s << 32) | (uint32_t)__float_as_int(e.y);
+}
+__device__ __forceinline__ float knn_key_dist(uint64_t k) {
+  const uint32_t s = (uint32_t)(k >> 32);
+  return __uint_as_float(s ^ ((s & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu));
+}
+constexpr uint64_t KNN_KEY_PAD = ~0ull;
+
+__device__ __forceinline__ void knn_emit(const KnnBigParams& p, int64_t row, int self, int rank, uint64_t key) {
+  if (rank < p.kk && (rank % p.d) == 0) {
+    const int64_t o = row * p.k + rank / p.d;
+    const bool empty = key == KNN_KEY_PAD;                        // NaN rows: fall back to the centre itself
+    p.idx[o] = empty ? self : (int)(uint32_t)key;
+    if (p.dist) p.dist[o] = empty ? INFINITY : knn_key_dist(key);
+  }
+}
+
+// Bitonic sort of the 32 * E candidate keys of one row held E per lane (element q * 32 + lane in register q);
+// the two half lists are concatenated, the padding sorts last.  Ranks 0, d, 2d, ... are written out.
+template <int E>
+__device__ __forceinline__ void sort_row(const float2* l0, int c0, const float2* l1, int c1, int lane,
+                                         const KnnBigParams& p, int64_t row, int self) {
+  uint64_t key[E];
+#pragma unroll
+  for (int q = 0; q < E; ++q) {
+    const int i = q * 32 + lane;
+    key[q] = KNN_KEY_PAD;
+    if (i < c0) key[q] = knn_key(__ldcg(l0 + i));
+    else if (i < c0 + c1) key[q] = knn_key(__ldcg(l1 + (i - c0)));
+  }
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int dq = j >> 5;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          if ((q & dq) == 0) {
+            const bool asc = (((q * 32) & k) == 0);              // bit k of the element index lives in q here
+            const uint64_t a = key[q], b = key[q | dq];
+            const bool sw = asc ? (a > b) : (a < b);
+            key[q] = sw ? b : a;
+            key[q | dq] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const uint64_t mine = key[q];
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, j);
+          const bool asc = (((q * 32 + lane) & k) == 0);
+          const bool lower = (lane & j) == 0;
+          const bool take_min = (asc == lower);
+          const uint64_t mn = mine < other ? mine : other, mx = mine < other ? other : mine;
+          key[q] = take_min ? mn : mx;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < E; ++q) knn_emit(p, row, self, q * 32 + lane, key[q]);
+}
+
+// more than 512 candidates (mass ties, e.g. an all-zero input): kk rounds of warp-wide minimum extraction
+// straight from the lists
+__device__ __noinline__ void extract_row(const float2* l0, int c0, const float2* l1, int c1, int lane,
+                                         const KnnBigParams& p, int64_t row, int self) {
+  uint64_t prev = 0;
+  bool first = true;
+  for (int rank = 0; rank < p.kk; ++rank) {
+    uint64_t best = KNN_KEY_PAD;
+    for (int i = lane; i < c0 + c1; i += 32) {
+      const uint64_t k = knn_key(i < c0 ? __ldcg(l0 + i) : __ldcg(l1 + (i - c0)));
+      if ((first || k > prev) && k < best) best = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    if (lane == 0) knn_emit(p, row, self, rank, best);
+    prev = best;
+    first = false;
+  }
+}
+
 template <int KH, int KMAX>
 __global__ void __launch_bounds__(KB_THREADS, 1)
 knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant__ CUtensorMap tmCols,
@@ -68,6 +161,7 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_sq[2][KB_BN];      // squared norms of the tile's column nodes, per TMEM buffer
   __shared__ int s_cnt[2][2][TC_BM];                  // [unit parity][half][row]: candidates appended
+  __shared__ float s_tau[2][TC_BM];                   // [half][row]: the two threads of a row exchange their bounds
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -79,6 +173,10 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
 
   const int nkb = p.C / KB_KBK;
   const int T = p.N / KB_BN;                               // column tiles per unit
+  // Every tile is contracted twice per unit when there is more than one: sweep 1 only derives the row's threshold,
+  // sweep 2 collects the candidates under it (the MMA is cheap next to the selection; a single tile stays in TMEM
+  // for both passes)
+  const int SU = T == 1 ? 1 : 2 * T;                       // MMA steps per unit
   const int64_t units = p.M / TC_BM;
 
   if (warp == 0 && lane == 0) {
@@ -107,7 +205,8 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
       uint32_t it = 0;
       for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
         const int64_t m0 = u * TC_BM, gs = (m0 / p.N) * p.N;
-        for (int t = 0; t < T; ++t) {
+        for (int su = 0; su < SU; ++su) {
+          const int t = su % T;
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1u;
@@ -125,7 +224,7 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
       const uint32_t idesc = umma_idesc_tf32(TC_BM, KB_BN);
       uint32_t it = 0, st = 0;
       for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        for (int t = 0; t < T; ++t, ++st) {
+        for (int su = 0; su < SU; ++su, ++st) {
           const uint32_t buf = st & 1u, tph = (st >> 1) & 1u;
           mbar_wait(&tmem_empty_bar[buf], tph ^ 1u);
           tc_fence_after();
@@ -163,8 +262,8 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
       float dn[6], ri[6];
       dn[0] = __ldg(p.den + m0 + rq);
       dn[1] = __ldg(p.den + m0 + rq + 64);
-      for (int tt = 0; tt < T; ++tt) {
-        const int64_t c0 = gs + (int64_t)tt * KB_BN;
+      for (int su = 0; su < SU; ++su) {
+        const int64_t c0 = gs + (int64_t)(su % T) * KB_BN;
 #pragma unroll
         for (int i = 2; i < 6; ++i) dn[i] = __ldg(p.den + c0 + rq + 64 * (i - 2));
 #pragma unroll
@@ -208,13 +307,12 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
     const int r = quad * 32 + lane;
     const int e = grp * 128 + r;                   // my slot when staging the column norms
     const int halfN = p.N >> 1;
-    const int h = (p.kk + 1) >> 1;                 // entries per threshold list
+    const int hq = (p.kk + 3) >> 2;                // entries per threshold list: four lists per row (two per thread)
     float2* cta_scratch = p.scratch + (size_t)blockIdx.x * 2u * TC_BM * 2u * (size_t)halfN;
     uint32_t st = 0, un = 0;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++un) {
       const int64_t m0 = u * TC_BM, gs = (m0 / p.N) * p.N;
       const int64_t grow = m0 + r;
-      const int self = (int)(grow - gs);
       const float sqi = __ldg(p.sq + grow);
       const uint32_t par = un & 1u;
       float2* my_list = cta_scratch + (((size_t)par * TC_BM + r) * 2u + grp) * (size_t)halfN;
@@ -225,17 +323,21 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
 #pragma unroll
         for (int i = 0; i < KH; ++i) tb[i] = *reinterpret_cast<const __nv_bfloat162*>(&inf2);
       }
-      float sq_next = __ldg(p.sq + gs + e);
-      for (int t = 0; t < T; ++t, ++st) {
+      float v[32];
+      float tau = INFINITY;
+      for (int su = 0; su < 2 * T; ++su) {
+        const int t = su % T;
+        const bool sweep2 = su >= T;
+        const bool fresh = !(T == 1 && sweep2);      // a single tile is kept in TMEM for both passes
         const uint32_t buf = st & 1u, tph = (st >> 1) & 1u;
-        s_sq[buf][e] = sq_next;
-        if (t + 1 < T) sq_next = __ldg(p.sq + gs + (int64_t)(t + 1) * KB_BN + e);
-        named_bar_sync(1, KB_EPI_THREADS);
+        if (fresh) {
+          s_sq[buf][e] = __ldg(p.sq + gs + (int64_t)t * KB_BN + e);
+          named_bar_sync(1, KB_EPI_THREADS);
+          mbar_wait(&tmem_full_bar[buf], tph);
+          tc_fence_after();
+        }
         const float4* sqv = reinterpret_cast<const float4*>(&s_sq[buf][grp * 128]);
-        mbar_wait(&tmem_full_bar[buf], tph);
-        tc_fence_after();
         const uint32_t tacc = tmem_base + buf * (uint32_t)KB_BN + (uint32_t)(grp * 128) + ((uint32_t)(quad * 32) << 16);
-        float v[32];
         auto load_dist = [&](int c) {
           tmem_ld16_nowait(tacc + (uint32_t)c, v);
           tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
@@ -249,118 +351,90 @@ knn_big_kernel(const __grid_constant__ CUtensorMap tmRows, const __grid_constant
             v[q4 + 3] = __fadd_rn(fmaf(v[q4 + 3], -2.0f, sqi), s4.w);
           }
         };
-        auto push2 = [&](float a, float b) {
-          const uint32_t pk = __byte_perm(bf16_up_bits(a), bf16_up_bits(b), 0x7632);
-          __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&pk);
+        if (!sweep2) {
+          // ---- sweep 1: group minima -> threshold lists ----
+          auto push2 = [&](float a, float b) {
+            const uint32_t pk = __byte_perm(bf16_up_bits(a), bf16_up_bits(b), 0x7632);
+            __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&pk);
 #pragma unroll
-          for (int i = 0; i < KH; ++i) {
-            const __nv_bfloat162 lo = __hmin2(tb[i], x);
-            x = __hmax2(tb[i], x);
-            tb[i] = lo;
+            for (int i = 0; i < KH; ++i) {
+              const __nv_bfloat162 lo = __hmin2(tb[i], x);
+              x = __hmax2(tb[i], x);
+              tb[i] = lo;
+            }
+          };
+          for (int c = 0; c < 128; c += 32) {
+            load_dist(c);
+            float m4[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+              m4[b] = fminf(fminf(v[4 * b], v[4 * b + 1]), fminf(v[4 * b + 2], v[4 * b + 3]));
+            if (p.gsel == 4) {
+              push2(m4[0], m4[1]); push2(m4[2], m4[3]); push2(m4[4], m4[5]); push2(m4[6], m4[7]);
+            } else if (p.gsel == 8) {
+              push2(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+              push2(fminf(m4[4], m4[5]), fminf(m4[6], m4[7]));
+            } else {
+              push2(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+            }
           }
-        };
-        // ---- pass 1: group minima -> threshold lists ----
-        for (int c = 0; c < 128; c += 32) {
-          load_dist(c);
-          float m4[8];
+          if (t == T - 1) {
+            // the row's threshold: each of its four lists (two per thread, two threads per row) holds the minima of
+            // disjoint column groups, so the max of their ceil(kk/4)-th smallest entries has >= kk distances under it
+            float mine = INFINITY;
 #pragma unroll
-          for (int b = 0; b < 8; ++b)
-            m4[b] = fminf(fminf(v[4 * b], v[4 * b + 1]), fminf(v[4 * b + 2], v[4 * b + 3]));
-          if (p.gsel == 4) {
-            push2(m4[0], m4[1]); push2(m4[2], m4[3]); push2(m4[4], m4[5]); push2(m4[6], m4[7]);
-          } else if (p.gsel == 8) {
-            push2(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
-            push2(fminf(m4[4], m4[5]), fminf(m4[6], m4[7]));
-          } else {
-            push2(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+            for (int i = 0; i < KH; ++i)
+              if (i == hq - 1) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(&tb[i]);
+                mine = fmaxf(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+              }
+            s_tau[grp][r] = mine;
+            named_bar_sync(1, KB_EPI_THREADS);
+            tau = fmaxf(mine, s_tau[grp ^ 1][r]);
+          }
+        } else {
+          // ---- sweep 2: append every distance <= tau to my candidate list (global scratch, L2 resident) ----
+          const int jl0 = t * KB_BN + grp * 128;
+          for (int c = 0; c < 128; c += 32) {
+            load_dist(c);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              uint32_t bump;
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t"
+                  "setp.le.f32 p, %2, %3;\n\t"
+                  "@p st.global.v2.b32 [%1], {%4, %5};\n\t"
+                  "selp.u32 %0, 1, 0, p;\n\t}"
+                  : "=r"(bump)
+                  : "l"(wp), "f"(v[q]), "f"(tau), "r"(__float_as_uint(v[q])), "r"(jl0 + c + q)
+                  : "memory");
+              wp += bump;
+            }
           }
         }
-        float tau = INFINITY;
-#pragma unroll
-        for (int i = 0; i < KH; ++i)
-          if (i == h - 1) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(&tb[i]);
-            tau = fmaxf(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
-          }
-        // ---- pass 2: append every distance <= tau to my candidate list (global scratch, L2 resident) ----
-        const int jl0 = t * KB_BN + grp * 128;
-        for (int c = 0; c < 128; c += 32) {
-          load_dist(c);
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            uint32_t bump;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.le.f32 p, %2, %3;\n\t"
-                "@p st.global.v2.b32 [%1], {%4, %5};\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(bump)
-                : "l"(wp), "f"(v[q]), "f"(tau), "r"(__float_as_uint(v[q])), "r"(jl0 + c + q)
-                : "memory");
-            wp += bump;
-          }
+        if (T > 1 || sweep2) {                        // done with this accumulator
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[buf]);
+          ++st;
         }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[buf]);
       }
-      // ---- end of the unit: publish my count, then group 0 sorts the unit's rows while group 1 moves on ----
+      // ---- end of the unit: publish my count; then the eight warps sort 16 rows each (warp per row) ----
       s_cnt[par][grp][r] = (int)(wp - my_list);
       __threadfence_block();
       named_bar_sync(1, KB_EPI_THREADS);
-      if (grp == 0) {
-        const int c0 = s_cnt[par][0][r], c1 = s_cnt[par][1][r];
-        const float2* l0 = my_list;
-        const float2* l1 = my_list + halfN;
-        int cmax = max(c0, c1);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-        float lbd = -INFINITY;
-        int lbj = -1;
-        for (int round = 0; round * KMAX < p.kk; ++round) {
-          float bd[KMAX];
-          int bj[KMAX];
-#pragma unroll
-          for (int i = 0; i < KMAX; ++i) { bd[i] = INFINITY; bj[i] = 0x7fffffff; }
-          // exact ascending (distance, index) insertion of the candidates strictly after (lbd, lbj)
-          auto insert = [&](float dv, int jl) {
-            bool lt[KMAX];
-#pragma unroll
-            for (int i = 0; i < KMAX; ++i) lt[i] = (dv < bd[i]) || (dv == bd[i] && jl < bj[i]);
-#pragma unroll
-            for (int i = KMAX - 1; i > 0; --i) {
-              bd[i] = lt[i - 1] ? bd[i - 1] : (lt[i] ? dv : bd[i]);
-              bj[i] = lt[i - 1] ? bj[i - 1] : (lt[i] ? jl : bj[i]);
-            }
-            bd[0] = lt[0] ? dv : bd[0];
-            bj[0] = lt[0] ? jl : bj[0];
-          };
-          for (int i = 0; i < cmax; i += 2) {
-            float2 cand[4];
-            cand[0] = (i < c0) ? __ldcg(l0 + i) : make_float2(INFINITY, __int_as_float(0x7fffffff));
-            cand[1] = (i + 1 < c0) ? __ldcg(l0 + i + 1) : make_float2(INFINITY, __int_as_float(0x7fffffff));
-            cand[2] = (i < c1) ? __ldcg(l1 + i) : make_float2(INFINITY, __int_as_float(0x7fffffff));
-            cand[3] = (i + 1 < c1) ? __ldcg(l1 + i + 1) : make_float2(INFINITY, __int_as_float(0x7fffffff));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float dv = cand[q].x;
-              const int jl = __float_as_int(cand[q].y);
-              const bool after = (dv > lbd) || (dv == lbd && jl > lbj);
-              insert(after ? dv : INFINITY, after ? jl : 0x7fffffff);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < KMAX; ++i) {
-            const int rank = round * KMAX + i;
-            if (rank < p.kk && (rank % p.d) == 0) {
-              const int64_t o = grow * p.k + rank / p.d;
-              const bool empty = bj[i] == 0x7fffffff;               // NaN rows: fall back to the centre itself
-              p.idx[o] = empty ? self : bj[i];
-              if (p.dist) p.dist[o] = bd[i];
-            }
-          }
-          lbd = bd[KMAX - 1];
-          lbj = bj[KMAX - 1];
-        }
+      for (int rr = ew * 16; rr < ew * 16 + 16; ++rr) {
+        const int c0 = s_cnt[par][0][rr], c1 = s_cnt[par][1][rr];
+        const float2* l0 = cta_scratch + (((size_t)par * TC_BM + rr) * 2u) * (size_t)halfN;
+        const float2* l1 = l0 + halfN;
+        const int64_t orow = m0 + rr;
+        const int oself = (int)(orow - gs);
+        const int c = c0 + c1;
+        if (c <= 32) sort_row<1>(l0, c0, l1, c1, lane, p, orow, oself);
+        else if (c <= 64) sort_row<2>(l0, c0, l1, c1, lane, p, orow, oself);
+        else if (c <= 128) sort_row<4>(l0, c0, l1, c1, lane, p, orow, oself);
+        else if (c <= 256) sort_row<8>(l0, c0, l1, c1, lane, p, orow, oself);
+        else if (c <= 512) sort_row<16>(l0, c0, l1, c1, lane, p, orow, oself);
+        else extract_row(l0, c0, l1, c1, lane, p, orow, oself);
       }
     }
   }
@@ -449,10 +523,10 @@ int knn_big_launch(const float* x, int B, int N, int C, int kk, int d, int k, in
   p.N = N; p.C = C; p.kk = kk; p.d = d; p.k = k; p.M = M;
   p.den = den; p.sq = sq; p.idx = idx; p.dist = dist;
   p.scratch = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace) + norms);
-  // columns per minimum group: the largest of 16 / 8 / 4 that still gives each thread (N/2 columns) at least
-  // 2 * kk minima, i.e. twice the entries the two threshold lists need
-  const int cols = N / 2;
-  p.gsel = (cols / 16 >= 2 * kk) ? 16 : (cols / 8 >= 2 * kk) ? 8 : 4;
+  // columns per minimum group: the largest of 16 / 8 / 4 that still feeds each of a thread's two threshold lists
+  // (N/2 columns per thread -> N / (4 g) minima per list) four times the ceil(kk/4) entries it keeps
+  const int hq = (kk + 3) / 4;
+  p.gsel = (N / 64 >= 4 * hq) ? 16 : (N / 32 >= 4 * hq) ? 8 : 4;
   {
     static int g_env = -1;
     if (g_env < 0) { const char* e = getenv("GRAFP_KNN_BIG_G"); g_env = e ? atoi(e) : 0; }
@@ -464,9 +538,9 @@ int knn_big_launch(const float* x, int B, int N, int C, int kk, int d, int k, in
   const int64_t units = M / TC_BM;
   int grid = sm_count();
   if (units < grid) grid = (int)units;
-  if (kk <= 16) return knn_big_launch_t<8, 16>(mr, mc, p, grid, st);
-  if (kk <= 32) return knn_big_launch_t<16, 32>(mr, mc, p, grid, st);
-  return knn_big_launch_t<32, 32>(mr, mc, p, grid, st);
+  if (kk <= 16) return knn_big_launch_t<4, 0>(mr, mc, p, grid, st);
+  if (kk <= 32) return knn_big_launch_t<8, 0>(mr, mc, p, grid, st);
+  return knn_big_launch_t<16, 0>(mr, mc, p, grid, st);
 }
 
 }  // namespace grafp
