@@ -192,7 +192,7 @@ int knn_tc_launch(const float* x, int B, int N, int C, int kk, int d, int k, int
                   const float* row_sumsq, int32_t* idx, float* dist, float* workspace, cudaStream_t st);
 // large graphs / long lists (knn_big.cu): N in {256, 512, ..., 2048}, k*d <= 64
 int knn_big_supported(int B, int N, int C, int kk);
-size_t knn_big_workspace_bytes(int B, int N);
+size_t knn_big_workspace_bytes(int B, int N, int C);
 int knn_big_launch(const float* x, int B, int N, int C, int kk, int d, int k, int normalize, int32_t* idx,
                    float* dist, void* workspace, cudaStream_t st);
 }  // namespace grafp
@@ -200,7 +200,7 @@ int knn_big_launch(const float* x, int B, int N, int C, int kk, int d, int k, in
 extern "C" size_t grafp_knn_workspace_bytes(int B, int N, int C, int k, int dilation) {
   if (B <= 0 || N <= 0 || C <= 0 || k <= 0 || dilation <= 0) return 0;
   if (knn_tc_supported(B, N, C, k * dilation)) return knn_tc_workspace_bytes(B, N);
-  if (knn_big_supported(B, N, C, k * dilation)) return knn_big_workspace_bytes(B, N);
+  if (knn_big_supported(B, N, C, k * dilation)) return knn_big_workspace_bytes(B, N, C);
   return 0;
 }
 
@@ -217,8 +217,9 @@ extern "C" int grafp_knn_fwd(const float* x, int B, int N, int C, int k, int dil
   cudaStream_t st = as_stream(stream);
   const bool tc_ok = knn_tc_supported(B, N, C, kk) && workspace &&
                      workspace_bytes >= knn_tc_workspace_bytes(B, N);
-  const bool big_ok = !tc_ok && knn_big_supported(B, N, C, kk) && workspace &&
-                      workspace_bytes >= knn_big_workspace_bytes(B, N);
+  // (un-normalised rows could leave the fp16 range of the large-graph kernel's operand planes: exact SIMT kernel)
+  const bool big_ok = !tc_ok && normalize && knn_big_supported(B, N, C, kk) && workspace &&
+                      workspace_bytes >= knn_big_workspace_bytes(B, N, C);
   if (engine == GRAFP_ENGINE_TC_3XTF32) {
     GRAFP_REQUIRE(tc_ok || big_ok, "knn: the tcgen05 engines need (N in {16..128 | 128, 256}, C %% 32 == 0, k*d <= 16) or "
                                    "(N in {256, 512, ..., 2048}, C %% 16 == 0, k*d <= 64), and a workspace of "

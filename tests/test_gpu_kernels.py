@@ -100,7 +100,7 @@ def test_knn_stress_sweep_points_on_tensor_cores(k, N):
 
 def test_knn_big_duplicates_zeros_and_other_widths():
     """knn_big.cu edge cases: exact duplicates and all-zero nodes (mass exact ties: the candidate lists grow to the
-    whole graph), post-ReLU features, C in {16, 32, 128, 256}, k*d = 64 = the list limit, un-normalised input."""
+    whole graph), post-ReLU features, C in {32, 96, 128, 256}, k*d = 64 = the list limit, un-normalised input."""
     ops = _ops()
     x = torch.relu(synth.synth_normal((2, 64, 512, 1), 17))
     x[:, :, 5] = x[:, :, 9]
@@ -109,13 +109,15 @@ def test_knn_big_duplicates_zeros_and_other_widths():
     assert ops.knn_engine(2, 512, 64, 9, 2) == "tcgen05"
     _knn_check(x, 9, 2)
     _knn_check(torch.zeros((1, 64, 256, 1)), 16, 2)                       # every distance ties
-    for C, N, k, d in ((16, 256, 17, 1), (32, 512, 8, 4), (128, 256, 32, 2), (256, 512, 5, 1), (64, 768, 6, 3)):
+    for C, N, k, d in ((96, 256, 17, 1), (32, 512, 8, 4), (128, 256, 32, 2), (256, 512, 5, 1), (64, 768, 6, 3)):
         assert ops.knn_engine(2, N, C, k, d) == "tcgen05"
         _knn_check(synth.synth_normal((2, C, N, 1), 600 + C + N), k, d)
     xn = torch.nn.functional.normalize(synth.synth_normal((2, 64, 512, 1), 18), dim=1)
     _knn_check(xn, 20, 1, normalize=False)
     # shapes neither tcgen05 kernel takes stay on the exact SIMT engine
     assert ops.knn_engine(1, 200, 64, 9, 2) == "simt" and ops.knn_engine(1, 512, 64, 40, 2) == "simt"
+    assert ops.knn_engine(1, 512, 16, 9, 2) == "simt"
+    _knn_check(synth.synth_normal((1, 16, 512, 1), 19), 9, 2)
 
 
 @pytest.mark.parametrize("engine", ["simt", "3xtf32"])
