@@ -310,10 +310,17 @@ int grafp_bn_bwd_apply(const float* dout, int64_t ldd, const float* raw, int64_t
 int grafp_bn_param_grad(const double* sum_dz, const double* sum_dz_xhat, int C, float* dgamma,
                         float* dbeta, void* stream);
 /* weight gradient  dw[g*n + j, :] += sum_m dy[m, g*n + j] * A_g[m, :]  (A_g as in grafp_gemm_fwd:
- * two sources, groups, tap3); dw (groups*n, k1+k2) accumulates (caller zeroes). */
+ * two sources, groups, tap3); dw (groups*n, k1+k2) accumulates (caller zeroes).
+ *   engine  GRAFP_ENGINE_AUTO: the tcgen05 kernel (3xTF32, the contraction over the rows m as MN-major operands, split
+ *           over m into TMEM accumulators, partial tiles reduced in a fixed order: deterministic, no atomics) when n,
+ *           k1, k2 are multiples of 32 (per group), tap3_nodes == 0 and a workspace is given; else the fp32 SIMT
+ *           kernel (split partials accumulated with atomics).  GRAFP_ENGINE_SIMT / GRAFP_ENGINE_TC_3XTF32 force one.
+ *   workspace  caller-owned scratch of grafp_gemm_wgrad_workspace_bytes() bytes (0 = shape not taken; may be NULL) */
+size_t grafp_gemm_wgrad_workspace_bytes(int64_t m, int n, int k1, int k2, int groups, int tap3_nodes);
 int grafp_gemm_wgrad(const float* dy, int64_t ldy, const float* a1, int64_t lda1, int k1,
                      const float* a2, int64_t lda2, int k2, int64_t m, int n, int groups,
-                     int tap3_nodes, float* dw, int64_t ldw, void* stream);
+                     int tap3_nodes, float* dw, int64_t ldw, int engine, void* workspace, size_t workspace_bytes,
+                     void* stream);
 /* Downsample input gradient: dA (rows, 3*cin) = dRaw W -> dX (2*rows, cin) */
 int grafp_tap3_bwd_input(const float* dA, int64_t rows, int rows_per_graph, int cin, float* dX,
                          void* stream);

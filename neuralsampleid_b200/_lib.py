@@ -77,7 +77,7 @@ SIGNATURES = {
     "grafp_bn_bwd_reduce": [_P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P],
     "grafp_bn_bwd_apply": [_P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _L, _P],
     "grafp_bn_param_grad": [_P, _P, _I, _P, _P, _P],
-    "grafp_gemm_wgrad": [_P, _L, _P, _L, _I, _P, _L, _I, _L, _I, _I, _I, _P, _L, _P],
+    "grafp_gemm_wgrad": [_P, _L, _P, _L, _I, _P, _L, _I, _L, _I, _I, _I, _P, _L, _I, _P, C.c_size_t, _P],
     "grafp_tap3_bwd_input": [_P, _L, _I, _I, _P, _P],
     "grafp_node_mean_bwd": [_P, _I, _I, _I, _P, _P],
     "grafp_l2_normalize_rows_bwd": [_P, _P, _L, _I, _F, _P, _P],
@@ -88,6 +88,7 @@ SIGNATURES = {
     "grafp_add_inplace": [_P, _P, _L, _P],
 }
 SPECIAL = {"grafp_knn_workspace_bytes": ([_I, _I, _I, _I, _I], C.c_size_t),
+           "grafp_gemm_wgrad_workspace_bytes": ([_L, _I, _I, _I, _I, _I], C.c_size_t),
            "grafp_abi_version": ([], C.c_int), "grafp_last_error": ([], C.c_char_p),
            "grafp_launch_count": ([], C.c_int64)}
 

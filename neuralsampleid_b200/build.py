@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgrafp_sm100a.so")
 SOURCES = ["misc.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "knn.cu", "knn_tc.cu", "knn_big.cu", "aggregate.cu",
-           "ntxent.cu", "train.cu", "attention.cu", "topk.cu", "frontend.cu"]
+           "ntxent.cu", "train.cu", "wgrad_tc.cu", "attention.cu", "topk.cu", "frontend.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v"]
 

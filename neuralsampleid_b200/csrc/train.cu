@@ -149,6 +149,13 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ s0, const double
   if (dbeta) dbeta[c] += (float)s0[c];
 }
 
+// tcgen05 engine (wgrad_tc.cu)
+int wgrad_tc_supported(int64_t m, int n, int k1, int k2, int groups, int tap3_nodes, int64_t ldy, int64_t lda1,
+                       int64_t lda2, int64_t ldw);
+size_t wgrad_tc_workspace_bytes(int64_t m, int n, int k1, int k2, int groups);
+int wgrad_tc_launch(const float* dy, int64_t ldy, const float* a1, int64_t lda1, int k1, const float* a2, int64_t lda2,
+                    int k2, int64_t m, int n, int groups, float* dw, int64_t ldw, float* workspace, cudaStream_t st);
+
 // ---- weight gradient: dW[g*n + j, kk] += sum_m dy[m, g*n + j] * A_g[m, kk] ------------------
 struct WgradP {
   const float* dy; int64_t ldy;
@@ -490,12 +497,34 @@ int grafp_bn_param_grad(const double* sum_dz, const double* sum_dz_xhat, int C, 
   return check_launch("bn_param_grad");
 }
 
+size_t grafp_gemm_wgrad_workspace_bytes(int64_t m, int n, int k1, int k2, int groups, int tap3_nodes) {
+  if (m <= 0 || n <= 0 || k1 <= 0 || k2 < 0 || groups <= 0) return 0;
+  // (row strides are checked at launch; packed operands are assumed for the query)
+  if (!grafp::wgrad_tc_supported(m, n, k1, k2, groups, tap3_nodes, 4, 4, 4, 4)) return 0;
+  return grafp::wgrad_tc_workspace_bytes(m, n, k1, k2, groups);
+}
+
 int grafp_gemm_wgrad(const float* dy, int64_t ldy, const float* a1, int64_t lda1, int k1,
                      const float* a2, int64_t lda2, int k2, int64_t m, int n, int groups,
-                     int tap3_nodes, float* dw, int64_t ldw, void* stream) {
+                     int tap3_nodes, float* dw, int64_t ldw, int engine, void* workspace, size_t workspace_bytes,
+                     void* stream) {
   GRAFP_REQUIRE(dy && a1 && dw && m > 0 && n > 0 && groups > 0 && k1 > 0 && k2 >= 0, "gemm_wgrad: bad arguments");
   GRAFP_REQUIRE(k1 % 4 == 0 && k2 % 4 == 0 && n % 4 == 0 && ldy % 4 == 0, "gemm_wgrad: sizes must be multiples of 4");
   GRAFP_REQUIRE((k2 == 0) == (a2 == nullptr), "gemm_wgrad: a2/k2 mismatch");
+  GRAFP_REQUIRE(engine == GRAFP_ENGINE_AUTO || engine == GRAFP_ENGINE_SIMT || engine == GRAFP_ENGINE_TC_3XTF32,
+                "gemm_wgrad: engine must be AUTO, SIMT or TC_3XTF32 (got %d)", engine);
+  {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(a1) |
+                           reinterpret_cast<uintptr_t>(a2) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0;
+    const bool tc_ok = aligned && grafp::wgrad_tc_supported(m, n, k1, k2, groups, tap3_nodes, ldy, lda1, lda2, ldw) &&
+                       workspace && workspace_bytes >= grafp::wgrad_tc_workspace_bytes(m, n, k1, k2, groups);
+    if (engine == GRAFP_ENGINE_TC_3XTF32)
+      GRAFP_REQUIRE(tc_ok, "gemm_wgrad: the tcgen05 engine needs n, k1, k2 multiples of 32, no tap3, 16-byte aligned "
+                           "operands and a workspace of grafp_gemm_wgrad_workspace_bytes()");
+    if (engine != GRAFP_ENGINE_SIMT && tc_ok)
+      return grafp::wgrad_tc_launch(dy, ldy, a1, lda1, k1, a2, lda2, k2, m, n, groups, dw, ldw,
+                                    static_cast<float*>(workspace), as_stream(stream));
+  }
   WgradP p;
   p.dy = dy; p.ldy = ldy; p.a1 = a1; p.lda1 = lda1; p.k1 = k1; p.a2 = a2; p.lda2 = lda2; p.k2 = k2;
   p.dw = dw; p.ldw = ldw; p.m = m; p.n = n; p.tap3_nodes = tap3_nodes;

@@ -593,8 +593,11 @@ def bn_param_grad(sums: torch.Tensor, want_gamma: bool, want_beta: bool):
 
 
 def gemm_wgrad(dy: torch.Tensor, a1: torch.Tensor, a2, n_total: int, groups: int = 1,
-               tap3_nodes: int = 0) -> torch.Tensor:
-    """dw (groups*n, k1+k2) = sum_m dy[m]^T A[m] (per group)."""
+               tap3_nodes: int = 0, engine: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dw (groups*n, k1+k2) = sum_m dy[m]^T A[m] (per group).  Default engine: the tcgen05 3xTF32 kernel where the
+    shape allows (deterministic split reduction), else the fp32 SIMT kernel; ``engine`` forces ENGINE_SIMT /
+    ENGINE_TC_3XTF32.  ``out``: accumulate into this (groups*n, k1+k2) fp32 view (row stride multiple of 4) instead
+    of a fresh zero tensor -- e.g. a slice of the flat gradient buffer."""
     dy = _chk(dy, name="dy")
     a1 = _chk(a1, name="a1")
     n = n_total // groups
@@ -605,11 +608,22 @@ def gemm_wgrad(dy: torch.Tensor, a1: torch.Tensor, a2, n_total: int, groups: int
         if a2 is not None:
             a2 = _chk(a2, name="a2")
             k2 = a2.shape[1] // groups
-    dw = torch.zeros((n_total, k1 + k2), device=dy.device, dtype=torch.float32)
+    if out is None:
+        dw = torch.zeros((n_total, k1 + k2), device=dy.device, dtype=torch.float32)
+    else:
+        dw = out
+        if dw.shape != (n_total, k1 + k2) or dw.stride(1) != 1 or dw.dtype != torch.float32 or not dw.is_cuda:
+            raise GrafpError("gemm_wgrad: out must be an fp32 CUDA (groups*n, k1+k2) view with unit column stride")
+    eng = _lib.ENGINE_AUTO if engine is None else engine
+    if engine is None and _effective_engine() == _lib.ENGINE_SIMT:
+        eng = _lib.ENGINE_SIMT
+    lib = _lib.load()
+    ws_bytes = int(lib.grafp_gemm_wgrad_workspace_bytes(M, n, k1, k2, groups, tap3_nodes)) if eng != _lib.ENGINE_SIMT else 0
+    ws = torch.empty((ws_bytes // 4,), device=dy.device, dtype=torch.float32) if ws_bytes else None
     with torch.cuda.device(dy.device):
-        check(_lib.load().grafp_gemm_wgrad(_ptr(dy), dy.stride(0), _ptr(a1), a1.stride(0), k1, _ptr(a2),
-                                           a2.stride(0) if a2 is not None else 0, k2, M, n, groups, tap3_nodes,
-                                           _ptr(dw), dw.stride(0), _stream(dy)), "gemm_wgrad")
+        check(lib.grafp_gemm_wgrad(_ptr(dy), dy.stride(0), _ptr(a1), a1.stride(0), k1, _ptr(a2),
+                                   a2.stride(0) if a2 is not None else 0, k2, M, n, groups, tap3_nodes,
+                                   _ptr(dw), dw.stride(0), eng, _ptr(ws), ws_bytes, _stream(dy)), "gemm_wgrad")
     return dw
 
 

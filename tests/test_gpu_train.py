@@ -35,6 +35,72 @@ def _inputs(B):
     return s_i, s_j
 
 
+WGRAD_CASES = [
+    # M, n, k1, k2, groups
+    (4096, 256, 64, 0, 1),        # FFN.fc1 stage 1
+    (4096, 64, 256, 0, 1),        # FFN.fc2 stage 1: n < 128 (half of the MMA tile is out of bounds)
+    (3000, 128, 64, 64, 1),       # MRConv stage 1 densified: two sources; m not a multiple of 32
+    (2048, 128, 64, 64, 4),       # MRConv stage 3: groups, two sources
+    (2048, 64, 64, 0, 4),         # groups with n = 64 per group: a 128-row MMA tile spans two groups' columns
+    (1024, 256, 128, 128, 4),     # MRConv stage 4
+    (777, 512, 2048, 0, 1),       # FFN.fc2 stage 4, ragged m
+    (64, 1024, 512, 0, 1),        # proj: fewer rows than one split
+    (33, 128, 4096, 0, 1),        # projector.2
+]
+
+
+@pytest.mark.parametrize("M,n,k1,k2,groups", WGRAD_CASES)
+def test_wgrad_engines_match_fp64(M, n, k1, k2, groups):
+    """grafp_gemm_wgrad on both engines against an fp64 restatement: dw[g*n + j, :] = sum_m dy[m, g*n + j] * [a1 | a2]_g.
+    The tcgen05 engine (bf16x3, MN-major operands, deterministic split reduction) must take every case, agree to
+    2e-5 of the gradient scale, be bit-reproducible run to run, and accumulate into a strided destination view."""
+    from neuralsampleid_b200 import _lib, ops
+    dy = synth.synth_normal((M, groups * n), 51)
+    a1 = synth.synth_normal((M, groups * k1), 52)
+    a2 = synth.synth_normal((M, groups * k2), 53) if k2 else None
+    want = torch.zeros((groups * n, k1 + k2), dtype=torch.float64)
+    for g in range(groups):
+        A = a1[:, g * k1:(g + 1) * k1].double()
+        if k2:
+            A = torch.cat([A, a2[:, g * k2:(g + 1) * k2].double()], dim=1)
+        want[g * n:(g + 1) * n] = dy[:, g * n:(g + 1) * n].double().T @ A
+    scale = float(want.abs().max())
+    assert int(_lib.load().grafp_gemm_wgrad_workspace_bytes(M, n, k1, k2, groups, 0)) > 0
+    args = (dy.to(DEV), a1.to(DEV), a2.to(DEV) if k2 else None, groups * n, groups, 0)
+    got = {}
+    for name in ("simt", "3xtf32"):
+        got[name] = ops.gemm_wgrad(*args, engine=_lib.ENGINES[name])
+        err = float((got[name].cpu().double() - want).abs().max()) / scale
+        assert err < 2e-5, (name, err)
+    again = ops.gemm_wgrad(*args, engine=_lib.ENGINES["3xtf32"])
+    assert torch.equal(again, got["3xtf32"])                       # no atomics: bit-reproducible
+    assert torch.equal(ops.gemm_wgrad(*args), got["3xtf32"])       # default engine = tcgen05 here
+    # accumulate into a column slice of a wider buffer (what the flat-gradient path does)
+    wide = torch.ones((groups * n, k1 + k2 + 8), device=DEV)
+    ops.gemm_wgrad(*args, out=wide[:, 4:4 + k1 + k2])
+    assert torch.equal(wide[:, 4:4 + k1 + k2], got["3xtf32"] + 1.0)
+    assert float(wide[:, :4].min()) == 1.0 and float(wide[:, -4:].max()) == 1.0
+
+
+def test_wgrad_shapes_outside_the_tensor_core_kernel_use_simt():
+    """k = 32 per source (stage-2 MRConv), the stem (k = 8) and the Downsample form stay on the fp32 SIMT kernel: no
+    workspace is requested, the default engine still returns the right gradient, the explicit tcgen05 engine fails."""
+    from neuralsampleid_b200 import _lib, ops
+    lib = _lib.load()
+    assert int(lib.grafp_gemm_wgrad_workspace_bytes(2048, 64, 32, 32, 4, 0)) == 0
+    assert int(lib.grafp_gemm_wgrad_workspace_bytes(2048, 64, 8, 0, 1, 0)) == 0
+    assert int(lib.grafp_gemm_wgrad_workspace_bytes(1024, 128, 192, 0, 1, 64)) == 0
+    dy, a1, a2 = synth.synth_normal((2048, 256), 54), synth.synth_normal((2048, 128), 55), synth.synth_normal((2048, 128), 56)
+    want = torch.zeros((256, 64), dtype=torch.float64)
+    for g in range(4):
+        A = torch.cat([a1[:, g * 32:(g + 1) * 32], a2[:, g * 32:(g + 1) * 32]], dim=1).double()
+        want[g * 64:(g + 1) * 64] = dy[:, g * 64:(g + 1) * 64].double().T @ A
+    got = ops.gemm_wgrad(dy.to(DEV), a1.to(DEV), a2.to(DEV), 256, 4, 0)
+    assert float((got.cpu().double() - want).abs().max()) < 2e-5 * float(want.abs().max())
+    with pytest.raises(_lib.GrafpError):
+        ops.gemm_wgrad(dy.to(DEV), a1.to(DEV), a2.to(DEV), 256, 4, 0, engine=_lib.ENGINES["3xtf32"])
+
+
 @pytest.mark.parametrize("act,use_bn,use_res,groups,dual", [
     ("relu", True, False, 1, False), (None, True, True, 1, False), ("relu", True, False, 4, True),
     ("elu", False, False, 1, False), ("leakyrelu", True, False, 1, False), ("gelu", True, True, 1, False)])
