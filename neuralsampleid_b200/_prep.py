@@ -18,6 +18,21 @@ def bump_epoch() -> None:
     _epoch += 1
 
 
+_wepoch = 0
+
+
+def bump_weights() -> None:
+    """Parameters themselves changed through raw pointers (fused optimizer step, CUDA-graph replay of a train step):
+    invalidates the eval path's prepared weights AND the train path's per-step operand cache."""
+    global _wepoch
+    _wepoch += 1
+    bump_epoch()
+
+
+def weights_epoch() -> int:
+    return _wepoch
+
+
 def sig(*tensors) -> tuple:
     """Cheap identity+version signature of parameters, used to invalidate prepared weights after
     optimizer steps / load_state_dict / .to()."""

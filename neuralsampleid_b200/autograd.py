@@ -36,13 +36,50 @@ def _w_split(w2d: torch.Tensor, groups: int, k_parts: int):
     return {}
 
 
+class GradSink(dict):
+    """A gradient dict with in-place destinations: ``views[p]`` is where the gradient of parameter p accumulates (a
+    slice of the fused optimizer's flat gradient buffer).  Kernels that accumulate (weight-gradient GEMM, BatchNorm
+    parameter gradients) write there directly; everything else is added with one grafp_add_inplace -- no per-parameter
+    temporaries and no second accumulation pass."""
+
+    def __init__(self, views):
+        super().__init__()
+        self.views = views
+
+    def view(self, p):
+        return self.views.get(p) if p is not None and p.requires_grad else None
+
+
+def _sink_view(grads, p):
+    return grads.view(p) if isinstance(grads, GradSink) else None
+
+
+# Per-step operand cache of the train path: derived weight layouts (MRConv even/odd regrouping, Downsample centre
+# column, transposes for the input gradient) and their tensor-core splits are functions of the parameters alone, and
+# both SimCLR views use the same parameters: built once per weight version instead of once per layer call.
+_WCACHE = {"epoch": -1, "items": {}}
+
+
+def _cached(param: torch.Tensor, tag, make):
+    ep = (_prep.weights_epoch(), ops.get_engine(), ops._engine_override)
+    if _WCACHE["epoch"] != ep:
+        _WCACHE["epoch"], _WCACHE["items"] = ep, {}
+    key = (param.data_ptr(), tuple(param.shape), tag)
+    hit = _WCACHE["items"].get(key)
+    if hit is None or hit[0] != param._version:        # a newer version replaces the entry: nothing accumulates
+        hit = (param._version, make())
+        _WCACHE["items"][key] = hit
+    return hit[1]
+
+
 def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: torch.Tensor, kind: str,
               bias: Optional[nn.Parameter] = None, bn: Optional[nn.BatchNorm2d] = None, act=None,
               slope: float = 0.0, residual: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
               groups: int = 1, tap3_nodes: int = 0) -> torch.Tensor:
     w2d = w2d.contiguous()
-    raw = ops.gemm(a1, w2d, None, None, None, 0.0, None, a2, groups, tap3_nodes, None, None,
-                   **_w_split(w2d, groups, 2 if a2 is not None else 1))
+    sp = _cached(weight, ("fwd", kind), lambda: (w2d, _w_split(w2d, groups, 2 if a2 is not None else 1)))
+    w2d = sp[0]
+    raw = ops.gemm(a1, w2d, None, None, None, 0.0, None, a2, groups, tap3_nodes, None, None, **sp[1])
     M, C = raw.shape
     if bn is not None:
         stats = ops.col_stats(raw)
@@ -72,6 +109,10 @@ def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: t
 
 def _acc(grads: Dict, p, g: torch.Tensor) -> None:
     if p is None or not p.requires_grad:
+        return
+    v = _sink_view(grads, p)
+    if v is not None:
+        ops.add_inplace(v, g.reshape(v.shape).contiguous())
         return
     g = g.reshape(p.shape)
     if p in grads:
@@ -103,35 +144,57 @@ def layer_bwd(L: _Layer, dout: torch.Tensor, grads: Dict, need_input: bool = Tru
     bn = L.bn is not None
     draw, sums = ops.bn_act_bwd(dout, L.raw, L.ssmi, L.act, L.slope, bn)
     if bn:
-        dg, db = ops.bn_param_grad(sums, True, True)
-        _acc(grads, L.bn.weight, dg)
-        _acc(grads, L.bn.bias, db)
+        vg, vb = _sink_view(grads, L.bn.weight), _sink_view(grads, L.bn.bias)
+        if vg is not None and vb is not None:
+            ops.bn_param_grad(sums, True, True, vg, vb)              # accumulates straight into the flat buffer
+        else:
+            dg, db = ops.bn_param_grad(sums, True, True)
+            _acc(grads, L.bn.weight, dg)
+            _acc(grads, L.bn.bias, db)
         # a conv bias in front of a train-mode BatchNorm has exactly zero gradient
-        if L.bias is not None and L.bias.requires_grad and L.bias not in grads:
+        if L.bias is not None and L.bias.requires_grad and L.bias not in grads and _sink_view(grads, L.bias) is None:
             grads[L.bias] = torch.zeros_like(L.bias)
     elif L.bias is not None:
-        _, db = ops.bn_param_grad(sums, False, True)
-        _acc(grads, L.bias, db)
+        vb = _sink_view(grads, L.bias)
+        if vb is not None:
+            ops.bn_param_grad(sums, False, True, None, vb)
+        else:
+            _, db = ops.bn_param_grad(sums, False, True)
+            _acc(grads, L.bias, db)
     if L.weight.requires_grad:
-        dw = ops.gemm_wgrad(draw, L.a1, L.a2, L.w2d.shape[0], L.groups, L.tap3_nodes)
-        _acc(grads, L.weight, _weight_grad_to_param(L, dw))
+        vw = _sink_view(grads, L.weight)
+        if vw is not None and L.kind == "dense":
+            # the GEMM-operand layout IS the parameter's: the kernel accumulates into the flat gradient buffer
+            ops.gemm_wgrad(draw, L.a1, L.a2, L.w2d.shape[0], L.groups, L.tap3_nodes, out=vw.view(L.w2d.shape))
+        else:
+            dw = ops.gemm_wgrad(draw, L.a1, L.a2, L.w2d.shape[0], L.groups, L.tap3_nodes)
+            _acc(grads, L.weight, _weight_grad_to_param(L, dw))
     if not need_input:
         return None, None
     n = L.w2d.shape[0] // L.groups
     if L.tap3_nodes:
         cin = L.k1 // 3
-        wT = L.w2d.t().contiguous()                                   # (3*Cin, Cout)
-        sp = _w_split(wT, 1, 1)
+
+        def make_t():
+            wT = L.w2d.t().contiguous()                               # (3*Cin, Cout)
+            return wT, _w_split(wT, 1, 1)
+        wT, sp = _cached(L.weight, ("T", L.kind), make_t)
         dA = ops.gemm(draw, wT, **sp)
         return ops.tap3_bwd_input(dA, L.tap3_nodes, cin), None
-    wg = L.w2d.view(L.groups, n, L.k1 + L.k2)
-    wT1 = wg[:, :, :L.k1].transpose(1, 2).reshape(L.groups * L.k1, n).contiguous()
-    sp = _w_split(wT1, L.groups, 1)
+
+    def make_t1():
+        wg = L.w2d.view(L.groups, n, L.k1 + L.k2)
+        wT1 = wg[:, :, :L.k1].transpose(1, 2).reshape(L.groups * L.k1, n).contiguous()
+        return wT1, _w_split(wT1, L.groups, 1)
+    wT1, sp = _cached(L.weight, ("T1", L.kind), make_t1)
     da1 = ops.gemm(draw, wT1, residual=add_to, groups=L.groups, **sp)
     da2 = None
     if L.k2:
-        wT2 = wg[:, :, L.k1:].transpose(1, 2).reshape(L.groups * L.k2, n).contiguous()
-        sp = _w_split(wT2, L.groups, 1)
+        def make_t2():
+            wg = L.w2d.view(L.groups, n, L.k1 + L.k2)
+            wT2 = wg[:, :, L.k1:].transpose(1, 2).reshape(L.groups * L.k2, n).contiguous()
+            return wT2, _w_split(wT2, L.groups, 1)
+        wT2, sp = _cached(L.weight, ("T2", L.kind), make_t2)
         da2 = ops.gemm(draw, wT2, groups=L.groups, **sp)
     return da1, da2
 
@@ -144,7 +207,7 @@ def _conv2d_w(conv: nn.Conv2d) -> torch.Tensor:
 
 
 class _EncTape:
-    __slots__ = ("layers", "blocks", "B", "N_out", "mean")
+    __slots__ = ("layers", "blocks", "B", "N_out", "mean", "enc")
 
 
 def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int, forced_idx=None):
@@ -152,7 +215,7 @@ def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int, forced_idx=Non
     ``forced_idx``: optional per-block int32 (B, N, k) neighbour lists (parity-test hook)."""
     from .encoder.graph_encoder import Downsample
     tape = _EncTape()
-    tape.layers, tape.blocks, tape.B = [], [], B
+    tape.layers, tape.blocks, tape.B, tape.enc = [], [], B, enc
     Ls = tape.layers
     stem = enc.stem
     h = layer_fwd(Ls, x_nodes, stem[0].weight, _conv2d_w(stem[0]), "dense", None, stem[1], "leakyrelu",
@@ -161,8 +224,8 @@ def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int, forced_idx=Non
     for entry in enc.backbone:
         if isinstance(entry, Downsample):
             conv, bn = entry.conv[0], entry.conv[1]
-            h = layer_fwd(Ls, h, conv.weight, tap3_weight(conv.weight), "tap3", conv.bias, bn,
-                          tap3_nodes=N // 2)
+            h = layer_fwd(Ls, h, conv.weight, _cached(conv.weight, "tap3w", lambda: tap3_weight(conv.weight)), "tap3",
+                          conv.bias, bn, tap3_nodes=N // 2)
             N //= 2
             tape.blocks.append(("down", 1))
             continue
@@ -176,8 +239,7 @@ def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int, forced_idx=Non
         m, arg = ops.mr_aggregate(y, idx, B, N, want_arg=True)
         mr = gc.gconv.nn
         conv, bnm = mr[0], mr[1]
-        w = _conv2d_w(conv)
-        w_mr = torch.cat([w[:, 0::2], w[:, 1::2]], dim=1)
+        w_mr = _cached(conv.weight, "mrw", lambda: torch.cat([_conv2d_w(conv)[:, 0::2], _conv2d_w(conv)[:, 1::2]], dim=1))
         act = mr[2] if len(mr) > 2 else None
         u = layer_fwd(Ls, y, conv.weight, w_mr, "mr", conv.bias, bnm, act.name if act else None,
                       act.neg_slope if act else 0.0, a2=m, groups=mr.GROUPS)
@@ -192,15 +254,20 @@ def encoder_train_fwd(enc, x_nodes: torch.Tensor, B: int, N: int, forced_idx=Non
     return emb, h, tape
 
 
-def encoder_train_bwd(tape: _EncTape, demb: torch.Tensor, grads: Dict, dnodes: Optional[torch.Tensor] = None,
-                      need_input: bool = False):
-    """Backward of encoder_train_fwd.  Returns d(x_nodes) if need_input."""
+def encoder_train_bwd_steps(enc, tape: _EncTape, demb: torch.Tensor, grads: Dict,
+                            dnodes: Optional[torch.Tensor] = None, need_input: bool = False, out: Optional[list] = None):
+    """Backward of encoder_train_fwd as a generator: yields the sub-module (enc.proj, each backbone entry from the
+    last to the first, enc.stem) whose parameter gradients have just been completed, so a data-parallel driver can
+    start reducing them while the rest of the backward runs.  d(x_nodes) is appended to ``out`` if need_input."""
     Ls = list(tape.layers)
     B = tape.B
     dmean, _ = layer_bwd(Ls.pop(), demb.contiguous(), grads)
     dh = ops.node_mean_bwd(dmean, B, tape.N_out)
     if dnodes is not None:
         ops.add_inplace(dh, dnodes.contiguous())
+    yield enc.proj
+    entries = list(enc.backbone)
+    ei = len(entries)
     for kind, info in reversed(tape.blocks):
         if kind == "block":
             idx, arg, N = info
@@ -211,12 +278,27 @@ def encoder_train_bwd(tape: _EncTape, demb: torch.Tensor, grads: Dict, dnodes: O
             dy, dm = layer_bwd(L_mr, du, grads)
             ops.mr_aggregate_bwd(dm, idx, arg, B, N, dy)             # dy += scatter(dm)
             dh, _ = layer_bwd(L_fc1, dy, grads, add_to=dh2)
+            ei -= 1
+            yield entries[ei]
         elif kind == "down":
             dh, _ = layer_bwd(Ls.pop(), dh, grads)
+            ei -= 1
+            yield entries[ei]
         else:                                                        # stem
             dx, _ = layer_bwd(Ls.pop(), dh, grads, need_input=need_input)
-            return dx
-    return None
+            if out is not None:
+                out.append(dx)
+            yield enc.stem
+            return
+
+
+def encoder_train_bwd(tape: _EncTape, demb: torch.Tensor, grads: Dict, dnodes: Optional[torch.Tensor] = None,
+                      need_input: bool = False, enc=None):
+    """Backward of encoder_train_fwd.  Returns d(x_nodes) if need_input."""
+    out: list = []
+    for _ in encoder_train_bwd_steps(enc if enc is not None else tape.enc, tape, demb, grads, dnodes, need_input, out):
+        pass
+    return out[0] if out else None
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -277,16 +359,27 @@ def view_fwd(model, spec: torch.Tensor, forced_idx=None):
     return h, z, c
 
 
-def view_bwd(model, c: _ViewCtx, dh: Optional[torch.Tensor], dz: torch.Tensor, grads: Dict) -> None:
+def view_bwd_steps(model, c: _ViewCtx, dh: Optional[torch.Tensor], dz: torch.Tensor, grads: Dict):
+    """Backward of one SimCLR view as a generator yielding the sub-modules whose parameter gradients are complete:
+    model.projector, then encoder_train_bwd_steps' sequence, then model.peak_extractor."""
     dz2 = ops.l2_normalize_rows_bwd(c.z2, dz.contiguous(), 1e-10)
     dz1, _ = layer_bwd(c.ptape[1], dz2, grads)
     dhh, _ = layer_bwd(c.ptape[0], dz1, grads, add_to=dh.contiguous() if dh is not None else None)
-    dnodes = encoder_train_bwd(c.tape, dhh, grads, None, need_input=True)
+    yield model.projector
+    out: list = []
+    yield from encoder_train_bwd_steps(model.encoder, c.tape, dhh, grads, None, True, out)
+    dnodes = out[0]
     pe = model.peak_extractor.convs[0]
     if pe.weight.requires_grad:
         dw, db = ops.peak_extract_bwd(c.spec, pe.weight.detach(), pe.bias.detach(), dnodes)
         _acc(grads, pe.weight, dw)
         _acc(grads, pe.bias, db)
+    yield model.peak_extractor
+
+
+def view_bwd(model, c: _ViewCtx, dh: Optional[torch.Tensor], dz: torch.Tensor, grads: Dict) -> None:
+    for _ in view_bwd_steps(model, c, dh, dz, grads):
+        pass
 
 
 class _ViewFn(torch.autograd.Function):

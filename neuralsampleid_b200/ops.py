@@ -582,10 +582,14 @@ def bn_act_bwd(dout: torch.Tensor, raw: torch.Tensor, ssmi: torch.Tensor, act, a
     return draw, sums
 
 
-def bn_param_grad(sums: torch.Tensor, want_gamma: bool, want_beta: bool):
+def bn_param_grad(sums: torch.Tensor, want_gamma: bool, want_beta: bool, out_gamma=None, out_beta=None):
+    """dgamma += sum dz*xhat, dbeta += sum dz.  ``out_gamma`` / ``out_beta``: accumulate into these (C,) fp32 views
+    (e.g. slices of the flat gradient buffer) instead of fresh zero tensors."""
     Cc = sums.shape[1]
-    dg = torch.zeros((Cc,), device=sums.device, dtype=torch.float32) if want_gamma else None
-    db = torch.zeros((Cc,), device=sums.device, dtype=torch.float32) if want_beta else None
+    dg = (out_gamma if out_gamma is not None else torch.zeros((Cc,), device=sums.device, dtype=torch.float32)) \
+        if want_gamma else None
+    db = (out_beta if out_beta is not None else torch.zeros((Cc,), device=sums.device, dtype=torch.float32)) \
+        if want_beta else None
     with torch.cuda.device(sums.device):
         check(_lib.load().grafp_bn_param_grad(_ptr(sums[0]), _ptr(sums[1]), Cc, _ptr(dg), _ptr(db), _stream(sums)),
               "bn_param_grad")

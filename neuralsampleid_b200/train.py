@@ -10,13 +10,14 @@ back-propagates d(global loss)/d(its rows)).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, Optional
 
 import torch
 import torch.distributed as dist
 
 from . import _prep, ops
-from .autograd import view_bwd, view_fwd
+from .autograd import GradSink, view_bwd_steps, view_fwd
 
 
 class FusedClipAdam:
@@ -83,16 +84,83 @@ class FusedClipAdam:
         self.last_grad_norm = self.sq
         ops.adam_clip_step_dev(self.flat_p, self.flat_g, self.m, self.v, self.lr_dev, self.betas[0],
                                self.betas[1], self.eps, self.step_dev, self.max_norm, self.sq, loss_guard)
-        _prep.bump_epoch()          # parameters changed through raw pointers: rebuild prepared weights
+        _prep.bump_weights()        # parameters changed through raw pointers: rebuild prepared weights
 
     def grad_norm(self) -> float:
         return float(self.sq.sqrt().item())
 
 
+class _BucketReducer:
+    """Gradient all-reduce (SUM) overlapped with the backward.  The flat gradient buffer is cut at sub-module
+    boundaries (projector, proj, every backbone entry, stem, peak extractor); a sub-module's range is ready once BOTH
+    views' backward have passed it, ready neighbours are merged, and a merged range of at least ``min_bytes`` is
+    all-reduced asynchronously (NCCL runs on its own stream, ordered after the kernels enqueued so far) while the
+    backward of the shallower layers continues.  ``finish`` flushes the rest and joins."""
+
+    def __init__(self, optimizer, group, passes: int = 2, min_bytes: int = 4 << 20):
+        self.opt, self.group, self.passes, self.min_bytes = optimizer, group, passes, min_bytes
+        self.offset = {}
+        off = 0
+        for p in optimizer.params:
+            self.offset[p] = (off, off + p.numel())
+            off += p.numel()
+        self.seen = {}
+        self.ready = []            # disjoint (lo, hi) element ranges, complete and not yet reduced
+        self.works = []
+        self.launched = 0
+
+    def _range(self, module):
+        spans = [self.offset[p] for p in module.parameters() if p in self.offset]
+        if not spans:
+            return None
+        return min(a for a, _ in spans), max(b for _, b in spans)
+
+    def done(self, module) -> None:
+        """One view's backward has completed ``module``'s parameter gradients."""
+        self.seen[module] = self.seen.get(module, 0) + 1
+        if self.seen[module] < self.passes:
+            return
+        r = self._range(module)
+        if r is None:
+            return
+        self.ready.append(r)
+        self.ready.sort()
+        merged = [self.ready[0]]
+        for a, b in self.ready[1:]:
+            if a <= merged[-1][1]:
+                merged[-1] = (merged[-1][0], max(b, merged[-1][1]))
+            else:
+                merged.append((a, b))
+        self.ready = merged
+        self._launch(False)
+
+    def _launch(self, everything: bool) -> None:
+        keep = []
+        for a, b in self.ready:
+            if everything or (b - a) * 4 >= self.min_bytes:
+                self.works.append(dist.all_reduce(self.opt.flat_g[a:b], op=dist.ReduceOp.SUM, group=self.group,
+                                                  async_op=True))
+                self.launched += 1
+            else:
+                keep.append((a, b))
+        self.ready = keep
+
+    def finish(self) -> None:
+        self._launch(True)
+        for w in self.works:
+            w.wait()               # the current stream waits for the collective
+        self.works = []
+
+
 def train_step(model, x_i: torch.Tensor, x_j: torch.Tensor, cfg, optimizer: FusedClipAdam,
                group=None, skip_nan: bool = True, forced_idx=None):
     """One step of train.py::train on this rank's shard of the batch.  Returns the (global) loss
-    tensor; a NaN loss skips the update like the reference (train.py:65-68)."""
+    tensor; a NaN loss skips the update like the reference (train.py:65-68).
+
+    Data parallel (one process per GPU): ONE small collective before the loss -- the all-gather of this rank's
+    normalised z rows; every rank then evaluates the whole NT-Xent (log-sum-exp of all rows and the scalar loss are
+    recomputed redundantly, 2 n^2 D flops, instead of a second all-gather and an all-reduce) -- and the summed
+    gradient all-reduce, bucketed and overlapped with the backward (_BucketReducer)."""
     if not model.training:
         raise RuntimeError("train_step needs model.train()")
     tau = float(cfg["tau"])
@@ -109,20 +177,23 @@ def train_step(model, x_i: torch.Tensor, x_j: torch.Tensor, cfg, optimizer: Fuse
             dist.all_gather_into_tensor(z_all, z_loc, group=group)
         else:
             z_all = z_loc
-        loss, lse = ops.ntxent_fwd(z_all, tau, rank * rows, rows)
-        if world > 1:
-            lse_all = torch.empty((world * rows,), device=z_loc.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(lse_all, lse, group=group)
-            dist.all_reduce(loss, group=group)
-        else:
-            lse_all = lse
+        loss, lse_all = ops.ntxent_fwd(z_all, tau)             # all n rows: the global loss, on every rank
         one = torch.ones(1, device=z_loc.device, dtype=torch.float32)
         dz = ops.ntxent_bwd(z_all, lse_all, tau, one, rank * rows, rows).view(-1, 2, z_loc.shape[1])
-        grads: Dict = {}
-        view_bwd(model, c_i, None, dz[:, 0].contiguous(), grads)
-        view_bwd(model, c_j, None, dz[:, 1].contiguous(), grads)
-        optimizer.accumulate(grads)
-        if world > 1:
+        grads = GradSink(optimizer.views)
+        reducer = _BucketReducer(optimizer, group) if world > 1 and not os.environ.get("GRAFP_TRAIN_NO_OVERLAP") else None
+        # the two views' backward advance in lockstep, sub-module by sub-module, so that a layer's summed gradient is
+        # final -- and its all-reduce can start -- as early as possible
+        gi = view_bwd_steps(model, c_i, None, dz[:, 0].contiguous(), grads)
+        gj = view_bwd_steps(model, c_j, None, dz[:, 1].contiguous(), grads)
+        for mi, mj in zip(gi, gj):
+            if reducer is not None:
+                reducer.done(mi)
+                reducer.done(mj)
+        optimizer.accumulate(grads)                            # whatever did not go to the flat buffer directly
+        if reducer is not None:
+            reducer.finish()
+        elif world > 1:
             dist.all_reduce(optimizer.flat_g, op=dist.ReduceOp.SUM, group=group)
         optimizer.step(loss if skip_nan else None)     # a NaN loss skips the update on the device
     return loss.reshape(())
@@ -164,11 +235,11 @@ class GraphedTrainStep:
             optimizer.step_dev.copy_(keep[3])
             for b, saved in bufs:
                 b.copy_(saved)
-        _prep.bump_epoch()
+        _prep.bump_weights()
 
     def __call__(self, x_i: torch.Tensor, x_j: torch.Tensor) -> torch.Tensor:
         self.x_i.copy_(x_i, non_blocking=True)
         self.x_j.copy_(x_j, non_blocking=True)
         self.graph.replay()
-        _prep.bump_epoch()
+        _prep.bump_weights()
         return self.loss
