@@ -167,6 +167,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------
+# MMA passes per k-step of each engine, in units of one bf16-rate pass (kind::tf32 runs at half the bf16 rate)
+ENGINE_PASSES = {"auto": 3, "f16x3": 3, "bf16x3": 3, "3xtf32": 6, "tf32": 2, "bf16": 1, "simt": 3}
+
+
 class KernelTimer:
     """Per-C-ABI-call CUDA-event timing on the launching stream (one instrumented step)."""
 
@@ -180,7 +184,7 @@ class KernelTimer:
         if name == "grafp_gemm_fwd":
             a = args[0]._obj
             info = "gemm m=%d k=%d+%d n=%d g=%d%s" % (a.m, a.k1, a.k2, a.n, a.groups, " tap3" if a.tap3_nodes else "")
-            self.last_gemm = (a.m, a.k1 + a.k2, a.n * a.groups, a.groups)
+            self.last_gemm = (a.m, a.k1 + a.k2, a.n * a.groups, 1)      # k1, k2, n are PER-GROUP sizes: 2 m k (n g)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         rc = fn(*args)
@@ -208,6 +212,125 @@ class KernelTimer:
             elif extra is not None:
                 d["shapes"].append(extra)
         return out
+
+
+def extra_records(args, world, rank, dev, barrier, max_over_ranks):
+    """Secondary records of the same JSON line (every rank takes part, rank 0 reports):
+      train_step  BASELINE configs[2]: contrastive train step, 32 pairs per GPU (bsz_train 256 over 8 GPUs), k = 5,
+                  CUDA-graph replay of the whole step incl. the NCCL all-gather of z and the bucketed, overlapped
+                  gradient all-reduce; step time = max over ranks; the two collectives also timed alone
+      db_1m       BASELINE configs[3]: 1 M synthetic spectrogram segments -> 128-d fingerprints, contiguous ranges per
+                  rank, pinned host in / out
+      chunks128   the reference's call shape (generate.py:40-46): one 128-segment chunk per call
+    """
+    import torch.distributed as dist
+    from neuralsampleid_b200 import ops
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    from neuralsampleid_b200.graphed import GraphedSimCLR
+    from neuralsampleid_b200.parallel import shard_range
+    from neuralsampleid_b200.simclr.simclr import SimCLR
+    from neuralsampleid_b200.train import FusedClipAdam, GraphedTrainStep, train_step
+    cfg = dict(CFG, tau=0.05, d=128, h=1024, u=32, dim=2048, arch="grafp", bsz_train=256, lr=8.0e-5)
+    out = {}
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n
+
+    # ---- contrastive train step ----
+    if not args.no_train:
+        pairs = 32
+        torch.manual_seed(0)
+        model = SimCLR(cfg, encoder=GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=5)).to(dev).train()
+        opt = FusedClipAdam(model.parameters(), lr=cfg["lr"], max_norm=1.0)
+        g = torch.Generator().manual_seed(2 + rank)
+        xi_h = torch.randn((pairs, 64, 128), generator=g).pin_memory()
+        xj_h = (xi_h + 0.1 * torch.randn((pairs, 64, 128), generator=g)).pin_memory()
+        launch = "cuda graph replay of the whole step"
+        with torch.no_grad():
+            try:
+                gs = GraphedTrainStep(model, cfg, opt, pairs)
+                step = lambda: gs(xi_h, xj_h)                        # H2D of both views inside the step
+            except Exception as e:                                    # pragma: no cover
+                launch = "eager (graph capture failed: %s)" % str(e)[:100]
+                xi_d, xj_d = xi_h.to(dev), xj_h.to(dev)
+                step = lambda: train_step(model, xi_d.copy_(xi_h, non_blocking=True), xj_d.copy_(xj_h, non_blocking=True), cfg, opt)
+            for _ in range(3):
+                step()
+            ms = timed(step, 10)
+            rec = {"ms_per_step": ms, "value": 2 * pairs * world / (ms * 1e-3), "unit": "encoder segments/s",
+                   "pairs_per_gpu": pairs, "global_pairs": pairs * world, "n_gpus": world, "launch": launch,
+                   "h2d_bytes_per_step": 2 * pairs * 64 * 128 * 4 * world,
+                   "config": "SimCLR(GraphEncoder t, k=5) fwd + bwd (tcgen05 dgrad / wgrad), NT-Xent over the global "
+                             "batch, clip 1.0, Adam 8e-5; per-rank BatchNorm statistics (DataParallel semantics)"}
+            if world > 1:
+                z = torch.zeros((2 * pairs, 128), device=dev)
+                z_all = torch.empty((world * 2 * pairs, 128), device=dev)
+                rec["all_gather_us"] = 1e3 * timed(lambda: dist.all_gather_into_tensor(z_all, z), 20)
+                buckets = getattr(opt, "last_buckets", None) or [(0, opt.flat_g.numel())]
+
+                def reduce_all():
+                    for a, b in buckets:
+                        dist.all_reduce(opt.flat_g[a:b])
+                rec["all_reduce_us"] = 1e3 * timed(reduce_all, 10)
+                rec["all_reduce_bytes"] = int(opt.flat_g.numel() * 4)
+                rec["all_reduce_buckets"] = len(buckets)
+                rec["all_reduce"] = "bucketed at sub-module boundaries, launched during the lock-stepped backward of the two views"
+            out["train_step"] = rec
+        del model, opt
+
+    # ---- spectrogram -> fingerprint: 1 M segment database, and the reference's 128-segment call shape ----
+    if not args.no_db:
+        torch.manual_seed(0)
+        model = SimCLR(cfg, encoder=GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=K_NEIGHBOURS)).to(dev).eval()
+        Bdb = 4096
+        total = args.db_segments
+        lo, hi = shard_range(total, rank, world)
+        n_batches = (hi - lo + Bdb - 1) // Bdb
+        with torch.no_grad():
+            gsim = GraphedSimCLR(model, Bdb)
+            spec = torch.randn((Bdb, 64, 128), generator=torch.Generator().manual_seed(rank)).pin_memory()
+            fp = torch.empty((n_batches * Bdb, 128), dtype=torch.float32).pin_memory()       # this rank's DB slice
+            it = [0]
+
+            def dbstep():
+                i = it[0] % n_batches
+                gsim.input.copy_(spec, non_blocking=True)
+                gsim.replay()
+                fp[i * Bdb:(i + 1) * Bdb].copy_(gsim.z, non_blocking=True)
+                it[0] += 1
+            for _ in range(2):
+                dbstep()
+            it[0] = 0
+            ms = timed(dbstep, n_batches) * n_batches
+            out["db_1m"] = {"value": total / (ms * 1e-3), "unit": "segments/s", "segments": total, "seconds": ms * 1e-3,
+                            "n_gpus": world, "batch": Bdb, "h2d_bytes_per_segment": 64 * 128 * 4,
+                            "d2h_bytes_per_segment": 128 * 4,
+                            "config": "SimCLR eval (peak extractor + GraphEncoder t k=3 + projector + L2 norm), CUDA graph "
+                                      "replay per 4096-segment batch, pinned host in/out, contiguous segment ranges per "
+                                      "rank in the reference's (n, 128) float32 layout (test_fp.py:158-171)"}
+            if rank == 0 or world == 1:
+                g128 = GraphedSimCLR(model, 128)
+                x128 = torch.randn((128, 64, 128), device=dev)
+                g128(x128)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(50):
+                    g128.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                out["chunks128"] = {"ms_per_chunk": e0.elapsed_time(e1) / 50, "value": 128 * 50 / (e0.elapsed_time(e1) * 1e-3),
+                                    "unit": "segments/s", "config": "generate.py:40-46 call shape: one 128-segment chunk, one "
+                                                                   "view, CUDA graph replay, one GPU"}
+        del model
+    return out
 
 
 def ncu_traffic(segments: int) -> dict:
@@ -243,7 +366,7 @@ def run_native(args):
     elif args.engine:
         ops._engine_override = args.engine       # tensor-core engine for every GEMM whose shape allows
     engine_name = args.engine or "auto"
-    parity_engine = engine_name in ("auto", "simt", "3xtf32", "bf16x3")
+    parity_engine = engine_name in ("auto", "simt", "3xtf32", "bf16x3", "f16x3")
 
     B = args.batch
     lo, hi = shard_range(B * world, rank, world)
@@ -418,9 +541,11 @@ def run_native(args):
                     "traffic_note": traffic.get("note"),
                     "peak_source": pk["source"] + " dense bf16 (cuBLAS, sustained)",
                     "note": "achieved counts useful 2*M*N*K flops; the fp32-parity engines issue 3 MMA passes "
-                            "per k-step (auto/bf16x3: kind::f16 -> ceiling peak/3; 3xtf32: kind::tf32 at half "
+                            "per k-step (auto/f16x3/bf16x3: kind::f16 -> ceiling peak/3; 3xtf32: kind::tf32 at half "
                             "rate -> peak/6); engine 'bf16' is 1 pass (ceiling = peak) and not parity grade",
                     "engine": engine_name,
+                    "frac_of_engine_ceiling": achieved / (pk["bf16_tflops_sustained"] / ENGINE_PASSES.get(engine_name, 3)),
+                    "engine_ceiling": "measured sustained bf16 peak / %d" % ENGINE_PASSES.get(engine_name, 3),
                     "share_of_step": g_all["ms"] / step_ms_instr,
                     "top_gemm": {"shape": top_gemm_name, "ms": top_gemm["ms"],
                                  "tflops": top_gemm["flops"] / (top_gemm["ms"] * 1e-3) / 1e12}}
@@ -431,9 +556,20 @@ def run_native(args):
                     "unit": "GB/s", "frac": r["frac"], "traffic": r.get("traffic"),
                     "peak_source": pk["source"], "share_of_step": by_entry[dominant]["ms"] / step_ms_instr}
 
-    if rank != 0:
+    extras = extra_records(args, world, rank, dev, barrier, max_over_ranks)
+
+    def leave():
+        # flush and leave WITHOUT tearing NCCL down: destroy_process_group() after a CUDA graph that captured NCCL
+        # collectives (the graphed train step) once hung every rank until the job's timeout
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     cpu = None
@@ -470,9 +606,9 @@ def run_native(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    line.update(extras)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():
@@ -482,8 +618,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="segments per GPU")
-    ap.add_argument("--engine", default=None, choices=[None, "auto", "simt", "3xtf32", "tf32", "bf16x3", "bf16"],
-                    help="GEMM engine (default auto = bf16x3, the fp32-parity tensor-core engine)")
+    ap.add_argument("--engine", default=None, choices=[None, "auto", "simt", "3xtf32", "tf32", "bf16x3", "bf16", "f16x3"],
+                    help="GEMM engine (default auto = f16x3, the fp32-parity tensor-core engine)")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step record")
+    ap.add_argument("--no-db", action="store_true", help="skip the db_1m / chunks128 records")
+    ap.add_argument("--db-segments", type=int, default=1000000)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")

@@ -107,6 +107,7 @@ class _BucketReducer:
         self.seen = {}
         self.ready = []            # disjoint (lo, hi) element ranges, complete and not yet reduced
         self.works = []
+        self.ranges = []
         self.launched = 0
 
     def _range(self, module):
@@ -140,6 +141,7 @@ class _BucketReducer:
             if everything or (b - a) * 4 >= self.min_bytes:
                 self.works.append(dist.all_reduce(self.opt.flat_g[a:b], op=dist.ReduceOp.SUM, group=self.group,
                                                   async_op=True))
+                self.ranges.append((a, b))
                 self.launched += 1
             else:
                 keep.append((a, b))
@@ -147,6 +149,7 @@ class _BucketReducer:
 
     def finish(self) -> None:
         self._launch(True)
+        self.opt.last_buckets = list(self.ranges)      # (bench bookkeeping: the element ranges that were reduced)
         for w in self.works:
             w.wait()               # the current stream waits for the collective
         self.works = []
