@@ -210,8 +210,16 @@ class GraphEncoder(_Cached):
             from ..autograd import encoder_forward_train
             return encoder_forward_train(self, x, return_pre_proj)
         if self.training:
-            raise RuntimeError("GraphEncoder in train mode under no_grad is ambiguous (BatchNorm "
-                               "statistics); call .eval() for inference")
+            # train mode under no_grad (e.g. a validation loss computed without .eval()): like the reference, a
+            # batch-statistics BatchNorm forward that also moves the running statistics; the tape is discarded
+            from ..autograd import encoder_train_fwd
+            if x.dim() != 3:
+                raise ValueError("expected (B, C, N) input, got %s" % (tuple(x.shape),))
+            B, _, N = x.shape
+            emb, nodes, tape = encoder_train_fwd(self, ops.nchw_to_nodes(x.detach()), B, N)
+            if return_pre_proj:
+                return ops.nodes_to_nchw(nodes, B, tape.N_out), emb
+            return emb
         if x.dim() != 3:
             raise ValueError("expected (B, C, N) input, got %s" % (tuple(x.shape),))
         B, cin, N = x.shape

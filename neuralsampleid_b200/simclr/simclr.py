@@ -42,7 +42,10 @@ class SimCLR(nn.Module):
     def _one_view(self, x, forced_idx=None):
         if isinstance(self.encoder, GraphEncoder) and not (self.training and torch.is_grad_enabled()):
             if self.encoder.training:
-                raise RuntimeError("call .eval() for inference (BatchNorm statistics)")
+                # train mode under no_grad: batch-statistics forward (as the reference does), tape discarded
+                from ..autograd import view_fwd
+                h, z, _ = view_fwd(self, x, forced_idx)
+                return h, z
             nodes, N = self.peak_extractor.forward_nodes(x)
             taps = [] if getattr(self, "_taps", None) is not None else None      # parity-test hook
             h = self.encoder.forward_nodes(nodes, x.shape[0], N, forced_idx=forced_idx, taps=taps)

@@ -54,6 +54,15 @@ class FusedClipAdam:
         self.lr_dev = torch.full((1,), lr, device=dev, dtype=torch.float32)
         self.sq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.last_grad_norm: Optional[torch.Tensor] = None
+        opt = self
+
+        class _Group(dict):                  # a torch-style param group whose 'lr' writes through to the device scalar
+            def __setitem__(self, key, value):
+                super().__setitem__(key, value)
+                if key == "lr":
+                    opt._lr = float(value)
+                    opt.lr_dev.fill_(float(value))
+        self._groups = [_Group(lr=lr, initial_lr=lr, betas=betas, eps=eps, params=self.params)]
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.flat_g.zero_()
@@ -70,8 +79,7 @@ class FusedClipAdam:
 
     @lr.setter
     def lr(self, value: float) -> None:          # e.g. CosineAnnealingLR per epoch (train.py:127)
-        self._lr = float(value)
-        self.lr_dev.fill_(self._lr)
+        self._groups[0]["lr"] = float(value)
 
     @property
     def step_count(self) -> int:
@@ -79,6 +87,7 @@ class FusedClipAdam:
 
     def step(self, loss_guard: Optional[torch.Tensor] = None) -> None:
         """clip_grad_norm_(max_norm) + Adam.  ``loss_guard``: a device scalar; NaN skips the update."""
+        self.check_views()
         self.sq.zero_()
         ops.sq_norm(self.flat_g, self.sq)
         self.last_grad_norm = self.sq
@@ -88,6 +97,52 @@ class FusedClipAdam:
 
     def grad_norm(self) -> float:
         return float(self.sq.sqrt().item())
+
+    # ---- torch.optim.Adam-compatible checkpointing (reference checkpoint format: util.py:149-158 stores
+    # optimizer.state_dict(); train.py resumes it) and the param_groups view LR schedulers drive -------------------
+    @property
+    def param_groups(self):
+        return self._groups
+
+    def state_dict(self) -> dict:
+        """The layout of torch.optim.Adam.state_dict(): per-parameter 'step', 'exp_avg', 'exp_avg_sq'."""
+        state, off = {}, 0
+        step = float(self.step_count)
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            state[i] = {"step": torch.tensor(step), "exp_avg": self.m[off:off + k].view(p.shape).clone(),
+                        "exp_avg_sq": self.v[off:off + k].view(p.shape).clone()}
+            off += k
+        group = {"lr": self._lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        off = 0
+        steps = []
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                k = p.numel()
+                st = sd["state"].get(i)
+                if st is not None:
+                    self.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                    self.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.append(int(float(st["step"])))
+                off += k
+            if steps:
+                self.step_dev.fill_(max(steps))
+        g = sd["param_groups"][0]
+        self.betas, self.eps = tuple(g["betas"]), g["eps"]
+        self.lr = g["lr"]
+
+    def check_views(self) -> None:
+        """Raises if a parameter no longer aliases the flat buffer (model.to(...), p.data reassigned elsewhere)."""
+        off = 0
+        for p in self.params:
+            if p.data_ptr() != self.flat_p.data_ptr() + 4 * off:
+                raise RuntimeError("FusedClipAdam: a parameter was detached from the flat buffer (model.to() / p.data "
+                                   "reassigned after the optimizer was built); rebuild the optimizer")
+            off += p.numel()
 
 
 class _BucketReducer:

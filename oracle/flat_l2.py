@@ -6,7 +6,10 @@ CPU oracle of the exact fingerprint search.  The refe
 /root/reference nor in this image).  Published semantics restated here: D[i, r] = r-th smallest squared
 Euclidean distance |q_i - x_j|^2, I[i, r] = its database position; -1 / +inf beyond ntotal.  Computed in
 float64; ties (FAISS leaves their order unspecified) are broken towards the lower index.
-PARITY UNPINNED: the reference ships no search fixtures and FAISS cannot be run here."""
+The reference ships no search fixtures and FAISS cannot be run here, so FAISS ITSELF WAS NEVER RUN; this oracle is
+pinned instead to tests/golden/search_expected.npz -- an independent float64 brute force (direct sum of squared
+differences, lexsort by (distance, id); tests/golden/make_search_golden.py) over a database written in the reference's
+memmap layout (tests/test_oracle_golden.py)."""
 import numpy as np
 
 

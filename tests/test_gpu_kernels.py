@@ -655,6 +655,26 @@ def test_flat_l2_index_matches_exact_search():
     _search_check(index, db, (0.3 * rng.standard_normal((40, d))).astype(np.float32), 32, tol=1e-3)   # un-normalised, k = 32
 
 
+def test_flat_l2_index_matches_the_independent_search_fixture(golden_dir):
+    """The GPU index over a database in the reference's on-disk layout against the committed fixture of an independent
+    exact float64 search (tests/golden/make_search_golden.py; FAISS was never run: it is absent from the image and
+    from /root/reference): identical ids -- the duplicate pair resolves to the lower id -- and distances to 1e-5."""
+    from neuralsampleid_b200.db import FlatL2Index, load_fingerprints
+    g = np.load(os.path.join(golden_dir, "search_expected.npz"))
+    emb, _ = load_fingerprints(os.path.join(golden_dir, "search_db"), "ref_db")
+    index = FlatL2Index(128, DEV)
+    index.add(np.asarray(emb))
+    k = int(g["k"])
+    D, I = index.search(g["q"], k)
+    Dw, Iw = g["D"], g["I"]
+    assert np.allclose(D, Dw, rtol=0, atol=1e-5)
+    bad = I != Iw
+    for r, c in zip(*np.nonzero(bad)):                     # only where the fixture's own distances are within 4e-6
+        assert abs(Dw[r, c] - Dw[r, min(c + 1, k - 1)]) < 4e-6 or abs(Dw[r, c] - Dw[r, max(c - 1, 0)]) < 4e-6, (r, c)
+    assert I[0, 0] == 33 and I[0, 1] == 700                # the exact duplicates, lower id first
+    assert float(bad.mean()) < 0.01
+
+
 def test_flat_l2_index_small_and_duplicates():
     from neuralsampleid_b200.db import FlatL2Index
     rng = np.random.Generator(np.random.PCG64(12))

@@ -467,3 +467,53 @@ def test_clip_adam_kernel_matches_oracle():
         assert abs(float(sq.sqrt()) - float(gr.double().norm())) < 1e-6 * float(gr.norm())
     assert torch.allclose(pd.cpu(), p_ref, rtol=1e-6, atol=1e-7)
     assert torch.allclose(md.cpu(), m_ref, rtol=1e-5, atol=1e-9)
+
+
+def test_fused_optimizer_checkpoint_round_trip_and_lr_group():
+    """FusedClipAdam.state_dict() has torch.optim.Adam's layout (the reference stores optimizer.state_dict() in its
+    checkpoints, util.py:149-158); a resumed optimizer continues identically; param_groups[0]['lr'] writes through."""
+    from neuralsampleid_b200.train import FusedClipAdam, train_step
+    s_i, s_j = _inputs(4)
+    model, _ = _model(5)
+    model.train()
+    opt = FusedClipAdam(model.parameters(), lr=CFG["lr"], max_norm=1.0)
+    for _ in range(2):
+        train_step(model, s_i.to(DEV), s_j.to(DEV), CFG, opt)
+    sd_o = opt.state_dict()
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))]).state_dict()
+    assert set(sd_o.keys()) == set(ref.keys()) and set(sd_o["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert int(sd_o["state"][0]["step"]) == 2 and sd_o["param_groups"][0]["lr"] == CFG["lr"]
+    model2, _ = _model(5)
+    model2.load_state_dict(model.state_dict())
+    model2.train()
+    opt2 = FusedClipAdam(model2.parameters(), lr=1.0, max_norm=1.0)
+    opt2.load_state_dict(sd_o)
+    assert opt2.step_count == 2 and opt2.lr == CFG["lr"]
+    train_step(model, s_i.to(DEV), s_j.to(DEV), CFG, opt)
+    train_step(model2, s_i.to(DEV), s_j.to(DEV), CFG, opt2)
+    assert torch.allclose(opt.flat_p, opt2.flat_p, rtol=0, atol=2e-7)
+    opt.param_groups[0]["lr"] = 1e-5                      # what an LR scheduler does
+    assert opt.lr == 1e-5 and abs(float(opt.lr_dev.item()) - 1e-5) < 1e-12
+    model.to(DEV)                                         # no-op move keeps the aliasing
+    opt.check_views()
+    next(model.parameters()).data = next(model.parameters()).data.clone()
+    with pytest.raises(RuntimeError):
+        opt.check_views()
+
+
+def test_train_mode_forward_under_no_grad_uses_batch_statistics():
+    """Reference behaviour (a validation loss computed without .eval()): train-mode BatchNorm forward, running
+    statistics move, no autograd tape -- same values as the train forward under grad."""
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    sd = synth.synth_state(synth.encoder_state_spec("t", 8, 1024, 256), 1234)
+    x = synth.synth_uniform((6, 8, 256), 77).to(DEV)
+    outs, stats = [], []
+    for grad in (True, False):
+        enc = GraphEncoder(cfg=CFG, in_channels=8, k=3)
+        enc.load_state_dict(sd)
+        enc = enc.to(DEV).train()
+        with torch.set_grad_enabled(grad):
+            outs.append(enc(x).detach())
+        stats.append(enc.stem[1].running_mean.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(stats[0], stats[1])
+    assert not torch.equal(stats[0], sd["stem.1.running_mean"].to(DEV))

@@ -269,3 +269,22 @@ def test_oracle_vs_live_reference_reranker():
     with torch.no_grad():
         assert torch.allclose(m2(x_i, x_j), O.cross_attention_classifier(dict(m2.state_dict()), x_i, x_j, 2),
                               rtol=1e-6, atol=1e-7)
+
+
+def test_flat_l2_oracle_and_db_loader_match_the_independent_search_fixture(golden_dir):
+    """SURVEY 8f rank 4 pin.  FAISS itself was never run (it is not in this image nor in /root/reference): the fixture
+    (tests/golden/make_search_golden.py) is a database written in the reference's memmap layout as test_fp.py:158-171
+    writes it and searched by an independent float64 brute force (direct sum of squared differences, lexsort by
+    (distance, id)).  The oracle's |q|^2 - 2 q.x + |x|^2 restatement and the product's loader must reproduce it."""
+    from neuralsampleid_b200.db import load_fingerprints
+    from oracle.flat_l2 import flat_l2_search
+    g = np.load(os.path.join(golden_dir, "search_expected.npz"))
+    import json
+    emb, shape = load_fingerprints(os.path.join(golden_dir, "search_db"), "ref_db")
+    lookup = json.load(open(os.path.join(golden_dir, "search_db", "ref_db_lookup.json")))
+    assert emb.shape == (1536, 128) and tuple(shape) == (1536, 128) and emb.dtype == np.float32
+    assert len(lookup) == 1536 and lookup[48] == "song_001"
+    D, I = flat_l2_search(np.asarray(emb), g["q"], int(g["k"]))
+    assert np.array_equal(I, g["I"])                      # incl. the exact duplicate pair: lower id first
+    assert np.allclose(D, g["D"], rtol=0, atol=1e-12)
+    assert int((g["I"][:, 0] == g["source"]).sum()) >= 23
