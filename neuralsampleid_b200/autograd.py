@@ -13,6 +13,7 @@ gradient) are O(parameters) index operations done with torch on the parameter si
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -64,12 +65,17 @@ def _cached(param: torch.Tensor, tag, make):
     ep = (_prep.weights_epoch(), ops.get_engine(), ops._engine_override)
     if _WCACHE["epoch"] != ep:
         _WCACHE["epoch"], _WCACHE["items"] = ep, {}
-    key = (param.data_ptr(), tuple(param.shape), tag)
+    # keyed by the parameter OBJECT (a freed model's storage address can be handed to the next model's parameters),
+    # validated by storage address and version; a newer version replaces the entry, so nothing accumulates
+    key = (id(param), tag)
+    stamp = (param.data_ptr(), param._version)
     hit = _WCACHE["items"].get(key)
-    if hit is None or hit[0] != param._version:        # a newer version replaces the entry: nothing accumulates
-        hit = (param._version, make())
+    if hit is None or hit[0]() is not param or hit[1] != stamp:
+        hit = (weakref.ref(param), stamp, make())
         _WCACHE["items"][key] = hit
-    return hit[1]
+        if len(_WCACHE["items"]) > 4096:                # dead models' entries
+            _WCACHE["items"] = {k: v for k, v in _WCACHE["items"].items() if v[0]() is not None}
+    return hit[2]
 
 
 def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: torch.Tensor, kind: str,

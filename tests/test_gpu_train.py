@@ -491,7 +491,10 @@ def test_fused_optimizer_checkpoint_round_trip_and_lr_group():
     assert opt2.step_count == 2 and opt2.lr == CFG["lr"]
     train_step(model, s_i.to(DEV), s_j.to(DEV), CFG, opt)
     train_step(model2, s_i.to(DEV), s_j.to(DEV), CFG, opt2)
-    assert torch.allclose(opt.flat_p, opt2.flat_p, rtol=0, atol=2e-7)
+    # identical up to the atomics of the max-relative backward: Adam turns a gradient that is pure round-off noise
+    # into a +-lr step, so a few parameters may differ by up to 2 lr
+    diff = (opt.flat_p - opt2.flat_p).abs()
+    assert float(diff.max()) <= 2.5 * CFG["lr"] and float((diff < 2e-7).float().mean()) > 0.99
     opt.param_groups[0]["lr"] = 1e-5                      # what an LR scheduler does
     assert opt.lr == 1e-5 and abs(float(opt.lr_dev.item()) - 1e-5) < 1e-12
     model.to(DEV)                                         # no-op move keeps the aliasing
