@@ -243,6 +243,31 @@ def extra_records(args, world, rank, dev, barrier, max_over_ranks):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / n
 
+    # ---- reduced-precision line (BASELINE configs[1] "fp32 and bf16"): 1-pass bf16 tensor-core operands, every
+    # GEMM-only activation (MRConv output, FFN hidden) stored as ONE bf16 plane, fp32 residual stream / kNN input /
+    # accumulation.  Not parity grade: stated separately (tests/test_gpu_encoder.py: teacher-forced embeddings within
+    # 3e-2 of the fp32 oracle, measured ~5e-3).
+    if not args.no_bf16 and (args.engine in (None, "auto")):
+        from neuralsampleid_b200.graphed import GraphedEncoder
+        enc = args._encoder
+        try:
+            ops._engine_override = "bf16"
+            with torch.no_grad():
+                gb = GraphedEncoder(enc, args._x_dev.shape[0], 256, 8, warmup=2)
+                gb.input.copy_(args._x_dev)
+                for _ in range(3):
+                    gb.replay()
+                ms = timed(gb.replay, max(5, args.steps // 2))
+            out["bf16"] = {"value": args._x_dev.shape[0] * world / (ms * 1e-3), "unit": "segments/s", "ms_per_step": ms,
+                           "n_gpus": world, "engine": "bf16 (1 MMA pass)",
+                           "storage": "GEMM-only activations as one bf16 plane; residual stream, kNN input and "
+                                      "accumulators fp32",
+                           "tolerance": "teacher-forced embeddings within 3e-2 relative of the fp32 oracle (measured ~5e-3); "
+                                        "neighbour lists are NOT compared in this mode"}
+            del gb
+        finally:
+            ops._engine_override = None
+
     # ---- contrastive train step ----
     if not args.no_train:
         pairs = 32
@@ -556,6 +581,7 @@ def run_native(args):
                     "unit": "GB/s", "frac": r["frac"], "traffic": r.get("traffic"),
                     "peak_source": pk["source"], "share_of_step": by_entry[dominant]["ms"] / step_ms_instr}
 
+    args._encoder, args._x_dev = enc, x_dev
     extras = extra_records(args, world, rank, dev, barrier, max_over_ranks)
 
     def leave():
@@ -621,6 +647,7 @@ def main():
     ap.add_argument("--engine", default=None, choices=[None, "auto", "simt", "3xtf32", "tf32", "bf16x3", "bf16", "f16x3"],
                     help="GEMM engine (default auto = f16x3, the fp32-parity tensor-core engine)")
     ap.add_argument("--no-train", action="store_true", help="skip the train_step record")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the reduced-precision (bf16) record")
     ap.add_argument("--no-db", action="store_true", help="skip the db_1m / chunks128 records")
     ap.add_argument("--db-segments", type=int, default=1000000)
     ap.add_argument("--cpu-budget", type=float, default=15.0)

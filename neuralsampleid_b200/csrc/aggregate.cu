@@ -37,6 +37,11 @@ __device__ __forceinline__ void mr_item(const float* __restrict__ sx, const int3
 // 4 channels) at a time so 4 independent idx -> gather -> max chains are in flight.
 constexpr int AGG_UNROLL = 4;
 
+// kArg == false (inference): max_t (x_j - x_i) is computed as (max_t x_j) - x_i.  Round-to-nearest subtraction is
+// monotone in x_j, so fl(max_t x_j - x_i) == max_t fl(x_j - x_i) BIT FOR BIT, and the inner loop is one 128-bit
+// shared-memory load + 4 FMNMX per neighbour instead of 4 subtractions + 4 compare / select pairs + the arg-max
+// bookkeeping (the profile showed the kernel issue-bound, not HBM-bound, once k grows: 0.93 TB/s at k = 32).
+template <bool kArg>
 __global__ void __launch_bounds__(AGG_THREADS, 1)
 mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int B,
                            int N, int C, int k, int stages, uint32_t stage_bytes, int idx_in_smem,
@@ -91,16 +96,36 @@ mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restric
         best[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         arg[u] = 0u;
       }
-      for (int t = 0; t < k; ++t) {
+      if (kArg) {
+        for (int t = 0; t < k; ++t) {
+#pragma unroll
+          for (int u = 0; u < AGG_UNROLL; ++u) {
+            const int j = gidx[node[u] * k + t];
+            const float4 xj = *reinterpret_cast<const float4*>(gx + (size_t)j * C + off[u]);
+            const float dx = xj.x - xi[u].x, dy = xj.y - xi[u].y, dz = xj.z - xi[u].z, dw = xj.w - xi[u].w;
+            if (dx > best[u].x) { best[u].x = dx; arg[u] = (arg[u] & 0xFFFFFF00u) | (uint32_t)t; }
+            if (dy > best[u].y) { best[u].y = dy; arg[u] = (arg[u] & 0xFFFF00FFu) | ((uint32_t)t << 8); }
+            if (dz > best[u].z) { best[u].z = dz; arg[u] = (arg[u] & 0xFF00FFFFu) | ((uint32_t)t << 16); }
+            if (dw > best[u].w) { best[u].w = dw; arg[u] = (arg[u] & 0x00FFFFFFu) | ((uint32_t)t << 24); }
+          }
+        }
+      } else {
+        // running maximum of the neighbour rows themselves (fmaxf: a NaN neighbour never wins, as in the
+        // compare-and-select form)
+        for (int t = 0; t < k; ++t) {
+#pragma unroll
+          for (int u = 0; u < AGG_UNROLL; ++u) {
+            const int j = gidx[node[u] * k + t];
+            const float4 xj = *reinterpret_cast<const float4*>(gx + (size_t)j * C + off[u]);
+            best[u].x = fmaxf(best[u].x, xj.x);
+            best[u].y = fmaxf(best[u].y, xj.y);
+            best[u].z = fmaxf(best[u].z, xj.z);
+            best[u].w = fmaxf(best[u].w, xj.w);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < AGG_UNROLL; ++u) {
-          const int j = gidx[node[u] * k + t];
-          const float4 xj = *reinterpret_cast<const float4*>(gx + (size_t)j * C + off[u]);
-          const float dx = xj.x - xi[u].x, dy = xj.y - xi[u].y, dz = xj.z - xi[u].z, dw = xj.w - xi[u].w;
-          if (dx > best[u].x) { best[u].x = dx; arg[u] = (arg[u] & 0xFFFFFF00u) | (uint32_t)t; }
-          if (dy > best[u].y) { best[u].y = dy; arg[u] = (arg[u] & 0xFFFF00FFu) | ((uint32_t)t << 8); }
-          if (dz > best[u].z) { best[u].z = dz; arg[u] = (arg[u] & 0xFF00FFFFu) | ((uint32_t)t << 16); }
-          if (dw > best[u].w) { best[u].w = dw; arg[u] = (arg[u] & 0x00FFFFFFu) | ((uint32_t)t << 24); }
+          best[u].x -= xi[u].x; best[u].y -= xi[u].y; best[u].z -= xi[u].z; best[u].w -= xi[u].w;
         }
       }
 #pragma unroll
@@ -134,8 +159,32 @@ mr_aggregate_direct_kernel(const float* __restrict__ x, const int32_t* __restric
   const int32_t* gidx = idx + (size_t)g * N * k;
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
     const int node = it / c4n, c4 = it - node * c4n;
-    float4 v; uint32_t a;
-    mr_item(gx, gidx + (size_t)node * k, k, C, node, c4, v, a);
+    float4 v; uint32_t a = 0;
+    if (arg_out) {
+      mr_item(gx, gidx + (size_t)node * k, k, C, node, c4, v, a);
+    } else {
+      // (max_t x_j) - x_i == max_t (x_j - x_i) bit for bit (monotone rounding); the k row loads are independent
+      const int32_t* nb = gidx + (size_t)node * k;
+      const float4 xi = *reinterpret_cast<const float4*>(gx + (size_t)node * C + c4 * 4);
+      float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      int t = 0;
+      for (; t + 4 <= k; t += 4) {
+        float4 xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xj[u] = __ldg(reinterpret_cast<const float4*>(gx + (size_t)__ldg(nb + t + u) * C + c4 * 4));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          best.x = fmaxf(best.x, xj[u].x); best.y = fmaxf(best.y, xj[u].y);
+          best.z = fmaxf(best.z, xj[u].z); best.w = fmaxf(best.w, xj[u].w);
+        }
+      }
+      for (; t < k; ++t) {
+        const float4 xj = __ldg(reinterpret_cast<const float4*>(gx + (size_t)__ldg(nb + t) * C + c4 * 4));
+        best.x = fmaxf(best.x, xj.x); best.y = fmaxf(best.y, xj.y);
+        best.z = fmaxf(best.z, xj.z); best.w = fmaxf(best.w, xj.w);
+      }
+      v = make_float4(best.x - xi.x, best.y - xi.y, best.z - xi.z, best.w - xi.w);
+    }
     reinterpret_cast<float4*>(m + (size_t)g * N * C)[it] = v;
     if (arg_out) arg_out[(size_t)g * items + it] = a;
   }
@@ -359,11 +408,15 @@ int grafp_mr_aggregate_fwd(const float* x, const int32_t* idx, int B, int N, int
     int grid = sm_count();
     if (grid > B) grid = B;
     const size_t smem = (size_t)stages * stage_bytes;
-    cudaFuncSetAttribute(mr_aggregate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    mr_aggregate_staged_kernel<<<grid, AGG_THREADS, smem, st>>>(
-        x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m,
-        reinterpret_cast<uint32_t*>(arg_out));
+    if (arg_out) {
+      cudaFuncSetAttribute(mr_aggregate_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      mr_aggregate_staged_kernel<true><<<grid, AGG_THREADS, smem, st>>>(
+          x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m, reinterpret_cast<uint32_t*>(arg_out));
+    } else {
+      cudaFuncSetAttribute(mr_aggregate_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      mr_aggregate_staged_kernel<false><<<grid, AGG_THREADS, smem, st>>>(
+          x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m, nullptr);
+    }
     return check_launch("mr_aggregate_staged");
   }
   for (int b0 = 0; b0 < B; b0 += 65535) {

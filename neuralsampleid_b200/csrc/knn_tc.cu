@@ -299,6 +299,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
       int bj[KMAX];
 #pragma unroll
       for (int t = 0; t < KMAX; ++t) { bd[t] = INFINITY; bj[t] = (int)(grow - gs); }
+      // Packed tiles (N < 128: 128 / N graphs per tile, block-diagonal): a warp's 32 rows belong to at most two
+      // graphs (one when N >= 32), whose columns lie inside ONE aligned window of max(N, 32) columns: only those
+      // 32-column chunks are scanned (warp-uniform bounds) -- the first version scanned all 128 columns of every row
+      // and masked 50-87 % of them away.
+      int c_begin = 0, c_end = p.bn;
+      if (!full_tile) {
+        const int w = p.N >= 32 ? p.N : 32;
+        c_begin = ((quad * 32) / w) * w;
+        c_end = c_begin + w;
+      }
       mbar_wait(&tmem_full_bar[buf], tph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
@@ -333,7 +343,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
         bj[0] = lt[0] ? jl : bj[0];
       };
       auto full_scan = [&]() {
-        for (int c = 0; c < p.bn; c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
           load_dist(c);
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
@@ -355,7 +365,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
             tb[t] = lo;
           }
         };
-        for (int c = 0; c < p.bn; c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
           load_dist(c);
           float m8[4];
 #pragma unroll
@@ -382,7 +392,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
         // the compiler emitted a divergent branch per distance (45 cycles each in the profile).  The
         // write pointer is clamped into the 8-slot sink once per 8 columns; reaching the sink = overflow.
         uint32_t wp = lst_addr;
-        for (int c = 0; c < p.bn; c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
           load_dist(c);
 #pragma unroll
           for (int b8 = 0; b8 < 4; ++b8) {
