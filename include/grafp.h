@@ -292,6 +292,12 @@ int grafp_bn_finalize(const double* sum, const double* sumsq, int64_t M, int C, 
                       const float* beta, const float* conv_bias, float eps, float momentum,
                       float* running_mean, float* running_var, float* scale, float* shift,
                       float* mean, float* invstd, void* stream);
+/* grafp_bn_finalize followed by grafp_affine_act on x (M, C) in one launch (the train step is launch-latency bound) */
+int grafp_bn_finalize_apply(const double* sum, const double* sumsq, int64_t M, int C, const float* gamma,
+                            const float* beta, const float* conv_bias, float eps, float momentum,
+                            float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                            float* invstd, const float* x, int64_t ld, int act, float act_param,
+                            const float* residual, int64_t ldr, float* out, int64_t ldo, void* stream);
 /* out = act(x * scale + shift) + residual   (C % 4 == 0; scale/shift/residual may be NULL) */
 int grafp_affine_act(const float* x, int64_t M, int C, int64_t ld, const float* scale,
                      const float* shift, int act, float act_param, const float* residual,
@@ -306,7 +312,8 @@ int grafp_bn_bwd_reduce(const float* dout, int64_t ldd, const float* raw, int64_
 int grafp_bn_bwd_apply(const float* dout, int64_t ldd, const float* raw, int64_t ld, int64_t M, int C,
                        const float* scale, const float* shift, const float* mean, const float* invstd,
                        int act, float act_param, int bn, const double* sum_dz, const double* sum_dz_xhat,
-                       float* draw, int64_t ldo, void* stream);
+                       float* draw, int64_t ldo, float* dgamma /* += sum_dz_xhat, may be NULL */,
+                       float* dbeta /* += sum_dz, may be NULL */, void* stream);
 int grafp_bn_param_grad(const double* sum_dz, const double* sum_dz_xhat, int C, float* dgamma,
                         float* dbeta, void* stream);
 /* weight gradient  dw[g*n + j, :] += sum_m dy[m, g*n + j] * A_g[m, :]  (A_g as in grafp_gemm_fwd:

@@ -75,7 +75,8 @@ SIGNATURES = {
     "grafp_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "grafp_affine_act": [_P, _L, _I, _L, _P, _P, _I, _F, _P, _L, _P, _L, _P],
     "grafp_bn_bwd_reduce": [_P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P],
-    "grafp_bn_bwd_apply": [_P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _L, _P],
+    "grafp_bn_bwd_apply": [_P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _L, _P, _P, _P],
+    "grafp_bn_finalize_apply": [_P, _P, _L, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P, _L, _P, _L, _P],
     "grafp_bn_param_grad": [_P, _P, _I, _P, _P, _P],
     "grafp_gemm_wgrad": [_P, _L, _P, _L, _I, _P, _L, _I, _L, _I, _I, _I, _P, _L, _I, _P, C.c_size_t, _P],
     "grafp_tap3_bwd_input": [_P, _L, _I, _I, _P, _P],

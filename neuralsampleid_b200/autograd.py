@@ -89,9 +89,15 @@ def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: t
     M, C = raw.shape
     if bn is not None:
         stats = ops.col_stats(raw)
-        ssmi = ops.bn_finalize(stats, M, bn.weight.detach(), bn.bias.detach(),
-                               bias.detach() if bias is not None else None, bn.eps, bn.momentum,
-                               bn.running_mean, bn.running_var)
+        if C % 4 == 0 and C <= 8192:
+            out, ssmi = ops.bn_finalize_apply(stats, raw, bn.weight.detach(), bn.bias.detach(),
+                                              bias.detach() if bias is not None else None, bn.eps, bn.momentum,
+                                              bn.running_mean, bn.running_var, act, slope, residual)
+        else:
+            ssmi = ops.bn_finalize(stats, M, bn.weight.detach(), bn.bias.detach(),
+                                   bias.detach() if bias is not None else None, bn.eps, bn.momentum,
+                                   bn.running_mean, bn.running_var)
+            out = ops.affine_act(raw, ssmi[0], ssmi[1], act, slope, residual)
         bn.num_batches_tracked += 1
         # running_mean / running_var were just updated through raw pointers (torch's version counters do not see
         # it): invalidate the eval path's folded (scale, shift) caches, which are keyed on _prep.sig()
@@ -102,7 +108,7 @@ def layer_fwd(tape: List[_Layer], a1: torch.Tensor, weight: nn.Parameter, w2d: t
         ssmi[3].fill_(1.0)
         if bias is not None:
             ssmi[1].copy_(bias.detach())
-    out = ops.affine_act(raw, ssmi[0], ssmi[1], act, slope, residual)
+        out = ops.affine_act(raw, ssmi[0], ssmi[1], act, slope, residual)
     L = _Layer()
     L.a1, L.a2, L.raw, L.ssmi, L.act, L.slope, L.bn = a1, a2, raw, ssmi, act, slope, bn
     L.w2d, L.groups, L.tap3_nodes, L.weight, L.bias, L.kind = w2d, groups, tap3_nodes, weight, bias, kind
@@ -148,25 +154,23 @@ def layer_bwd(L: _Layer, dout: torch.Tensor, grads: Dict, need_input: bool = Tru
               add_to: Optional[torch.Tensor] = None):
     """Returns (da1, da2).  The shortcut gradient of a residual layer is `dout` itself (caller's)."""
     bn = L.bn is not None
-    draw, sums = ops.bn_act_bwd(dout, L.raw, L.ssmi, L.act, L.slope, bn)
+    # the parameter gradients (dgamma / dbeta, or the bias gradient of a layer without BatchNorm) are accumulated by
+    # the apply kernel itself: into the flat gradient buffer when there is one, else into fresh tensors
+    pg = L.bn.weight if bn else None
+    pb = L.bn.bias if bn else L.bias
+    vg, vb = _sink_view(grads, pg), _sink_view(grads, pb)
+    tg = None if (pg is None or not pg.requires_grad or vg is not None) else torch.zeros_like(pg)
+    tb = None if (pb is None or not pb.requires_grad or vb is not None) else torch.zeros_like(pb)
+    draw, sums = ops.bn_act_bwd(dout, L.raw, L.ssmi, L.act, L.slope, bn,
+                                vg if vg is not None else tg, vb if vb is not None else tb)
+    if tg is not None:
+        _acc(grads, pg, tg)
+    if tb is not None:
+        _acc(grads, pb, tb)
     if bn:
-        vg, vb = _sink_view(grads, L.bn.weight), _sink_view(grads, L.bn.bias)
-        if vg is not None and vb is not None:
-            ops.bn_param_grad(sums, True, True, vg, vb)              # accumulates straight into the flat buffer
-        else:
-            dg, db = ops.bn_param_grad(sums, True, True)
-            _acc(grads, L.bn.weight, dg)
-            _acc(grads, L.bn.bias, db)
         # a conv bias in front of a train-mode BatchNorm has exactly zero gradient
         if L.bias is not None and L.bias.requires_grad and L.bias not in grads and _sink_view(grads, L.bias) is None:
             grads[L.bias] = torch.zeros_like(L.bias)
-    elif L.bias is not None:
-        vb = _sink_view(grads, L.bias)
-        if vb is not None:
-            ops.bn_param_grad(sums, False, True, None, vb)
-        else:
-            _, db = ops.bn_param_grad(sums, False, True)
-            _acc(grads, L.bias, db)
     if L.weight.requires_grad:
         vw = _sink_view(grads, L.weight)
         if vw is not None and L.kind == "dense":

@@ -115,6 +115,66 @@ __global__ void affine_act_kernel(const float* __restrict__ x, int64_t M, int C,
   }
 }
 
+// Train-mode BatchNorm in ONE launch: every block derives the C (scale, shift) pairs from the fp64 column sums into
+// shared memory (block 0 also publishes them with the saved mean / invstd and moves the running statistics), then
+// applies out = act(x * scale + shift) + residual.  Same arithmetic as bn_finalize_kernel + affine_act_kernel.
+__global__ void __launch_bounds__(256)
+bn_finalize_apply_kernel(const double* __restrict__ s0, const double* __restrict__ s1, int64_t M, int C,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ conv_bias, float eps, float momentum,
+                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                         float* __restrict__ scale_out, float* __restrict__ shift_out, float* __restrict__ mean_out,
+                         float* __restrict__ invstd_out, const float* __restrict__ x, int64_t ld, int act,
+                         float act_param, const float* __restrict__ residual, int64_t ldr, float* __restrict__ out,
+                         int64_t ldo) {
+  extern __shared__ __align__(16) float s_ss[];        // scale[C] | shift[C]
+  float* s_scale = s_ss;
+  float* s_shift = s_ss + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = s0[c] / (double)M;
+    double var = s1[c] / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+    const float sc = (float)(g * invstd), sh = (float)(b - mean * g * invstd);
+    s_scale[c] = sc;
+    s_shift[c] = sh;
+    if (blockIdx.x == 0) {
+      scale_out[c] = sc;
+      shift_out[c] = sh;
+      mean_out[c] = (float)mean;
+      invstd_out[c] = (float)invstd;
+      if (running_mean) {
+        const double bias = conv_bias ? (double)conv_bias[c] : 0.0;   // the conv bias is not in `raw`
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * (mean + bias));
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+      }
+    }
+  }
+  __syncthreads();
+  const int c4n = C >> 2;
+  const int64_t total = M * c4n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / c4n;
+    const int c = (int)(i - m * c4n) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + m * ld + c);
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+    float4 o;
+    o.x = apply_act(fmaf(v.x, sc.x, sh.x), act, act_param);
+    o.y = apply_act(fmaf(v.y, sc.y, sh.y), act, act_param);
+    o.z = apply_act(fmaf(v.z, sc.z, sh.z), act, act_param);
+    o.w = apply_act(fmaf(v.w, sc.w, sh.w), act, act_param);
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + m * ldr + c);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    *reinterpret_cast<float4*>(out + m * ldo + c) = o;
+  }
+}
+
 // draw = scale * (dz - [bn] (s0/M + xhat * s1/M)),  dz = dout * act'(raw*scale+shift)
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ raw,
                                     int64_t M, int C, int64_t ldd, int64_t ld,
@@ -122,9 +182,15 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dout, const float*
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     int act, float act_param, int bn, const double* __restrict__ s0,
                                     const double* __restrict__ s1, float* __restrict__ draw,
-                                    int64_t ldo) {
+                                    int64_t ldo, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int64_t total = M * C;
   const double invM = 1.0 / (double)M;
+  if (blockIdx.x == 0) {            // parameter gradients (accumulating): dgamma += sum dz*xhat, dbeta += sum dz
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dgamma) dgamma[c] += (float)s1[c];
+      if (dbeta) dbeta[c] += (float)s0[c];
+    }
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / C;
@@ -457,6 +523,21 @@ int grafp_bn_finalize(const double* sum, const double* sumsq, int64_t M, int C, 
   return check_launch("bn_finalize");
 }
 
+int grafp_bn_finalize_apply(const double* sum, const double* sumsq, int64_t M, int C, const float* gamma,
+                            const float* beta, const float* conv_bias, float eps, float momentum,
+                            float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                            float* invstd, const float* x, int64_t ld, int act, float act_param,
+                            const float* residual, int64_t ldr, float* out, int64_t ldo, void* stream) {
+  GRAFP_REQUIRE(sum && sumsq && scale && shift && mean && invstd && x && out && M > 0 && C > 0 && C % 4 == 0 &&
+                    C <= 8192, "bn_finalize_apply: bad arguments");
+  int64_t blocks = (M * (C / 4) + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();     // every block repeats the C-column finalize
+  bn_finalize_apply_kernel<<<(unsigned)blocks, 256, 2 * (size_t)C * sizeof(float), as_stream(stream)>>>(
+      sum, sumsq, M, C, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift, mean,
+      invstd, x, ld, act, act_param, residual, ldr, out, ldo);
+  return check_launch("bn_finalize_apply");
+}
+
 int grafp_affine_act(const float* x, int64_t M, int C, int64_t ld, const float* scale,
                      const float* shift, int act, float act_param, const float* residual,
                      int64_t ldr, float* out, int64_t ldo, void* stream) {
@@ -482,11 +563,13 @@ int grafp_bn_bwd_reduce(const float* dout, int64_t ldd, const float* raw, int64_
 int grafp_bn_bwd_apply(const float* dout, int64_t ldd, const float* raw, int64_t ld, int64_t M, int C,
                        const float* scale, const float* shift, const float* mean, const float* invstd,
                        int act, float act_param, int bn, const double* sum_dz, const double* sum_dz_xhat,
-                       float* draw, int64_t ldo, void* stream) {
+                       float* draw, int64_t ldo, float* dgamma, float* dbeta, void* stream) {
   GRAFP_REQUIRE(M > 0 && C > 0 && dout && raw && scale && shift && mean && invstd && draw,
                 "bn_bwd_apply: bad arguments");
+  GRAFP_REQUIRE((!dgamma && !dbeta) || (sum_dz && sum_dz_xhat), "bn_bwd_apply: parameter gradients need the column sums");
   bn_bwd_apply_kernel<<<grid_for(M * C), 256, 0, as_stream(stream)>>>(
-      dout, raw, M, C, ldd, ld, scale, shift, mean, invstd, act, act_param, bn, sum_dz, sum_dz_xhat, draw, ldo);
+      dout, raw, M, C, ldd, ld, scale, shift, mean, invstd, act, act_param, bn, sum_dz, sum_dz_xhat, draw, ldo,
+      dgamma, dbeta);
   return check_launch("bn_bwd_apply");
 }
 

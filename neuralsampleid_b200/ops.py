@@ -561,9 +561,27 @@ def affine_act(x: torch.Tensor, scale, shift, act=None, act_param: float = 0.0, 
     return out
 
 
-def bn_act_bwd(dout: torch.Tensor, raw: torch.Tensor, ssmi: torch.Tensor, act, act_param: float, bn: bool):
+def bn_finalize_apply(stats: torch.Tensor, raw: torch.Tensor, gamma, beta, conv_bias, eps: float, momentum: float,
+                      running_mean, running_var, act=None, act_param: float = 0.0, residual=None):
+    """bn_finalize + affine_act in one launch -> (out (M, C), ssmi fp32 (4, C) = scale, shift, mean, invstd)."""
+    raw = _chk(raw, name="raw")
+    M, Cc = raw.shape
+    ssmi = torch.empty((4, Cc), device=raw.device, dtype=torch.float32)
+    out = torch.empty_like(raw)
+    with torch.cuda.device(raw.device):
+        check(_lib.load().grafp_bn_finalize_apply(
+            _ptr(stats[0]), _ptr(stats[1]), M, Cc, _ptr(gamma), _ptr(beta), _ptr(conv_bias), eps, momentum,
+            _ptr(running_mean), _ptr(running_var), _ptr(ssmi[0]), _ptr(ssmi[1]), _ptr(ssmi[2]), _ptr(ssmi[3]),
+            _ptr(raw), raw.stride(0), act_code(act), act_param, _ptr(residual),
+            residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), _stream(raw)), "bn_finalize_apply")
+    return out, ssmi
+
+
+def bn_act_bwd(dout: torch.Tensor, raw: torch.Tensor, ssmi: torch.Tensor, act, act_param: float, bn: bool,
+               dgamma=None, dbeta=None):
     """Backward of (BatchNorm | bias) + activation.  ssmi: (4, C) scale/shift/mean/invstd.
-    Returns (draw (M, C), sums fp64 (2, C) = [sum dz, sum dz*xhat])."""
+    Returns (draw (M, C), sums fp64 (2, C) = [sum dz, sum dz*xhat]).  ``dgamma`` / ``dbeta``: (C,) fp32 views that
+    accumulate the parameter gradients inside the apply kernel (saves the separate bn_param_grad launch)."""
     dout = _chk(dout, name="dout")
     raw = _chk(raw, name="raw")
     M, Cc = raw.shape
@@ -577,8 +595,8 @@ def bn_act_bwd(dout: torch.Tensor, raw: torch.Tensor, ssmi: torch.Tensor, act, a
                                       _ptr(sums[1]), _stream(raw)), "bn_bwd_reduce")
         check(lib.grafp_bn_bwd_apply(_ptr(dout), dout.stride(0), _ptr(raw), raw.stride(0), M, Cc, _ptr(ssmi[0]),
                                      _ptr(ssmi[1]), _ptr(ssmi[2]), _ptr(ssmi[3]), a, act_param, int(bn),
-                                     _ptr(sums[0]), _ptr(sums[1]), _ptr(draw), draw.stride(0), _stream(raw)),
-              "bn_bwd_apply")
+                                     _ptr(sums[0]), _ptr(sums[1]), _ptr(draw), draw.stride(0), _ptr(dgamma), _ptr(dbeta),
+                                     _stream(raw)), "bn_bwd_apply")
     return draw, sums
 
 
