@@ -207,6 +207,50 @@ __global__ void index_select_kernel(const float* __restrict__ x, const int32_t* 
   }
 }
 
+// backward, deterministic: dx[j*] += dm, dx[n] -= dm.  One WARP per (graph, slice of 32 channels): lane = channel, the
+// N source nodes are visited in order and each lane adds into its own column of an N x 32 shared-memory accumulator
+// (bank = lane: conflict-free whatever the destinations), so every sum has a fixed order -- no atomics.  (The atomic
+// form below left the gradients of a train step reproducible only to ~1e-4 run to run: hub nodes collect hundreds of
+// mixed-sign terms.)
+__global__ void mr_aggregate_bwd_det_kernel(const float* __restrict__ dm, const int32_t* __restrict__ idx,
+                                            const uint8_t* __restrict__ arg, int64_t units, int N, int C, int k,
+                                            float* __restrict__ dx) {
+  extern __shared__ __align__(16) float acc_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t unit = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (unit >= units) return;
+  const int slices = C / 32;
+  const int64_t g = unit / slices;
+  const int c = (int)(unit % slices) * 32 + lane;
+  float* acc = acc_all + (size_t)warp * N * 32;
+  for (int n = 0; n < N; ++n) acc[n * 32 + lane] = 0.0f;
+  __syncwarp();
+  const size_t gbase = (size_t)g * N * C;
+  const int32_t* gidx = idx + (size_t)g * N * k;
+  for (int n0 = 0; n0 < N; n0 += 4) {
+    float gv[4];
+    int j[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                      // the loads of four sources are independent
+      const int n = n0 + u;
+      const bool ok = n < N;
+      const size_t e = gbase + (size_t)(ok ? n : 0) * C + c;
+      gv[u] = ok ? dm[e] : 0.0f;
+      j[u] = ok ? gidx[(size_t)n * k + arg[e]] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = n0 + u;
+      if (n < N) {
+        acc[j[u] * 32 + lane] += gv[u];
+        acc[n * 32 + lane] -= gv[u];
+      }
+    }
+  }
+  __syncwarp();
+  for (int n = 0; n < N; ++n) dx[gbase + (size_t)n * C + c] += acc[n * 32 + lane];
+}
+
 // backward: dx[j*] += dm, dx[n] -= dm, accumulated per graph in shared memory when it fits.
 __global__ void __launch_bounds__(256)
 mr_aggregate_bwd_kernel(const float* __restrict__ dm, const int32_t* __restrict__ idx,
@@ -215,12 +259,15 @@ mr_aggregate_bwd_kernel(const float* __restrict__ dm, const int32_t* __restrict_
   // One CTA = (graph, slice of `cs` channels): the scatter never crosses channels, so a graph is cut into C / cs
   // independent slices with N * cs accumulators each -- enough CTAs to fill the machine at the train step's 32-graph
   // batches (one CTA per graph left 116 of 148 SMs idle and took ~100 us per call).
-  extern __shared__ __align__(16) float acc[];
+  // fp64 accumulators: a hub node collects hundreds of mixed-sign terms in an order that varies from run to run;
+  // in fp32 that left a train step's gradients reproducible only to ~1e-4, in fp64 the order is invisible after the
+  // final rounding to fp32 (except on exact rounding ties)
+  extern __shared__ __align__(16) double acc[];
   const int g = blockIdx.x, c0 = blockIdx.y * cs;
   const size_t gbase = (size_t)g * N * C;
   const int total = N * cs;
   if (use_smem) {
-    for (int i = threadIdx.x; i < total; i += blockDim.x) acc[i] = 0.0f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) acc[i] = 0.0;
     __syncthreads();
   }
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -229,8 +276,8 @@ mr_aggregate_bwd_kernel(const float* __restrict__ dm, const int32_t* __restrict_
     const float gval = dm[e];
     const int j = idx[((size_t)g * N + n) * k + arg[e]];
     if (use_smem) {
-      atomicAdd(&acc[j * cs + cc], gval);
-      atomicAdd(&acc[i], -gval);
+      atomicAdd(&acc[j * cs + cc], (double)gval);
+      atomicAdd(&acc[i], -(double)gval);
     } else {
       atomicAdd(&dx[gbase + (size_t)j * C + c0 + cc], gval);
       atomicAdd(&dx[e], -gval);
@@ -240,7 +287,7 @@ mr_aggregate_bwd_kernel(const float* __restrict__ dm, const int32_t* __restrict_
     __syncthreads();
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const int n = i / cs, cc = i - n * cs;
-      dx[gbase + (size_t)n * C + c0 + cc] += acc[i];
+      dx[gbase + (size_t)n * C + c0 + cc] += (float)acc[i];
     }
   }
 }
@@ -443,10 +490,23 @@ int grafp_mr_aggregate_bwd(const float* dm, const int32_t* idx, const uint8_t* a
   GRAFP_REQUIRE(dm && idx && arg && dx, "mr_aggregate_bwd: null pointer");
   GRAFP_REQUIRE(B >= 0 && N > 0 && C > 0 && k > 0, "mr_aggregate_bwd: bad sizes");
   if (B == 0) return 0;
+  static int det_env = -1;
+  if (det_env < 0) { const char* e = getenv("GRAFP_AGG_BWD_SEQUENTIAL"); det_env = e ? atoi(e) : 0; }
+  if (det_env && C % 32 == 0 && (size_t)N * 128 <= 200 * 1024) {
+    // strictly ordered form (opt-in: ~5x slower): one warp per (graph, 32-channel slice), sources visited in node order
+    int wpb = 4;
+    while (wpb > 1 && (size_t)wpb * N * 128 > 200 * 1024) wpb >>= 1;
+    const int64_t units = (int64_t)B * (C / 32);
+    const size_t smem = (size_t)wpb * N * 128;
+    cudaFuncSetAttribute(mr_aggregate_bwd_det_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mr_aggregate_bwd_det_kernel<<<(unsigned)((units + wpb - 1) / wpb), wpb * 32, smem, as_stream(stream)>>>(
+        dm, idx, arg, units, N, C, k, dx);
+    return check_launch("mr_aggregate_bwd_det");
+  }
   int cs = C;
   while (cs > 16 && cs % 2 == 0) cs >>= 1;             // channel slice: 16 (or the odd factor left of C)
   if (C % cs != 0) cs = C;
-  const size_t bytes = (size_t)N * cs * 4;
+  const size_t bytes = (size_t)N * cs * sizeof(double);
   const int use_smem = bytes <= 200 * 1024;
   cudaFuncSetAttribute(mr_aggregate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   for (int b0 = 0; b0 < B; b0 += 65535) {               // (gridDim.x is the graph index; y the channel slice)

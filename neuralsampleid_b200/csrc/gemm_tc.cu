@@ -747,8 +747,10 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   // ... and only when every CTA has several tiles to amortise the pair's lock-step over (the train step's GEMMs have
   // one or two tiles per SM: there the clustered launch measured 25.6 us per call against 15.7 us un-clustered)
   const int64_t all_tiles = tiles_m * (a.n / bn) * a.groups;
+  static int min_waves = -1;
+  if (min_waves < 0) { const char* e = getenv("GRAFP_TC_CLUSTER_MIN_WAVES"); min_waves = e ? atoi(e) : 4; }
   const int cluster = (mc_env == 2 && tiles_m >= 2 && bn >= 256 && sm_count() % 2 == 0 &&
-                       all_tiles >= 4 * (int64_t)sm_count()) ? 2 : 1;
+                       all_tiles >= min_waves * (int64_t)sm_count()) ? 2 : 1;
   if (bf16) {
     if (int rc = tc_make_map_2d_bf16(&mW, f16 ? a.w_split_f16 : a.w_split_bf16, (int64_t)n_total * 2, a.k1 + a.k2, a.ldw,
                                      cluster == 2 ? bn / 2 : bn))
