@@ -188,6 +188,19 @@ int grafp_split_bf16(const float* w, int64_t count, void* out_bf16_hi_lo, void* 
  * out[count:2*count] = f16(w*2^s - f16(w*2^s)); values are clamped to the finite half range */
 int grafp_split_f16(const float* w, int64_t count, float prescale, void* out_f16_hi_lo, void* stream);
 
+/* ---- fused node FFN ------------------------------------------------------------------------------
+ * FFN.forward (encoder/graph_encoder.py:82-89), eval-mode BatchNorm folded:
+ *   y = x + scale2 * ( act(scale1 * (x W1^T) + shift1) W2^T ) + shift2
+ * in ONE kernel: the (M, Hd) hidden tensor never reaches HBM (it is the largest tensor of the forward).  Both GEMMs run
+ * on the f16x3 engine with the operand values and accumulation order of the two grafp_gemm_fwd launches they replace:
+ * the result is bit-identical.  x (M, C) fp32 (also the shortcut); w1_split_f16 (2*Hd, C), w2_split_f16 (2*C, Hd): the
+ * grafp_split_f16 planes of the pre-scaled weights, w*_unscale = 2^-s.  C in {64, 128}, Hd a multiple of 64. */
+int grafp_ffn_fused_supported(int64_t M, int C, int Hd);
+int grafp_ffn_fused_fwd(const float* x, int64_t ldx, int64_t M, int C, int Hd, const void* w1_split_f16, int64_t ldw1,
+                        float w1_unscale, const float* scale1, const float* shift1, int act, float act_param,
+                        const void* w2_split_f16, int64_t ldw2, float w2_unscale, const float* scale2,
+                        const float* shift2, float* y, int64_t ldy, void* stream);
+
 /* Stem: Conv2d(Cin -> Cout, 1x1, no bias) + BatchNorm2d + activation on a tiny input width
  * (encoder/graph_encoder.py:151-153, 201-202), fused with the layout change: reads the reference's
  * (B, Cin, N) tensor directly (nchw != 0) or node-major (B*N, Cin) features (nchw == 0, what

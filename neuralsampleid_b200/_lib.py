@@ -56,6 +56,8 @@ SIGNATURES = {
     "grafp_split_bf16": [_P, _L, _P, _P],
     "grafp_split_f16": [_P, _L, _F, _P, _P],
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
+    "grafp_ffn_fused_supported": [_L, _I, _I],
+    "grafp_ffn_fused_fwd": [_P, _L, _L, _I, _I, _P, _L, _F, _P, _P, _I, _F, _P, _L, _F, _P, _P, _P, _L, _P],
     "grafp_frame_window_fwd": [_P, _L, _P, _I, _I, _L, _P, _P],
     "grafp_power_spectrum_fwd": [_P, _L, _L, _I, _I, _P, _L, _P],
     "grafp_amplitude_to_db_fwd": [_P, _L, _F, _F, _F, _P, _P],

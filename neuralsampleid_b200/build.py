@@ -10,10 +10,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgrafp_sm100a.so")
-SOURCES = ["misc.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "knn.cu", "knn_tc.cu", "knn_big.cu", "aggregate.cu",
+SOURCES = ["misc.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "ffn_fused.cu", "knn.cu", "knn_tc.cu", "knn_big.cu", "aggregate.cu",
            "ntxent.cu", "train.cu", "wgrad_tc.cu", "attention.cu", "topk.cu", "frontend.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v"] + os.environ.get("GRAFP_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

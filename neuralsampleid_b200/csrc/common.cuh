@@ -98,6 +98,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Latency-critical wait: plain polling without the suspend-time hint (a hardware-suspended warp wakes up noticeably
+// later than a polling one; used where a hand-off sits on the critical path of a short dependent chain).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint64_t t0 = global_timer_ns();
+  while (true) {
+#pragma unroll 1
+    for (int i = 0; i < 65536; ++i) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(smem_u32(bar)), "r"(parity)
+          : "memory");
+      if (ok) return;
+    }
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("grafp: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 // 1-D bulk async copy global -> shared, completion on an mbarrier (TMA engine, UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes,
                                          uint64_t* bar) {

@@ -1,0 +1,446 @@
+// Fused node FFN (sm_100a):  y = x + s2 * (act(s1 * (x W1^T) + t1) W2^T) + t2   in ONE kernel, the hidden tile on chip.
+// Reference: FFN.forward (encoder/graph_encoder.py:82-89) with eval-mode BatchNorm folded into (s, t).
+//
+// The two 1x1-conv GEMMs of the FFN are HBM-bound at C <= 128 (stages 1-2 of size 't'): the 4C-wide hidden tensor
+// (1.07 GB at 4096 segments) is written by fc1 and read back by fc2.  Here a persistent CTA owns 128 rows at a time:
+//   TMA        x rows (fp32, 128B swizzle) through a small raw ring; weight k-blocks (pre-split fp16 hi/lo) through
+//              a ring, in exactly the order the MMA warp consumes them
+//   transform  x -> fp16 hi / lo operand k-blocks (the f16x3 split of gemm_tc.cu), resident for the whole tile
+//   GEMM 1     for every chunk of 64 hidden columns: acc1[j & 1] (TMEM, 64 columns) = x W1_j^T, 3 kind::f16 passes
+//   epilogue 1 TMEM -> registers -> s1 / t1 / activation -> fp16 hi / lo -> shared memory, written directly in the
+//              K-major 64B-swizzled operand layout GEMM 2 reads (the same layout the un-fused fc1 epilogue stages for
+//              its TMA store of the split activation)
+//   GEMM 2     acc2 (TMEM, C columns) += h_j W2[:, chunk j]^T
+//   epilogue 2 s2 / t2 + the shortcut x (re-read from L2) -> y
+// GEMM 1 of chunk j+1 is issued before GEMM 2 of chunk j, so the tensor pipe works while epilogue 1 converts.
+// The arithmetic (operand values, accumulation order over k) is that of the two gemm_tc.cu launches it replaces:
+// the result is bit-identical (tests/test_gpu_kernels.py::test_ffn_fused_bit_exact).
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+
+namespace grafp {
+
+#ifndef FF_WAIT
+#define FF_WAIT mbar_wait
+#endif
+// w0 TMA x, w1 MMA + TMEM, w2 TMA W, w4-7 epilogue 2, w8-11 transform, w12-27 epilogue 1 (the activation is the
+// instruction-heaviest stage: 16 warps = {chunk parity} x {32-column half} x {TMEM lane quarter})
+constexpr int FF_THREADS = 896;
+constexpr int FF_HC = 64;            // hidden columns per chunk
+constexpr int FF_RAW = 2;            // fp32 x k-blocks in flight
+constexpr int FF_WMAX = 6;           // weight ring slots
+constexpr uint32_t FF_KB_BYTES = TC_BM * 64;          // one 128-row fp16 k-block (32 columns): 8 KB
+
+#ifdef FF_TRACE
+__device__ unsigned long long g_ff_trace[3 * 1024];
+#define FF_T(region, id)                                                                          \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && tr_n < 1023) g_ff_trace[(region) * 1024 + tr_n++] = (global_timer_ns() << 8) | (id); \
+  } while (0)
+#define FF_ACC(var, stmt) do { const long long c0_ = clock64(); stmt; var += clock64() - c0_; } while (0)
+#else
+#define FF_T(region, id) do { } while (0)
+#define FF_ACC(var, stmt) do { stmt; } while (0)
+#endif
+
+struct FfnParams {
+  int C, Hd;                 // channels, hidden width
+  int64_t M;
+  int wslots; uint32_t wslot_bytes;
+  const float* scale1; const float* shift1; float unscale1;
+  const float* scale2; const float* shift2; float unscale2;
+  int act; float act_param;
+  const float* x; int64_t ldx;       // shortcut (the same tensor as the A operand)
+  float* y; int64_t ldy;
+};
+
+// one arrival per warp (the barriers count warps): 32 serialised arrivals on one barrier word cost more than the sync
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+__device__ __forceinline__ uint32_t ff_pack(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 ff_unpack(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
+constexpr int FF_HMAX = 1024;        // widest hidden layer (its folded scale / shift are staged in shared memory)
+
+// sc = folded scale * weight un-scale (one fp32 product, formed once at kernel start), sh = folded shift: shared memory
+template <int ACT>
+__device__ __forceinline__ void ff_act32(float (&v)[32], const float* sc, const float* sh, float act_param) {
+#pragma unroll
+  for (int q = 0; q < 32; q += 4) {
+    const float4 s4 = *reinterpret_cast<const float4*>(sc + q);
+    const float4 t4 = *reinterpret_cast<const float4*>(sh + q);
+    v[q + 0] = apply_act(fmaf(v[q + 0], s4.x, t4.x), ACT, act_param);
+    v[q + 1] = apply_act(fmaf(v[q + 1], s4.y, t4.y), ACT, act_param);
+    v[q + 2] = apply_act(fmaf(v[q + 2], s4.z, t4.z), ACT, act_param);
+    v[q + 3] = apply_act(fmaf(v[q + 3], s4.w, t4.w), ACT, act_param);
+  }
+}
+
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t raw_full[FF_RAW], raw_empty[FF_RAW];
+  __shared__ __align__(8) uint64_t xop_full, xop_free;
+  __shared__ __align__(8) uint64_t w_full[FF_WMAX], w_empty[FF_WMAX];
+  __shared__ __align__(8) uint64_t acc1_full[2], acc1_empty[2];
+  __shared__ __align__(8) uint64_t h_full[2], h_empty[2];
+  __shared__ __align__(8) uint64_t acc2_full[2], acc2_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_sc1[FF_HMAX], s_sh1[FF_HMAX], s_sc2[128], s_sh2[128];
+
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int nkb1 = p.C / 32;                 // k-blocks of GEMM 1
+  const int nch = p.Hd / FF_HC;              // hidden chunks
+  const int64_t tiles = (p.M + TC_BM - 1) / TC_BM;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // [ x operand: nkb1 x (hi 8 KB | lo 8 KB) ][ h operand: 2 buffers x 2 k-blocks x (hi | lo) ][ raw ring ][ W ring ]
+  uint8_t* xop = smem;
+  uint8_t* hop = xop + (size_t)nkb1 * 2 * FF_KB_BYTES;
+  uint8_t* rawb = hop + 2 * 2 * 2 * FF_KB_BYTES;
+  uint8_t* wring = rawb + FF_RAW * TC_A_BYTES;
+  auto x_hi = [&](int kb) { return xop + (size_t)kb * 2 * FF_KB_BYTES; };
+  auto h_hi = [&](int buf, int kb) { return hop + ((size_t)buf * 2 + kb) * 2 * FF_KB_BYTES; };
+  auto w_slot = [&](int s) { return wring + (size_t)s * p.wslot_bytes; };
+  const uint32_t w1_bytes = 2u * FF_HC * 64u;            // hi + lo of one W1 k-block (64 rows x 64 B)
+  const uint32_t w2_bytes = 2u * (uint32_t)p.C * 64u;    // hi + lo of one W2 k-block (C rows x 64 B)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int i = 0; i < FF_RAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
+    mbar_init(&xop_full, 4);
+    mbar_init(&xop_free, 1);
+    for (int i = 0; i < FF_WMAX; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 8);
+      mbar_init(&h_full[i], 8); mbar_init(&h_empty[i], 1);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.Hd; i += FF_THREADS) { s_sc1[i] = p.scale1[i] * p.unscale1; s_sh1[i] = p.shift1[i]; }
+  for (int i = threadIdx.x; i < p.C; i += FF_THREADS) { s_sc2[i] = p.scale2[i] * p.unscale2; s_sh2[i] = p.shift2[i]; }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t t_acc1 = tmem_base;                      // 2 x 64 columns
+  const uint32_t t_acc2 = tmem_base + 128;                // 2 x C columns (C <= 128)
+
+  if (warp == 0) {
+    // ===== TMA: x rows of my tiles, k-block by k-block, into the raw ring =====
+    if (lane == 0) {
+      uint32_t r = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+        for (int kb = 0; kb < nkb1; ++kb, ++r) {
+          const int s = r % FF_RAW;
+          mbar_wait(&raw_empty[s], ((r / FF_RAW) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&raw_full[s], TC_A_BYTES);
+          tma_load_2d(rawb + (size_t)s * TC_A_BYTES, &tmX, kb * 32, (int)(tile * TC_BM), &raw_full[s]);
+        }
+    }
+  } else if (warp == 2) {
+    // ===== TMA: weight k-blocks in the MMA's consumption order =====
+    if (lane == 0) {
+      uint32_t w = 0;
+      int tr_n = 0; (void)tr_n;
+      auto load_w1 = [&](int j) {
+        for (int kb = 0; kb < nkb1; ++kb, ++w) {
+          const int s = w % p.wslots;
+          mbar_wait(&w_empty[s], ((w / p.wslots) & 1u) ^ 1u);
+          FF_T(2, 30);
+          mbar_arrive_expect_tx(&w_full[s], w1_bytes);
+          tma_load_2d(w_slot(s), &tmW1, kb * 32, j * FF_HC, &w_full[s]);
+          tma_load_2d(w_slot(s) + FF_HC * 64, &tmW1, kb * 32, p.Hd + j * FF_HC, &w_full[s]);
+        }
+      };
+      auto load_w2 = [&](int j) {
+        for (int kb = 0; kb < FF_HC / 32; ++kb, ++w) {
+          const int s = w % p.wslots;
+          mbar_wait(&w_empty[s], ((w / p.wslots) & 1u) ^ 1u);
+          FF_T(2, 31);
+          mbar_arrive_expect_tx(&w_full[s], w2_bytes);
+          tma_load_2d(w_slot(s), &tmW2, j * FF_HC + kb * 32, 0, &w_full[s]);
+          tma_load_2d(w_slot(s) + (size_t)p.C * 64, &tmW2, j * FF_HC + kb * 32, p.C, &w_full[s]);
+        }
+      };
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int j = 0; j < nch; ++j) {
+          load_w1(j);
+          if (j >= 1) load_w2(j - 1);
+        }
+        load_w2(nch - 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: converged warp, one elected lane issues (tc_common.cuh) =====
+    {
+      const uint32_t idesc1 = umma_idesc_f16(TC_BM, FF_HC), idesc2 = umma_idesc_f16(TC_BM, p.C);
+      const uint32_t d_x0 = umma_desc_lo(smem_u32(xop)), d_h0 = umma_desc_lo(smem_u32(hop)), d_w0 = umma_desc_lo(smem_u32(wring));
+      constexpr uint32_t d_kb = (2 * FF_KB_BYTES) >> 4, d_lo = FF_KB_BYTES >> 4;     // k-block stride, hi -> lo plane
+      const uint32_t d_wslot = p.wslot_bytes >> 4, d_w1lo = (FF_HC * 64) >> 4, d_w2lo = ((uint32_t)p.C * 64u) >> 4;
+      uint32_t ws = 0, wph = 0, c1 = 0, hcnt = 0, ti = 0;     // W slot + phase, GEMM-1 chunks, GEMM-2 chunks, tiles
+      long long cy_w = 0, cy_h = 0, cy_a = 0, cy_x = 0, cy_2 = 0; const long long cy_t0 = clock64(); (void)cy_t0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+        const uint32_t a2 = t_acc2 + (ti & 1u) * (uint32_t)p.C;
+        auto gemm = [&](uint32_t tacc, uint32_t da0, int nkb, uint32_t d_wlo, uint32_t idesc, bool fresh, uint64_t* done) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
+            tc_fence_after();
+            const uint32_t dah = da0 + kb * d_kb, dal = dah + d_lo, dbh = d_w0 + ws * d_wslot, dbl = dbh + d_wlo;
+            if (elect_one()) {
+#pragma unroll
+              for (uint32_t k = 0; k < 4; k += 2) {
+                umma_f16_lh(tacc, dal + k, dbh + k, UMMA_HI_SW64, idesc, (!fresh || kb > 0 || k > 0) ? 1u : 0u);
+                umma_f16_lh(tacc, dah + k, dbl + k, UMMA_HI_SW64, idesc, 1u);
+                umma_f16_lh(tacc, dah + k, dbh + k, UMMA_HI_SW64, idesc, 1u);
+              }
+              umma_commit(&w_empty[ws]);
+              if (kb == nkb - 1) umma_commit(done);
+            }
+            __syncwarp();
+            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
+          }
+        };
+        auto gemm1 = [&](int j) {
+          const uint32_t b = c1 & 1u;
+          FF_ACC(cy_a, FF_WAIT(&acc1_empty[b], ((c1 >> 1) & 1u) ^ 1u));
+          tc_fence_after();
+          gemm(t_acc1 + b * FF_HC, d_x0, nkb1, d_w1lo, idesc1, true, &acc1_full[b]);
+          ++c1;
+        };
+        auto gemm2 = [&](int j) {
+          const uint32_t b = hcnt & 1u;
+          FF_ACC(cy_h, FF_WAIT(&h_full[b], (hcnt >> 1) & 1u));
+          if (j == 0) FF_ACC(cy_2, FF_WAIT(&acc2_empty[ti & 1u], ((ti >> 1) & 1u) ^ 1u));
+          tc_fence_after();
+          gemm(a2, d_h0 + b * 2 * d_kb, FF_HC / 32, d_w2lo, idesc2, j == 0, &h_empty[b]);
+          ++hcnt;
+        };
+        FF_ACC(cy_x, FF_WAIT(&xop_full, ti & 1u));
+        tc_fence_after();
+        for (int j = 0; j < nch; ++j) {
+          gemm1(j);
+          if (j == nch - 1) {       // every GEMM 1 of this tile issued: x operand reusable when they retire
+            if (elect_one()) umma_commit(&xop_free);
+            __syncwarp();
+          }
+          if (j >= 1) gemm2(j - 1);
+        }
+        gemm2(nch - 1);
+        if (elect_one()) umma_commit(&acc2_full[ti & 1u]);
+        __syncwarp();
+      }
+#ifdef FF_TRACE
+      if (blockIdx.x == 0 && lane == 0) {
+        g_ff_trace[0] = clock64() - cy_t0; g_ff_trace[1] = cy_w; g_ff_trace[2] = cy_h; g_ff_trace[3] = cy_a;
+        g_ff_trace[4] = cy_x; g_ff_trace[5] = cy_2; g_ff_trace[6] = ti;
+      }
+#endif
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ===== transform: fp32 x k-block (128B-swizzled rows) -> fp16 hi / lo operand k-block (64B-swizzled rows) =====
+    const int t = threadIdx.x - 256;
+    uint32_t r = 0, ti = 0;
+    int tr_n = 1 << 20; (void)tr_n;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+      for (int kb = 0; kb < nkb1; ++kb, ++r) {
+        const int s = r % FF_RAW;
+        mbar_wait(&raw_full[s], (r / FF_RAW) & 1u);
+        FF_T(2, 20);
+        const float4* raw = reinterpret_cast<const float4*>(rawb + (size_t)s * TC_A_BYTES);
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = raw[t + 128 * i];
+        fence_proxy_async_smem();
+        warp_arrive(&raw_empty[s], lane);
+        if (kb == 0 && ti > 0) mbar_wait(&xop_free, (ti - 1) & 1u);      // the previous tile's GEMM 1s have retired
+        FF_T(2, 21);
+        uint8_t* hi = x_hi(kb);
+        uint8_t* lo = hi + FF_KB_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = t + 128 * i;
+          const int row = q >> 3;
+          const int lc = (q & 7) ^ (row & 7);                          // logical 4-float chunk 0..7
+          const uint32_t dst = (uint32_t)row * 64u + ((uint32_t)((lc >> 1) ^ ((row >> 1) & 3)) << 4) + ((uint32_t)(lc & 1) << 3);
+          uint2 hv, lv;
+          hv.x = ff_pack(v[i].x, v[i].y);
+          hv.y = ff_pack(v[i].z, v[i].w);
+          const float2 f01 = ff_unpack(hv.x), f23 = ff_unpack(hv.y);
+          lv.x = ff_pack(v[i].x - f01.x, v[i].y - f01.y);
+          lv.y = ff_pack(v[i].z - f23.x, v[i].w - f23.y);
+          *reinterpret_cast<uint2*>(hi + dst) = hv;
+          *reinterpret_cast<uint2*>(lo + dst) = lv;
+        }
+      }
+      fence_proxy_async_smem();
+      warp_arrive(&xop_full, lane);
+      FF_T(2, 22);
+    }
+  } else if (warp >= 12) {
+    // ===== epilogue 1: hidden chunk -> s1 / t1 / activation -> fp16 hi / lo operand of GEMM 2 =====
+    // Warp (parity, half, quad) converts columns [32 half, 32 half + 32) -- k-block `half` of the h operand -- of the
+    // chunks whose accumulator buffer is `parity`, for TMEM lanes [32 quad, 32 quad + 32).
+    const int quad = warp & 3;
+    const int sub = (warp - 12) >> 2;
+    const uint32_t mine = sub & 1, half = sub >> 1;
+    const int row = quad * 32 + lane;
+    uint32_t c1 = 0;
+    int tr_n = (warp == 12 && lane == 0) ? 0 : 1 << 20; (void)tr_n;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int j = 0; j < nch; ++j, ++c1) {
+        const uint32_t b = c1 & 1u;
+        if (b != mine) continue;
+        const float* sc = s_sc1 + j * FF_HC + half * 32;
+        const float* sh = s_sh1 + j * FF_HC + half * 32;
+        FF_WAIT(&acc1_full[b], (c1 >> 1) & 1u);
+        tc_fence_after();
+        FF_T(1, 10);
+        const uint32_t tacc = t_acc1 + b * FF_HC + half * 32u + ((uint32_t)(quad * 32) << 16);
+        float v[32];
+        tmem_ld16_nowait(tacc, v);
+        tmem_ld16_nowait(tacc + 16u, v + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        warp_arrive(&acc1_empty[b], lane);
+        FF_T(1, 11);
+        switch (p.act) {
+          case GRAFP_ACT_NONE:  ff_act32<GRAFP_ACT_NONE>(v, sc, sh, p.act_param); break;
+          case GRAFP_ACT_RELU:  ff_act32<GRAFP_ACT_RELU>(v, sc, sh, p.act_param); break;
+          case GRAFP_ACT_LEAKY: ff_act32<GRAFP_ACT_LEAKY>(v, sc, sh, p.act_param); break;
+          case GRAFP_ACT_GELU:  ff_act32<GRAFP_ACT_GELU>(v, sc, sh, p.act_param); break;
+          default:              ff_act32<GRAFP_ACT_ELU>(v, sc, sh, p.act_param); break;
+        }
+        FF_T(1, 12);
+        FF_WAIT(&h_empty[b], ((c1 >> 1) & 1u) ^ 1u);                // GEMM 2 of chunk c1 - 2 has read this buffer
+        FF_T(1, 13);
+        uint8_t* hi = h_hi(b, half);
+        uint8_t* lo = hi + FF_KB_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hp[4], lp[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hp[e] = ff_pack(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            const float2 f = ff_unpack(hp[e]);
+            lp[e] = ff_pack(v[8 * q + 2 * e] - f.x, v[8 * q + 2 * e + 1] - f.y);
+          }
+          const uint32_t off = (uint32_t)row * 64u + ((uint32_t)(q ^ ((row >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
+        fence_proxy_async_smem();
+        warp_arrive(&h_full[b], lane);
+        FF_T(1, 14);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue 2: output tile -> s2 / t2 + shortcut -> y =====
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    uint32_t ti = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+      const int64_t row = tile * TC_BM + r;
+      const bool ok = row < p.M;
+      FF_WAIT(&acc2_full[ti & 1u], (ti >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = t_acc2 + (ti & 1u) * (uint32_t)p.C + ((uint32_t)(quad * 32) << 16);
+      for (int c = 0; c < p.C; c += 16) {
+        float4 res[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          res[q] = ok ? __ldg(reinterpret_cast<const float4*>(p.x + row * p.ldx + c + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[16];
+        tmem_ld16_nowait(tacc + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c + 16 >= p.C) {
+          tc_fence_before();
+          warp_arrive(&acc2_empty[ti & 1u], lane);
+        }
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 s4 = *reinterpret_cast<const float4*>(s_sc2 + c + 4 * q);
+            const float4 t4 = *reinterpret_cast<const float4*>(s_sh2 + c + 4 * q);
+            float4 o;
+            o.x = fmaf(v[4 * q + 0], s4.x, t4.x) + res[q].x;
+            o.y = fmaf(v[4 * q + 1], s4.y, t4.y) + res[q].y;
+            o.z = fmaf(v[4 * q + 2], s4.z, t4.z) + res[q].z;
+            o.w = fmaf(v[4 * q + 3], s4.w, t4.w) + res[q].w;
+            *reinterpret_cast<float4*>(p.y + row * p.ldy + c + 4 * q) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace grafp
+
+using namespace grafp;
+
+#ifdef FF_TRACE
+extern "C" int grafp_debug_ffn_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_ff_trace, sizeof(unsigned long long) * 3 * 1024);
+}
+#endif
+
+extern "C" int grafp_ffn_fused_supported(int64_t M, int C, int Hd) {
+  return M >= 1 && (C == 64 || C == 128) && Hd % FF_HC == 0 && Hd >= FF_HC && Hd <= FF_HMAX;
+}
+
+extern "C" int grafp_ffn_fused_fwd(const float* x, int64_t ldx, int64_t M, int C, int Hd, const void* w1_split_f16,
+                                   int64_t ldw1, float w1_unscale, const float* scale1, const float* shift1, int act,
+                                   float act_param, const void* w2_split_f16, int64_t ldw2, float w2_unscale,
+                                   const float* scale2, const float* shift2, float* y, int64_t ldy, void* stream) {
+  GRAFP_REQUIRE(grafp_ffn_fused_supported(M, C, Hd), "ffn_fused: needs C in {64, 128} and a hidden width that is a multiple of 64");
+  GRAFP_REQUIRE(x && y && w1_split_f16 && w2_split_f16 && scale1 && shift1 && scale2 && shift2, "ffn_fused: null pointer");
+  GRAFP_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldw1 % 8 == 0 && ldw2 % 8 == 0 && w1_unscale > 0.0f && w2_unscale > 0.0f,
+                "ffn_fused: bad strides / scales");
+  GRAFP_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w1_split_f16) |
+                  reinterpret_cast<uintptr_t>(w2_split_f16)) & 15) == 0, "ffn_fused: operands must be 16-byte aligned");
+  GRAFP_REQUIRE(act >= GRAFP_ACT_NONE && act <= GRAFP_ACT_ELU, "ffn_fused: unsupported activation %d", act);
+  CUtensorMap mX, mW1, mW2;
+  if (int rc = tc_make_map_2d(&mX, x, M, C, ldx, TC_BM)) return rc;
+  if (int rc = tc_make_map_2d_bf16(&mW1, w1_split_f16, 2 * (int64_t)Hd, C, ldw1, FF_HC)) return rc;
+  if (int rc = tc_make_map_2d_bf16(&mW2, w2_split_f16, 2 * (int64_t)C, Hd, ldw2, C)) return rc;
+  FfnParams p;
+  p.C = C; p.Hd = Hd; p.M = M;
+  p.scale1 = scale1; p.shift1 = shift1; p.unscale1 = w1_unscale;
+  p.scale2 = scale2; p.shift2 = shift2; p.unscale2 = w2_unscale;
+  p.act = act; p.act_param = act_param;
+  p.x = x; p.ldx = ldx; p.y = y; p.ldy = ldy;
+  const uint32_t w1b = 2u * FF_HC * 64u, w2b = 2u * (uint32_t)C * 64u;
+  p.wslot_bytes = w1b > w2b ? w1b : w2b;
+  const size_t fixed = (size_t)(C / 32) * 2 * FF_KB_BYTES + 2 * 2 * 2 * FF_KB_BYTES + FF_RAW * TC_A_BYTES;
+  int slots = (int)((212 * 1024 - fixed) / p.wslot_bytes);
+  if (slots > FF_WMAX) slots = FF_WMAX;
+  GRAFP_REQUIRE(slots >= 2, "ffn_fused: not enough shared memory");
+  p.wslots = slots;
+  const size_t smem = fixed + (size_t)slots * p.wslot_bytes + 1024;
+  const int64_t tiles = (M + TC_BM - 1) / TC_BM;
+  int grid = sm_count();
+  if (tiles < grid) grid = (int)tiles;
+  cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ffn_fused_kernel<<<grid, FF_THREADS, smem, as_stream(stream)>>>(mX, mW1, mW2, p);
+  return check_launch("ffn_fused");
+}

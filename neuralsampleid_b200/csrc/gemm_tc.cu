@@ -143,7 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __shared__ __align__(16) float s_shift[2][256];
   __shared__ float s_rowsq[TC_BM];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int S = p.stages;
   constexpr uint32_t kOpRow = kBf16 ? 64u : 128u;             // operand bytes per row per k-block
   constexpr uint32_t kAop = TC_BM * kOpRow;                   // one A operand tile: 8 KB / 16 KB
@@ -281,59 +281,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the warp stays converged, one elected lane issues (tc_common.cuh) =====
+    {
       const uint32_t idesc = kBf16 ? (kF16 ? umma_idesc_f16(TC_BM, p.bn) : umma_idesc_bf16(TC_BM, p.bn))
                                    : umma_idesc_tf32(TC_BM, p.bn);
-      uint32_t it = 0, ti = 0;
+      constexpr uint32_t kHi = kBf16 ? UMMA_HI_SW64 : UMMA_HI_SW128;
+      const uint32_t d_stage0 = umma_desc_lo(smem_u32(stage0)), d_stage = stage_bytes >> 4;
+      const uint32_t d_alo = kAop >> 4, d_bhi = (kNP * kAop) >> 4, d_blo = d_bhi + (b_bytes >> 4);
+      uint32_t s = 0, ph = 0, ti = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
         const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[buf], tph ^ 1u);          // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
+        for (int kb = 0; kb < nkb; ++kb) {
           if (kBf16) mbar_wait(&full_bar[s], ph);             // W tiles landed (A comes via xf)
           if (!kASplit) mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph);
           tc_fence_after();
-          if (kBf16) {
-            const uint64_t dah = umma_desc_sw64(smem_u32(a_hi(s))), dbh = umma_desc_sw64(smem_u32(b_hi(s)));
-            const uint64_t dal = umma_desc_sw64(smem_u32(a_lo(s))), dbl = umma_desc_sw64(smem_u32(b_lo(s)));
+          const uint32_t dah = d_stage0 + s * d_stage, dal = dah + d_alo, dbh = dah + d_bhi, dbl = dah + d_blo;
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {                    // UMMA_K = 16 bf16 = 32 B
-              const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+            for (int k = 0; k < (kBf16 ? TC_BK / 16 : TC_BK / 8); ++k) {   // UMMA_K = 32 B of the operand row
+              const uint32_t koff = 2u * k;
               const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              if (kPasses == 3) {
-                umma_bf16(tacc, dal + koff, dbh + koff, idesc, acc);
-                umma_bf16(tacc, dah + koff, dbl + koff, idesc, 1u);
-                umma_bf16(tacc, dah + koff, dbh + koff, idesc, 1u);
+              if (kBf16) {
+                if (kPasses == 3) {
+                  umma_f16_lh(tacc, dal + koff, dbh + koff, kHi, idesc, acc);
+                  umma_f16_lh(tacc, dah + koff, dbl + koff, kHi, idesc, 1u);
+                  umma_f16_lh(tacc, dah + koff, dbh + koff, kHi, idesc, 1u);
+                } else {
+                  umma_f16_lh(tacc, dah + koff, dbh + koff, kHi, idesc, acc);
+                }
               } else {
-                umma_bf16(tacc, dah + koff, dbh + koff, idesc, acc);
+                if (kPasses == 3) {
+                  umma_tf32_lh(tacc, dal + koff, dbh + koff, kHi, idesc, acc);
+                  umma_tf32_lh(tacc, dah + koff, dbl + koff, kHi, idesc, 1u);
+                  umma_tf32_lh(tacc, dah + koff, dbh + koff, kHi, idesc, 1u);
+                } else {
+                  umma_tf32_lh(tacc, dah + koff, dbh + koff, kHi, idesc, acc);
+                }
               }
             }
-          } else {
-            const uint64_t dah = umma_desc_sw128(smem_u32(a_hi(s)));
-            const uint64_t dbh = umma_desc_sw128(smem_u32(b_hi(s)));
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
-              const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);       // 32 B per k-step
-              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              if (kPasses == 3) {
-                const uint64_t dal = umma_desc_sw128(smem_u32(a_lo(s)));
-                const uint64_t dbl = umma_desc_sw128(smem_u32(b_lo(s)));
-                umma_tf32(tacc, dal + koff, dbh + koff, idesc, acc);
-                umma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
-                umma_tf32(tacc, dah + koff, dbh + koff, idesc, 1u);
-              } else {
-                umma_tf32(tacc, dah + koff, dbh + koff, idesc, acc);
-              }
-            }
+            // smem slot reusable once these MMAs retire (in both CTAs of a pair)
+            if (kCluster == 2) umma_commit_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
+            if (kb == nkb - 1) umma_commit(&tmem_full_bar[buf]);       // accumulator complete
           }
-          // smem slot reusable once these MMAs retire (in both CTAs of a pair)
-          if (kCluster == 2) umma_commit_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&tmem_full_bar[buf]);       // accumulator complete
       }
     }
   } else if (warp >= 10 && warp < 14) {

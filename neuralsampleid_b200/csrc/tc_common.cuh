@@ -122,6 +122,43 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-uniform MMA issue -------------------------------------------------------------------------------------------
+// The MMA warp runs its loop CONVERGED (all 32 lanes take the waits and the loop control) and one elected lane issues:
+// with a warp index the compiler can prove uniform (warp_idx_uniform) every operand of tcgen05.mma lives in uniform
+// registers and the instruction is a plain predicated UTCHMMA.  Issued from inside `if (lane == 0)` instead, each MMA is
+// wrapped in an ELECT / BRA.U.ANY "waterfall" loop and costs 57-67 issue cycles on an idle SM (measured,
+// scripts/micro/umma_rate.cu) -- more than the 48 / 64 cycles an N = 64 / 128 MMA executes in.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// Shared-memory descriptors as (lo, hi) words: lo = start address >> 4 | LBO 1, hi = SBO >> 4 | version 1 | layout.
+// Stage and k-slice advances are 32-bit adds on `lo` (byte offset >> 4; shared addresses stay below 2^18).
+constexpr uint32_t UMMA_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+constexpr uint32_t UMMA_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major, SWIZZLE_64B descriptor (rows of 64 B = 32 bf16): SBO = 8 rows * 64 B = 512, layout_type=4
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   uint64_t d = 0;

@@ -116,6 +116,9 @@ class FFN(_Cached):
                                "neuralsampleid_b200.autograd")
         fc1, fc2 = self._folded("fc1"), self._folded("fc2")
         M, hid = x.shape[0], fc1.w.shape[0]
+        if x_split is None and ops.ffn_fused_ok(fc1, fc2, x):
+            # C <= 128: both GEMMs are HBM-bound on the 4C-wide hidden tensor -- one kernel keeps it on chip
+            return ops.ffn_fused(x, fc1, fc2, self.act.name, self.act.neg_slope)
         slab = _ffn_slab_rows(hid)
         if slab <= 0 or M <= slab:
             # the hidden tensor feeds only fc2: on the bf16 tensor-core engines it travels as the

@@ -412,6 +412,39 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor] = None
     return SplitAct(out) if out_split else out
 
 
+def ffn_fused_ok(lin1, lin2, x) -> bool:
+    """True when FFN fc1 -> act -> fc2 (+ shortcut) can run as ONE kernel with the hidden tile on chip
+    (grafp_ffn_fused_fwd): fp32 x of C in {64, 128} channels, f16x3 engine, both layers un-grouped with folded scale
+    and shift.  GRAFP_NO_FFN_FUSED=1 keeps the two-GEMM route."""
+    if os.environ.get("GRAFP_NO_FFN_FUSED", "0") == "1" or isinstance(x, SplitAct):
+        return False
+    if _effective_engine() not in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_F16X3):
+        return False
+    if lin1.groups != 1 or lin2.groups != 1 or lin1.w_split_f16 is None or lin2.w_split_f16 is None:
+        return False
+    if lin1.scale is None or lin1.shift is None or lin2.scale is None or lin2.shift is None:
+        return False
+    hid, c = lin1.w.shape
+    if lin2.w.shape != (c, hid) or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != c:
+        return False
+    return bool(_lib.load().grafp_ffn_fused_supported(x.shape[0], c, hid)) and x.shape[0] > 0
+
+
+def ffn_fused(x: torch.Tensor, lin1, lin2, act=None, act_param: float = 0.0) -> torch.Tensor:
+    """y = x + scale2 * (act(scale1 * (x W1^T) + shift1) W2^T) + shift2 in one kernel (include/grafp.h)."""
+    x = _chk(x, name="x")
+    M, c = x.shape
+    hid = lin1.w.shape[0]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_ffn_fused_fwd(
+            _ptr(x), x.stride(0), M, c, hid, _ptr(lin1.w_split_f16), lin1.w_split_f16.stride(0), float(lin1.f16_unscale),
+            _ptr(lin1.scale), _ptr(lin1.shift), act_code(act), act_param, _ptr(lin2.w_split_f16),
+            lin2.w_split_f16.stride(0), float(lin2.f16_unscale), _ptr(lin2.scale), _ptr(lin2.shift), _ptr(y),
+            y.stride(0), _stream(x)), "ffn_fused_fwd")
+    return y
+
+
 def stem_supported(cin: int, cout: int, N: int) -> bool:
     return cin in (4, 8, 16) and cout % 4 == 0 and 4 <= cout <= 1024 and 256 % (cout // 4) == 0 and \
         (cin * N + cin * cout) * 4 <= 96 * 1024

@@ -445,6 +445,33 @@ def test_gemm_fused_max_relative_bit_exact(B, N, C, k, groups, out_split):
         assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("act", ["relu", "gelu"])
+@pytest.mark.parametrize("M,C", [(128 * 5 + 7, 64), (4096, 64), (300, 128), (128 * 37, 128), (20000, 128)])
+def test_ffn_fused_bit_exact(M, C, act):
+    """grafp_ffn_fused_fwd (fc1 -> activation -> fc2 -> + shortcut in one kernel, hidden tile on chip) is BIT-identical
+    to the two f16x3 GEMM launches it replaces (same operand values, same accumulation order), ragged last tile and
+    several tiles per CTA included; and within the engine's tolerance of an fp64 restatement."""
+    ops = _ops()
+    from neuralsampleid_b200 import _prep
+    hid = 4 * C
+    x = synth.synth_normal((M, C), 40).to(DEV)
+    w1 = (synth.synth_normal((hid, C), 41) / float(np.sqrt(C))).to(DEV)
+    w2 = (synth.synth_normal((C, hid), 42) / float(np.sqrt(hid))).to(DEV)
+    sc1, sh1 = synth.synth_uniform((hid,), 43, 0.5, 1.5).to(DEV), synth.synth_uniform((hid,), 44, -0.5, 0.5).to(DEV)
+    sc2, sh2 = synth.synth_uniform((C,), 45, 0.5, 1.5).to(DEV), synth.synth_uniform((C,), 46, -0.5, 0.5).to(DEV)
+    l1 = _prep.make_linear(w1, sc1, sh1, 1)
+    l2 = _prep.make_linear(w2, sc2, sh2, 1)
+    assert ops.ffn_fused_ok(l1, l2, x)
+    h = ops.linear(x, l1, act, 0.0, out_split=True)
+    want = ops.linear(h, l2, None, 0.0, x)
+    got = ops.ffn_fused(x, l1, l2, act, 0.0)
+    assert torch.equal(got, want), float((got - want).abs().max())
+    assert torch.equal(ops.ffn_fused(x, l1, l2, act, 0.0), got)                    # deterministic
+    ref = _gemm_ref(x.cpu(), w1.cpu(), sc1.cpu(), sh1.cpu(), act, 0.0, None, None, 1, 0)
+    ref = _gemm_ref(ref.float(), w2.cpu(), sc2.cpu(), sh2.cpu(), None, 0.0, x.cpu(), None, 1, 0)
+    assert float((got.cpu().double() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
 def test_gemm_split_bf16_needs_bf16_engine():
     ops = _ops()
     from neuralsampleid_b200 import _lib, _prep
