@@ -34,7 +34,7 @@ for r in rows[hi + 1:]:
 
 
 def klass(k):
-    if "gemm" in k:
+    if "gemm" in k or "ffn_fused" in k:      # the fused FFN is two GEMMs in one launch
         return "gemm"
     if "knn" in k:
         return "knn"
