@@ -115,8 +115,9 @@ __device__ __forceinline__ float2 unpack16(uint32_t v) {
 // 64-byte-row bf16 tiles (64B swizzle); W is pre-split on the host into stacked bf16 [w1 ; w2].
 //
 // kASplit (bf16 engines): the A operand arrives already split, as the bf16 (2, M, K) [hi ; lo] planes a
-// previous GEMM's epilogue wrote (p.y_split): the W producer warp TMA-loads the hi / lo tiles straight
-// into the operand stage, there is no fp32 ring and no transform, the MMA waits on full[s] alone.
+// previous GEMM's epilogue wrote (p.y_split): warp 0 TMA-loads the hi / lo tiles straight into a ring of A operand
+// tiles (as many as shared memory holds beside three W stages: the A stream comes from HBM, W from L2), there is no
+// fp32 ring and no transform, the MMA waits on raw_full[sa] and full[s] and frees both with its commits.
 // kGather: fused max-relative aggregation of the second A source (opt-in, see TcParams::gat_idx); a separate
 // instantiation so the default kernels carry none of its registers or code.
 // kF16 (with kBf16, which selects the 16-bit kind::f16 operand path): the operand pair is IEEE fp16 instead of
@@ -149,7 +150,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   constexpr uint32_t kAop = TC_BM * kOpRow;                   // one A operand tile: 8 KB / 16 KB
   constexpr uint32_t kNP = kPasses == 3 ? 2u : 1u;            // operand copies (hi [+ lo])
   const uint32_t b_bytes = (uint32_t)p.bn * kOpRow;
-  const uint32_t stage_bytes = kNP * (kAop + b_bytes);
+  // kASplit: the pre-split A tiles have their own ring (p.raw slots of hi [+ lo], filled by warp 0 straight from HBM,
+  // freed by the MMA commits) so the HBM-latency-bound A stream runs deeper than the L2-resident W stream; the operand
+  // stages then hold W only.
+  const uint32_t stage_bytes = kASplit ? kNP * b_bytes : kNP * (kAop + b_bytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* store_buf = smem;                                  // 2 (4 in dual-output mode) x 16 KB staging tiles
   const uint32_t n_store = p.y_both ? 4u : 2u;
@@ -159,11 +163,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   //       [A_hi | A_lo (3x) | B_hi | B_lo (3x)]
   uint8_t* raw0 = smem + n_store * TC_STORE_BYTES;
   const int RAW = p.raw;
-  uint8_t* stage0 = raw0 + ((kBf16 && !kASplit) ? RAW * TC_A_BYTES : 0);
+  uint8_t* stage0 = raw0 + (kBf16 ? RAW * (kASplit ? kNP * kAop : (uint32_t)TC_A_BYTES) : 0);
   auto a_raw = [&](int s) { return kBf16 ? raw0 + (size_t)s * TC_A_BYTES : stage0 + (size_t)s * stage_bytes; };
-  auto a_hi = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
+  auto a_hi = [&](int s) { return kASplit ? raw0 + (size_t)s * (kNP * kAop) : stage0 + (size_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return a_hi(s) + kAop; };
-  auto b_hi = [&](int s) { return a_hi(s) + kNP * kAop; };
+  auto b_hi = [&](int s) { return stage0 + (size_t)s * stage_bytes + (kASplit ? 0u : kNP * kAop); };
   auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
 
   const int nkb = (p.k1 + p.k2) / TC_BK;
@@ -188,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int r = 0; r < TC_RAW_MAX; ++r) {
       mbar_init(&raw_full_bar[r], 1);
-      mbar_init(&raw_empty_bar[r], TC_XF_THREADS);
+      mbar_init(&raw_empty_bar[r], kASplit ? 1 : TC_XF_THREADS);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -208,6 +212,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // the raw ring (gated by the transform), warp 14 streams the W tiles into the operand stages
     // (gated by the MMA commits), so A prefetch depth is not tied to the MMA's progress.
     const bool do_a = warp == 0 && !kASplit, do_w = kBf16 ? warp == 14 : warp == 0;
+    if (kASplit && warp == 0 && lane == 0) {
+      // pre-split A: hi / lo planes of my rows, k-block by k-block, into the A ring
+      uint32_t ra = 0;
+      for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
+        const int64_t rest = tile / tiles_n;
+        const int g = (int)(rest % p.groups);
+        const int m0 = (int)(((rest / p.groups) * kCluster + crank) * TC_BM);
+        for (int kb = 0; kb < nkb; ++kb, ++ra) {
+          const int r = ra % RAW;
+          mbar_wait(&raw_empty_bar[r], ((ra / RAW) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&raw_full_bar[r], kNP * kAop);
+          tma_load_3d(a_hi(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 0, &raw_full_bar[r]);
+          if (kPasses == 3) tma_load_3d(a_lo(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 1, &raw_full_bar[r]);
+        }
+      }
+    }
     if (lane == 0 && (do_a || do_w)) {
       uint32_t it = 0, ra = 0;                  // ra: fp32 A tiles issued into the raw ring
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step) {
@@ -234,11 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
             if (do_w) {
               mbar_wait(&empty_bar[s], ph ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[s], kNP * (b_bytes + (kASplit ? kAop : 0u)));
-              if (kASplit) {
-                tma_load_3d(a_hi(s), &tmA1, g * p.k1 + k, m0, 0, &full_bar[s]);
-                if (kPasses == 3) tma_load_3d(a_lo(s), &tmA1, g * p.k1 + k, m0, 1, &full_bar[s]);
-              }
+              mbar_arrive_expect_tx(&full_bar[s], kNP * b_bytes);
             }
           } else {
             abar = &full_bar[s];
@@ -287,8 +303,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                                    : umma_idesc_tf32(TC_BM, p.bn);
       constexpr uint32_t kHi = kBf16 ? UMMA_HI_SW64 : UMMA_HI_SW128;
       const uint32_t d_stage0 = umma_desc_lo(smem_u32(stage0)), d_stage = stage_bytes >> 4;
-      const uint32_t d_alo = kAop >> 4, d_bhi = (kNP * kAop) >> 4, d_blo = d_bhi + (b_bytes >> 4);
-      uint32_t s = 0, ph = 0, ti = 0;
+      const uint32_t d_alo = kAop >> 4, d_bhi = kASplit ? 0u : (kNP * kAop) >> 4, d_blo = d_bhi + (b_bytes >> 4);
+      const uint32_t d_ring0 = umma_desc_lo(smem_u32(raw0)), d_ring = (kNP * kAop) >> 4;     // kASplit: the A ring
+      uint32_t s = 0, ph = 0, ti = 0, sa = 0, pha = 0;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
         const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[buf], tph ^ 1u);          // epilogue drained this accumulator
@@ -297,8 +314,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb) {
           if (kBf16) mbar_wait(&full_bar[s], ph);             // W tiles landed (A comes via xf)
           if (!kASplit) mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph);
+          else mbar_wait(&raw_full_bar[sa], pha);
           tc_fence_after();
-          const uint32_t dah = d_stage0 + s * d_stage, dal = dah + d_alo, dbh = dah + d_bhi, dbl = dah + d_blo;
+          const uint32_t dst = d_stage0 + s * d_stage;
+          const uint32_t dah = kASplit ? d_ring0 + sa * d_ring : dst, dal = dah + d_alo, dbh = dst + d_bhi, dbl = dst + d_blo;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < (kBf16 ? TC_BK / 16 : TC_BK / 8); ++k) {   // UMMA_K = 32 B of the operand row
@@ -324,10 +343,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
             // smem slot reusable once these MMAs retire (in both CTAs of a pair)
             if (kCluster == 2) umma_commit_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
+            if (kASplit) umma_commit(&raw_empty_bar[sa]);             // my A tile (not shared with the pair)
             if (kb == nkb - 1) umma_commit(&tmem_full_bar[buf]);       // accumulator complete
           }
           __syncwarp();
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+          if (kASplit && ++sa == (uint32_t)RAW) { sa = 0; pha ^= 1u; }
         }
       }
     }
@@ -775,7 +796,8 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   while ((int)cols < 2 * bn) cols <<= 1;
   p.tmem_cols = cols;
   const size_t np = passes == 3 ? 2 : 1;
-  const size_t stage_bytes = bf16 ? np * ((size_t)TC_BM * 64 + (size_t)bn * 64)
+  const size_t a_slot = np * (size_t)TC_BM * 64;                          // pre-split A tile: hi [+ lo]
+  const size_t stage_bytes = bf16 ? (asplit ? np * (size_t)bn * 64 : np * ((size_t)TC_BM * 64 + (size_t)bn * 64))
                                   : np * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
   // Shared-memory plan.  The fp32 A ring covers the HBM latency (a memory-bound shape needs ~75 KB in flight
   // per SM to stream at the HBM rate), the operand stages only the transform -> MMA hand-off: narrow tiles
@@ -793,10 +815,24 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
     }
     if (raw_env >= 2 && raw_env <= TC_RAW_MAX) raw = raw_env;
   }
+  size_t ring_bytes = (size_t)raw * TC_A_BYTES;
+  if (asplit) {
+    // W stages cover the L2 latency (three, two when the tile is so wide that the A ring would starve), the rest of
+    // shared memory is A tiles in flight from HBM
+    static int ws_env = -1;
+    if (ws_env < 0) { const char* e = getenv("GRAFP_TC_ASPLIT_WSTAGES"); ws_env = e ? atoi(e) : 0; }
+    int ws = ws_env >= 1 && ws_env <= TC_MAX_STAGES ? ws_env : 3;
+    while (ws > 1 && budget < ws * stage_bytes + 3 * a_slot) --ws;
+    raw = (int)((budget - ws * stage_bytes) / a_slot);
+    if (raw > TC_RAW_MAX) raw = TC_RAW_MAX;
+    if (raw < 1) raw = 1;
+    ring_bytes = (size_t)raw * a_slot;
+  }
   p.raw = raw > 0 ? raw : 1;
-  const size_t fixed_bytes = n_store * TC_STORE_BYTES + (size_t)raw * TC_A_BYTES;
+  const size_t fixed_bytes = n_store * TC_STORE_BYTES + ring_bytes;
   const int nkb = (a.k1 + a.k2) / TC_BK;
   stages = (int)((220 * 1024 - fixed_bytes - 1024) / stage_bytes);
+  if (asplit && raw < TC_RAW_MAX && stages > 3) stages = 3;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 1) stages = 1;
   p.stages = stages;
