@@ -125,6 +125,14 @@ __device__ __forceinline__ float2 unpack16(uint32_t v) {
 // floor of 2^-25 where lo is subnormal) and the dropped a2*w2 term is 2^-24: fp32-class products at the bf16 MMA
 // rate.  The weights are pre-scaled by a power of two on the host (p.unscale undoes it in the epilogue) so that
 // their lo parts stay normal numbers.
+#ifdef TC_TRACE
+// debug build (GRAFP_NVCC_EXTRA=-DTC_TRACE): where block 0's MMA warp spends its cycles (scripts/gemm_trace.py)
+__device__ unsigned long long g_tc_trace[8];
+#define TC_ACC(var, stmt) do { const long long c0_ = clock64(); stmt; var += clock64() - c0_; } while (0)
+#else
+#define TC_ACC(var, stmt) do { stmt; } while (0)
+#endif
+
 template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather, bool kF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -306,15 +314,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const uint32_t d_alo = kAop >> 4, d_bhi = kASplit ? 0u : (kNP * kAop) >> 4, d_blo = d_bhi + (b_bytes >> 4);
       const uint32_t d_ring0 = umma_desc_lo(smem_u32(raw0)), d_ring = (kNP * kAop) >> 4;     // kASplit: the A ring
       uint32_t s = 0, ph = 0, ti = 0, sa = 0, pha = 0;
+      long long cy_e = 0, cy_w = 0, cy_a = 0; const long long cy_t0 = clock64(); (void)cy_t0; (void)cy_e; (void)cy_w; (void)cy_a;
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
         const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
-        mbar_wait(&tmem_empty_bar[buf], tph ^ 1u);          // epilogue drained this accumulator
+        TC_ACC(cy_e, mbar_wait(&tmem_empty_bar[buf], tph ^ 1u));          // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn;
         for (int kb = 0; kb < nkb; ++kb) {
-          if (kBf16) mbar_wait(&full_bar[s], ph);             // W tiles landed (A comes via xf)
-          if (!kASplit) mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph);
-          else mbar_wait(&raw_full_bar[sa], pha);
+          if (kBf16) TC_ACC(cy_w, mbar_wait(&full_bar[s], ph));             // W tiles landed (A comes via xf)
+          if (!kASplit) TC_ACC(cy_a, mbar_wait((kPasses == 3 || kBf16) ? &xf_bar[s] : &full_bar[s], ph));
+          else TC_ACC(cy_a, mbar_wait(&raw_full_bar[sa], pha));
           tc_fence_after();
           const uint32_t dst = d_stage0 + s * d_stage;
           const uint32_t dah = kASplit ? d_ring0 + sa * d_ring : dst, dal = dah + d_alo, dbh = dst + d_bhi, dbl = dst + d_blo;
@@ -351,6 +360,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (kASplit && ++sa == (uint32_t)RAW) { sa = 0; pha ^= 1u; }
         }
       }
+#ifdef TC_TRACE
+      if (blockIdx.x == 0 && lane == 0) {
+        g_tc_trace[0] = clock64() - cy_t0; g_tc_trace[1] = cy_e; g_tc_trace[2] = cy_w; g_tc_trace[3] = cy_a;
+        g_tc_trace[4] = ti; g_tc_trace[5] = (unsigned long long)nkb; g_tc_trace[6] = (unsigned long long)S; g_tc_trace[7] = (unsigned long long)RAW;
+      }
+#endif
     }
   } else if (warp >= 10 && warp < 14) {
     // ===== transform (warps 10..13, 128 threads): build the MMA A operand(s) from the fp32 stage =====
@@ -589,6 +604,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
 }
 
+#ifdef TC_TRACE
+extern "C" int grafp_debug_tc_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, grafp::g_tc_trace, sizeof(unsigned long long) * 8);
+}
+#endif
 // ---- host side -------------------------------------------------------------------------
 EncodeTiledFn tc_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -816,6 +836,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
     if (raw_env >= 2 && raw_env <= TC_RAW_MAX) raw = raw_env;
   }
   size_t ring_bytes = (size_t)raw * TC_A_BYTES;
+  int asplit_ws = 3;
   if (asplit) {
     // W stages cover the L2 latency (three, two when the tile is so wide that the A ring would starve), the rest of
     // shared memory is A tiles in flight from HBM
@@ -827,12 +848,13 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
     if (raw > TC_RAW_MAX) raw = TC_RAW_MAX;
     if (raw < 1) raw = 1;
     ring_bytes = (size_t)raw * a_slot;
+    asplit_ws = ws;
   }
   p.raw = raw > 0 ? raw : 1;
   const size_t fixed_bytes = n_store * TC_STORE_BYTES + ring_bytes;
   const int nkb = (a.k1 + a.k2) / TC_BK;
   stages = (int)((220 * 1024 - fixed_bytes - 1024) / stage_bytes);
-  if (asplit && raw < TC_RAW_MAX && stages > 3) stages = 3;
+  if (asplit && raw < TC_RAW_MAX && stages > asplit_ws) stages = asplit_ws;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 1) stages = 1;
   p.stages = stages;
