@@ -133,7 +133,7 @@ __device__ unsigned long long g_tc_trace[8];
 #define TC_ACC(var, stmt) do { stmt; } while (0)
 #endif
 
-template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather, bool kF16 = false>
+template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather, bool kF16 = false, bool kPair = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -150,21 +150,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_scale[2][256];   // folded scale / shift of the tile's columns
   __shared__ __align__(16) float s_shift[2][256];
-  __shared__ float s_rowsq[TC_BM];
+  __shared__ float s_rowsq[2][TC_BM];
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int S = p.stages;
   constexpr uint32_t kOpRow = kBf16 ? 64u : 128u;             // operand bytes per row per k-block
   constexpr uint32_t kAop = TC_BM * kOpRow;                   // one A operand tile: 8 KB / 16 KB
   constexpr uint32_t kNP = kPasses == 3 ? 2u : 1u;            // operand copies (hi [+ lo])
-  const uint32_t b_bytes = (uint32_t)p.bn * kOpRow;
+  // kPair (with kCluster == 2, kASplit, 3 passes of kind::f16): ONE tcgen05.mma.cta_group::2 per k-slice computes the pair's
+  // 256 x bn tile; each CTA keeps its 128 rows of A and its bn/2 rows of W (half the W bytes per k-block: twice the k-blocks
+  // in flight in the same shared memory), the leader (rank 0) issues, every barrier the MMA waits on lives in the leader.
+  static_assert(!kPair || (kCluster == 2 && kASplit && kBf16 && kPasses == 3 && !kGather), "pair MMA: pre-split 16-bit operands only");
+  const uint32_t b_bytes = (uint32_t)(kPair ? p.bn / 2 : p.bn) * kOpRow;
   // kASplit: the pre-split A tiles have their own ring (p.raw slots of hi [+ lo], filled by warp 0 straight from HBM,
   // freed by the MMA commits) so the HBM-latency-bound A stream runs deeper than the L2-resident W stream; the operand
   // stages then hold W only.
   const uint32_t stage_bytes = kASplit ? kNP * b_bytes : kNP * (kAop + b_bytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* store_buf = smem;                                  // 2 (4 in dual-output mode) x 16 KB staging tiles
-  const uint32_t n_store = p.y_both ? 4u : 2u;
+  // epilogue groups of 128 threads: warps 2..9, plus the transform warps 10..13 (idle: A arrives pre-split) in pair mode,
+  // where the main loop is fast enough for the epilogue of short-k tiles to become the limiter
+  constexpr int kEpiGroups = kPair ? 3 : 2;
+  constexpr int kEpiThreads = kEpiGroups * 128;
+  const uint32_t n_store = (p.y_both ? 2u : 1u) * kEpiGroups;
   // tf32: operand stages [A raw = hi | A_lo (3x) | B_hi | B_lo (3x)]
   // bf16: a separate ring of p.raw fp32 A tiles (freed as soon as the transform has read them, so the
   //       HBM-latency-bound A loads run up to p.raw k-blocks ahead of the MMA), then operand stages
@@ -196,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&xf_bar[s], TC_XF_THREADS);
-      mbar_init(&empty_bar[s], kCluster);
+      mbar_init(&empty_bar[s], kPair ? 1 : kCluster);
     }
     for (int r = 0; r < TC_RAW_MAX; ++r) {
       mbar_init(&raw_full_bar[r], 1);
@@ -204,11 +212,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], TC_EPI_THREADS);
+      mbar_init(&tmem_empty_bar[b], (kPair ? 2 : 1) * kEpiThreads / 32);      // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  if (warp == 1) { if (kPair) tmem_alloc_pair(&tmem_base_s, p.tmem_cols); else tmem_alloc(&tmem_base_s, p.tmem_cols); }
   tc_fence_before();
   if (kCluster == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -230,6 +238,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb, ++ra) {
           const int r = ra % RAW;
           mbar_wait(&raw_empty_bar[r], ((ra / RAW) & 1u) ^ 1u);
+          if (kPair) {
+            if (crank == 0) mbar_arrive_expect_tx(&raw_full_bar[r], 2 * kNP * kAop);      // both CTAs' tiles
+            const uint32_t lb = mapa_rank(smem_u32(&raw_full_bar[r]), 0);
+            tma_load_3d_pair(a_hi(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 0, lb);
+            tma_load_3d_pair(a_lo(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 1, lb);
+            continue;
+          }
           mbar_arrive_expect_tx(&raw_full_bar[r], kNP * kAop);
           tma_load_3d(a_hi(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 0, &raw_full_bar[r]);
           if (kPasses == 3) tma_load_3d(a_lo(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 1, &raw_full_bar[r]);
@@ -262,7 +277,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
             if (do_w) {
               mbar_wait(&empty_bar[s], ph ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[s], kNP * b_bytes);
+              if (!kPair) mbar_arrive_expect_tx(&full_bar[s], kNP * b_bytes);
+              else if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * kNP * b_bytes);   // both halves of the W tile
             }
           } else {
             abar = &full_bar[s];
@@ -287,7 +303,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               tma_load_2d(adst, &tmA2, g * p.k2 + (k - p.k1), m0, abar);
             }
           }
-          if (do_w) {
+          if (do_w && kPair) {
+            // my half of the W tile into MY shared memory, counted on the leader's barrier
+            const int half = p.bn / 2;
+            const uint32_t lb = mapa_rank(smem_u32(&full_bar[s]), 0);
+            tma_load_2d_pair(b_hi(s), &tmW, k, g * p.n + n0 + (int)crank * half, lb);
+            tma_load_2d_pair(b_lo(s), &tmW, k, p.n_total + g * p.n + n0 + (int)crank * half, lb);
+          } else if (do_w) {
             if (kCluster == 2) {
               // my half of the weight tile, multicast to both CTAs of the pair (tmW box = bn/2 rows)
               const int half = p.bn / 2;
@@ -306,9 +328,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the warp stays converged, one elected lane issues (tc_common.cuh) =====
-    {
-      const uint32_t idesc = kBf16 ? (kF16 ? umma_idesc_f16(TC_BM, p.bn) : umma_idesc_bf16(TC_BM, p.bn))
-                                   : umma_idesc_tf32(TC_BM, p.bn);
+    if (!kPair || crank == 0) {
+      constexpr int kMmaM = kPair ? 2 * TC_BM : TC_BM;
+      const uint32_t idesc = kBf16 ? (kF16 ? umma_idesc_f16(kMmaM, p.bn) : umma_idesc_bf16(kMmaM, p.bn))
+                                   : umma_idesc_tf32(kMmaM, p.bn);
       constexpr uint32_t kHi = kBf16 ? UMMA_HI_SW64 : UMMA_HI_SW128;
       const uint32_t d_stage0 = umma_desc_lo(smem_u32(stage0)), d_stage = stage_bytes >> 4;
       const uint32_t d_alo = kAop >> 4, d_bhi = kASplit ? 0u : (kNP * kAop) >> 4, d_blo = d_bhi + (b_bytes >> 4);
@@ -332,7 +355,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             for (int k = 0; k < (kBf16 ? TC_BK / 16 : TC_BK / 8); ++k) {   // UMMA_K = 32 B of the operand row
               const uint32_t koff = 2u * k;
               const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              if (kBf16) {
+              if (kPair) {
+                umma_f16_lh_pair(tacc, dal + koff, dbh + koff, kHi, idesc, acc);
+                umma_f16_lh_pair(tacc, dah + koff, dbl + koff, kHi, idesc, 1u);
+                umma_f16_lh_pair(tacc, dah + koff, dbh + koff, kHi, idesc, 1u);
+              } else if (kBf16) {
                 if (kPasses == 3) {
                   umma_f16_lh(tacc, dal + koff, dbh + koff, kHi, idesc, acc);
                   umma_f16_lh(tacc, dah + koff, dbl + koff, kHi, idesc, 1u);
@@ -351,9 +378,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               }
             }
             // smem slot reusable once these MMAs retire (in both CTAs of a pair)
-            if (kCluster == 2) umma_commit_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
-            if (kASplit) umma_commit(&raw_empty_bar[sa]);             // my A tile (not shared with the pair)
-            if (kb == nkb - 1) umma_commit(&tmem_full_bar[buf]);       // accumulator complete
+            if (kPair) {                                             // every commit reaches both CTAs of the pair
+              umma_commit_pair(&empty_bar[s]);
+              umma_commit_pair(&raw_empty_bar[sa]);
+              if (kb == nkb - 1) umma_commit_pair(&tmem_full_bar[buf]);
+            } else {
+              if (kCluster == 2) umma_commit_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
+              if (kASplit) umma_commit(&raw_empty_bar[sa]);             // my A tile (not shared with the pair)
+              if (kb == nkb - 1) umma_commit(&tmem_full_bar[buf]);       // accumulator complete
+            }
           }
           __syncwarp();
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
@@ -367,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
 #endif
     }
-  } else if (warp >= 10 && warp < 14) {
+  } else if (!kPair && warp >= 10 && warp < 14) {
     // ===== transform (warps 10..13, 128 threads): build the MMA A operand(s) from the fp32 stage =====
     // tf32: hi = v with the 13 low mantissa bits cleared (exactly representable in tf32), lo = v - hi
     //       (exact in fp32, |lo| < 2^-10 |v|; the tensor core reads its top 19 bits), in place.
@@ -478,17 +511,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 2 && warp < 10) {
-    // ===== epilogue (warps 2..9): two groups of 128 threads, group h owns the chunks of parity h =====
-    const int ew = warp - 2;                     // 0..7
-    const int half = ew >> 2;
+  } else if (warp >= 2 && warp < 2 + 4 * kEpiGroups) {
+    // ===== epilogue: groups of 128 threads, group h owns the 32-column chunks h, h + G, h + 2G, ... =====
+    const int ew = warp - 2;                     // 0..7 (0..11 with three groups)
+    const int half = ew >> 2;                    // my group
     const int et = (ew & 3) * 32 + lane;         // 0..127 inside the group
-    const int e256 = ew * 32 + lane;             // 0..255 over both groups
+    const int e256 = ew * 32 + lane;             // 0..255 over the first two groups (they stage scale / shift)
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;              // row inside the tile
     const bool store_thread = (et == 0);
     uint8_t* sb = store_buf + half * TC_STORE_BYTES;
-    uint8_t* sb32 = store_buf + (2 + half) * TC_STORE_BYTES;   // dual-output mode: the fp32 tile beside the split tiles
+    uint8_t* sb32 = store_buf + (kEpiGroups + half) * TC_STORE_BYTES;   // dual-output mode: the fp32 tile beside the split tiles
+    // hand an accumulator back to the MMA thread (pair mode: the leader's, from both CTAs)
+    auto tmem_release = [&](uint64_t* bar) {
+      __syncwarp();
+      if (lane == 0) { if (kPair && crank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(bar), 0)); else mbar_arrive(bar); }
+    };
     uint32_t ti = 0;
     for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
       const int nt = (int)(tile % tiles_n);
@@ -510,18 +548,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
       const float* res_row = (p.residual && row_ok) ? p.residual + row * p.ldr + col0 : nullptr;
       if (res_row)
-        for (int c = half * 32; c < p.bn; c += 64)
+        for (int c = half * 32; c < p.bn; c += 32 * kEpiGroups)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(res_row + c));
-      named_bar_sync(3, TC_EPI_THREADS);
+      named_bar_sync(3, kEpiThreads);
       mbar_wait(&tmem_full_bar[buf], tph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
       float rowsq = 0.0f;
-      if (half * 32 >= p.bn) {                    // a 32-column tile: nothing for group 1 to read
+      if (half * 32 >= p.bn) {                    // a narrow tile: nothing for this group to read
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[buf]);
+        tmem_release(&tmem_empty_bar[buf]);
       }
-      for (int c = half * 32; c < p.bn; c += 64) {
+      for (int c = half * 32; c < p.bn; c += 32 * kEpiGroups) {
         float4 r4[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -530,9 +568,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
         tmem_ld_wait();
-        if (c + 64 >= p.bn) {                     // my last read of this accumulator: hand it back
+        if (c + 32 * kEpiGroups >= p.bn) {        // my last read of this accumulator: hand it back
           tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[buf]);
+          tmem_release(&tmem_empty_bar[buf]);
         }
         switch (p.act) {        // one specialised, branch-free instance per activation
           case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, ssc + c, ssh + c, r4, p.act_param); break;
@@ -546,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           for (int q = 0; q < 32; ++q) rowsq = fmaf(v[q], v[q], rowsq);
         }
         if (store_thread) bulk_wait_group_read<0>();      // my group's previous store has read `sb`
-        named_bar_sync(1 + half, 128);
+        named_bar_sync(half < 2 ? 1 + half : 5, 128);
         if (p.y_split) {
           // bf16 [hi ; lo] planes: exactly the operand pair a consuming bf16x3 GEMM would derive from the
           // fp32 value (hi = bf16(v), lo = bf16(v - hi)); two 128 x 64 B tiles, 64B swizzle
@@ -574,7 +612,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1 + half, 128);
+        named_bar_sync(half < 2 ? 1 + half : 5, 128);
         if (store_thread) {
           if (p.y_split) {
             tma_store_3d(&tmYs, sb, (int)(col0 + c), m0, 0);
@@ -589,9 +627,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       if (p.row_sumsq) {
         // deterministic: group 1 hands its partial to group 0 (fixed order), one atomic per row and
         // column tile (at most two column tiles: fp32 addition of two terms commutes)
-        if (half == 1) s_rowsq[r] = rowsq;
-        named_bar_sync(4, TC_EPI_THREADS);
-        if (half == 0 && row_ok) atomicAdd(p.row_sumsq + row, rowsq + (p.bn > 32 ? s_rowsq[r] : 0.0f));
+        if (half >= 1) s_rowsq[half - 1][r] = rowsq;
+        named_bar_sync(4, kEpiThreads);
+        if (half == 0 && row_ok) {
+          float t = rowsq + (p.bn > 32 ? s_rowsq[0][r] : 0.0f);
+          if (kEpiGroups == 3 && p.bn > 64) t += s_rowsq[1][r];
+          atomicAdd(p.row_sumsq + row, t);
+        }
       }
     }
     if (store_thread) bulk_wait_group_all();
@@ -600,7 +642,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (kCluster == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal my barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (kPair) tmem_dealloc_pair(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -817,12 +859,21 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   p.tmem_cols = cols;
   const size_t np = passes == 3 ? 2 : 1;
   const size_t a_slot = np * (size_t)TC_BM * 64;                          // pre-split A tile: hi [+ lo]
-  const size_t stage_bytes = bf16 ? (asplit ? np * (size_t)bn * 64 : np * ((size_t)TC_BM * 64 + (size_t)bn * 64))
+  // CTA-pair MMA (cta_group::2) for the pre-split f16x3 GEMMs on 256-wide tiles: half the W bytes per CTA and k-block
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("GRAFP_TC_PAIR"); pair_env = e ? atoi(e) : 1; }
+  // Measured (scripts/gemm_trace.py, M = 262 144 / 131 072): k-block time 1 200 -> 830-990 cycles for k >= 512; at k = 256 the
+  // tile's main loop becomes shorter than its epilogue and the pair is 4 % slower than two independent CTAs.
+  static int pair_min_k = -1;
+  if (pair_min_k < 0) { const char* e = getenv("GRAFP_TC_PAIR_MIN_K"); pair_min_k = e ? atoi(e) : 512; }
+  const bool pair = pair_env != 0 && cluster == 2 && asplit && f16 && passes == 3 && a.groups == 1 && !a.row_sumsq &&
+                    a.k1 + a.k2 >= pair_min_k;
+  const size_t stage_bytes = bf16 ? (asplit ? np * (size_t)(pair ? bn / 2 : bn) * 64 : np * ((size_t)TC_BM * 64 + (size_t)bn * 64))
                                   : np * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
   // Shared-memory plan.  The fp32 A ring covers the HBM latency (a memory-bound shape needs ~75 KB in flight
   // per SM to stream at the HBM rate), the operand stages only the transform -> MMA hand-off: narrow tiles
   // (small stages) get a deep ring and three operand stages, 256-wide tiles keep three ring slots.
-  const size_t n_store = y_both ? 4 : 2;
+  const size_t n_store = (y_both ? 2 : 1) * (pair ? 3 : 2);        // staging tiles: one (two) per epilogue group
   const size_t budget = 220 * 1024 - 1024 - n_store * TC_STORE_BYTES;      // 227 KB minus ~6 KB static
   int raw = 0, stages;
   if (bf16 && !asplit) {
@@ -842,7 +893,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
     // shared memory is A tiles in flight from HBM
     static int ws_env = -1;
     if (ws_env < 0) { const char* e = getenv("GRAFP_TC_ASPLIT_WSTAGES"); ws_env = e ? atoi(e) : 0; }
-    int ws = ws_env >= 1 && ws_env <= TC_MAX_STAGES ? ws_env : 3;
+    int ws = ws_env >= 1 && ws_env <= TC_MAX_STAGES ? ws_env : (pair ? 5 : 3);
     while (ws > 1 && budget < ws * stage_bytes + 3 * a_slot) --ws;
     raw = (int)((budget - ws * stage_bytes) / a_slot);
     if (raw > TC_RAW_MAX) raw = TC_RAW_MAX;
@@ -868,7 +919,8 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   KernFn kern;
   if (f16) {
     GRAFP_REQUIRE(passes == 3 && !a.a2_gather_idx, "gemm_tc: the fp16 operand format exists as the 3-pass f16x3 engine only");
-    if (asplit) kern = cluster == 2 ? gemm_tc_kernel<3, 2, true, true, false, true> : gemm_tc_kernel<3, 1, true, true, false, true>;
+    if (pair) kern = gemm_tc_kernel<3, 2, true, true, false, true, true>;
+    else if (asplit) kern = cluster == 2 ? gemm_tc_kernel<3, 2, true, true, false, true> : gemm_tc_kernel<3, 1, true, true, false, true>;
     else kern = cluster == 2 ? gemm_tc_kernel<3, 2, true, false, false, true> : gemm_tc_kernel<3, 1, true, false, false, true>;
   } else if (a.a2_gather_idx)
     kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, true, false, true> : gemm_tc_kernel<3, 1, true, false, true>)
