@@ -241,13 +241,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (kPair) {
             if (crank == 0) mbar_arrive_expect_tx(&raw_full_bar[r], 2 * kNP * kAop);      // both CTAs' tiles
             const uint32_t lb = mapa_rank(smem_u32(&raw_full_bar[r]), 0);
-            tma_load_3d_pair(a_hi(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 0, lb);
-            tma_load_3d_pair(a_lo(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 1, lb);
+            tma_load_3d_pair(a_hi(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 0, lb);      // hi and lo planes in one box
             continue;
           }
           mbar_arrive_expect_tx(&raw_full_bar[r], kNP * kAop);
-          tma_load_3d(a_hi(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 0, &raw_full_bar[r]);
-          if (kPasses == 3) tma_load_3d(a_lo(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 1, &raw_full_bar[r]);
+          tma_load_3d(a_hi(r), &tmA1, g * p.k1 + kb * TC_BK, m0, 0, &raw_full_bar[r]);   // hi [and lo] planes in one box
         }
       }
     }
@@ -307,11 +305,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             // my half of the W tile into MY shared memory, counted on the leader's barrier
             const int half = p.bn / 2;
             const uint32_t lb = mapa_rank(smem_u32(&full_bar[s]), 0);
-            tma_load_2d_pair(b_hi(s), &tmW, k, g * p.n + n0 + (int)crank * half, lb);
-            tma_load_2d_pair(b_lo(s), &tmW, k, p.n_total + g * p.n + n0 + (int)crank * half, lb);
+            tma_load_3d_pair(b_hi(s), &tmW, k, g * p.n + n0 + (int)crank * half, 0, lb);
           } else if (do_w) {
-            if (kCluster == 2) {
-              // my half of the weight tile, multicast to both CTAs of the pair (tmW box = bn/2 rows)
+            if (kBf16) {
+              // 16-bit engines: tmW is (k, n_total, planes); without multicast one box carries the hi and the lo tile
+              if (kCluster == 2) {
+                // my half of the weight tile, multicast to both CTAs of the pair (tmW box = bn/2 rows per plane): the hi
+                // half-tile lands at b_hi + off, the lo half-tile b_bytes further
+                const int half = p.bn / 2;
+                const uint32_t off = crank * (uint32_t)half * kOpRow;
+                // (my hi half-tile and my lo half-tile are a whole tile apart in shared memory: two requests, the map's
+                // box holds one plane in this mode)
+                tma_load_3d_mc(b_hi(s) + off, &tmW, k, g * p.n + n0 + (int)crank * half, 0, &full_bar[s], 0x3);
+                if (kPasses == 3)
+                  tma_load_3d_mc(b_lo(s) + off, &tmW, k, g * p.n + n0 + (int)crank * half, 1, &full_bar[s], 0x3);
+              } else {
+                tma_load_3d(b_hi(s), &tmW, k, g * p.n + n0, 0, &full_bar[s]);
+              }
+            } else if (kCluster == 2) {
               const int half = p.bn / 2;
               const uint32_t off = crank * (uint32_t)half * kOpRow;
               tma_load_2d_mc(b_hi(s) + off, &tmW, k, g * p.n + n0 + (int)crank * half, &full_bar[s], 0x3);
@@ -615,8 +626,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         named_bar_sync(half < 2 ? 1 + half : 5, 128);
         if (store_thread) {
           if (p.y_split) {
-            tma_store_3d(&tmYs, sb, (int)(col0 + c), m0, 0);
-            if (p.y_split == 2) tma_store_3d(&tmYs, sb + TC_STORE_BYTES / 2, (int)(col0 + c), m0, 1);
+            tma_store_3d(&tmYs, sb, (int)(col0 + c), m0, 0);      // one box: the hi tile and (3-pass engines) the lo tile
             if (p.y_both) tma_store_2d(&tmY, sb32, (int)(col0 + c), m0);
           } else {
             tma_store_2d(&tmY, sb, (int)(col0 + c), m0);
@@ -713,12 +723,15 @@ int tc_make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_
 
 // bf16 (planes, rows, cols) with element strides (plane_stride, ld, 1); box = (32 cols, box_rows, 1), 64B swizzle
 int tc_make_map_3d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t planes,
-                        int64_t ld, int64_t plane_stride, int box_rows) {
+                        int64_t ld, int64_t plane_stride, int box_rows, int box_planes) {
+  // box_planes = 2: ONE request moves the hi and the lo tile (they are adjacent in shared memory).  A TMA request costs
+  // its issuing thread ~400 cycles whatever its size (scripts/micro/tma_rate.cu): two requests per operand and k-block
+  // made the producers, not the tensor pipe, the pace-setters of the 3-pass GEMMs.
   EncodeTiledFn fn = tc_encode_fn();
   GRAFP_REQUIRE(fn, "tc: cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -806,7 +819,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
     if (a.a1_split) {
       GRAFP_REQUIRE(bf16, "gemm_tc: a split-bf16 A operand needs a bf16 engine");
       if (int rc = tc_make_map_3d_bf16(&mA1, a.a1_split, (int64_t)a.groups * a.k1, a.m, passes == 3 ? 2 : 1, a.lda1s,
-                                       a.m * a.lda1s, TC_BM))
+                                       a.m * a.lda1s, TC_BM, passes == 3 ? 2 : 1))
         return rc;
     } else if (int rc = tc_make_map_2d(&mA1, a.a1, a.m, (int64_t)a.groups * a.k1, a.lda1, TC_BM)) {
       return rc;
@@ -829,16 +842,9 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   if (min_waves < 0) { const char* e = getenv("GRAFP_TC_CLUSTER_MIN_WAVES"); min_waves = e ? atoi(e) : 4; }
   const int cluster = (mc_env == 2 && tiles_m >= 2 && bn >= 256 && sm_count() % 2 == 0 &&
                        all_tiles >= min_waves * (int64_t)sm_count()) ? 2 : 1;
-  if (bf16) {
-    if (int rc = tc_make_map_2d_bf16(&mW, f16 ? a.w_split_f16 : a.w_split_bf16, (int64_t)n_total * 2, a.k1 + a.k2, a.ldw,
-                                     cluster == 2 ? bn / 2 : bn))
-      return rc;
-  } else if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
-                                     a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
-    return rc;
   const bool y_both = a.y_split && a.y;                    // dual output: fp32 and split
   if (a.y_split) {
-    if (int rc = tc_make_map_3d_bf16(&mYs, a.y_split, n_total, a.m, passes == 3 ? 2 : 1, a.ldys, a.m * a.ldys, TC_BM)) return rc;
+    if (int rc = tc_make_map_3d_bf16(&mYs, a.y_split, n_total, a.m, passes == 3 ? 2 : 1, a.ldys, a.m * a.ldys, TC_BM, passes == 3 ? 2 : 1)) return rc;
   }
   if (a.y) {
     if (int rc = tc_make_map_2d(&mY, a.y, a.m, n_total, a.ldy, TC_BM)) return rc;
@@ -868,6 +874,15 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   if (pair_min_k < 0) { const char* e = getenv("GRAFP_TC_PAIR_MIN_K"); pair_min_k = e ? atoi(e) : 512; }
   const bool pair = pair_env != 0 && cluster == 2 && asplit && f16 && passes == 3 && a.groups == 1 && !a.row_sumsq &&
                     a.k1 + a.k2 >= pair_min_k;
+  if (bf16) {
+    // the stacked [hi ; lo] weight matrix as (k, n_total, 2 planes): one box = the hi and the lo tile of a k-block
+    if (int rc = tc_make_map_3d_bf16(&mW, f16 ? a.w_split_f16 : a.w_split_bf16, a.k1 + a.k2, n_total, passes == 3 ? 2 : 1, a.ldw,
+                                     (int64_t)n_total * a.ldw, cluster == 2 ? bn / 2 : bn,
+                                     (passes == 3 && (cluster == 1 || pair)) ? 2 : 1))
+      return rc;
+  } else if (int rc = tc_make_map_2d(&mW, passes == 3 ? a.w_split : a.w, (int64_t)n_total * (passes == 3 ? 2 : 1),
+                                     a.k1 + a.k2, a.ldw, cluster == 2 ? bn / 2 : bn))
+    return rc;
   const size_t stage_bytes = bf16 ? (asplit ? np * (size_t)(pair ? bn / 2 : bn) * 64 : np * ((size_t)TC_BM * 64 + (size_t)bn * 64))
                                   : np * (TC_A_BYTES + (size_t)bn * TC_BK * 4);
   // Shared-memory plan.  The fp32 A ring covers the HBM latency (a memory-bound shape needs ~75 KB in flight

@@ -37,6 +37,14 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
       ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -286,6 +294,6 @@ int tc_make_map_3d(CUtensorMap* map, const float* base, int64_t d0, int64_t d1, 
                    int64_t s1, int64_t s2, int box1, int box2);
 // bf16 (planes, rows, cols), element strides (plane_stride, ld, 1); box = (32, box_rows, 1), 64B swizzle
 int tc_make_map_3d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t planes,
-                        int64_t ld, int64_t plane_stride, int box_rows);
+                        int64_t ld, int64_t plane_stride, int box_rows, int box_planes = 1);
 
 }  // namespace grafp
