@@ -162,8 +162,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(&w_empty[s], ((w / p.wslots) & 1u) ^ 1u);
           FF_T(2, 30);
           mbar_arrive_expect_tx(&w_full[s], w1_bytes);
-          tma_load_2d(w_slot(s), &tmW1, kb * 32, j * FF_HC, &w_full[s]);
-          tma_load_2d(w_slot(s) + FF_HC * 64, &tmW1, kb * 32, p.Hd + j * FF_HC, &w_full[s]);
+          tma_load_3d(w_slot(s), &tmW1, kb * 32, j * FF_HC, 0, &w_full[s]);       // hi and lo tile in one request
         }
       };
       auto load_w2 = [&](int j) {
@@ -172,8 +171,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(&w_empty[s], ((w / p.wslots) & 1u) ^ 1u);
           FF_T(2, 31);
           mbar_arrive_expect_tx(&w_full[s], w2_bytes);
-          tma_load_2d(w_slot(s), &tmW2, j * FF_HC + kb * 32, 0, &w_full[s]);
-          tma_load_2d(w_slot(s) + (size_t)p.C * 64, &tmW2, j * FF_HC + kb * 32, p.C, &w_full[s]);
+          tma_load_3d(w_slot(s), &tmW2, j * FF_HC + kb * 32, 0, 0, &w_full[s]);
         }
       };
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -421,8 +419,10 @@ extern "C" int grafp_ffn_fused_fwd(const float* x, int64_t ldx, int64_t M, int C
   GRAFP_REQUIRE(act >= GRAFP_ACT_NONE && act <= GRAFP_ACT_ELU, "ffn_fused: unsupported activation %d", act);
   CUtensorMap mX, mW1, mW2;
   if (int rc = tc_make_map_2d(&mX, x, M, C, ldx, TC_BM)) return rc;
-  if (int rc = tc_make_map_2d_bf16(&mW1, w1_split_f16, 2 * (int64_t)Hd, C, ldw1, FF_HC)) return rc;
-  if (int rc = tc_make_map_2d_bf16(&mW2, w2_split_f16, 2 * (int64_t)C, Hd, ldw2, C)) return rc;
+  // weights as (k, rows, 2 planes): one TMA request brings the hi and the lo tile of a k-block (a request costs the issuing
+  // thread ~400 cycles whatever its size, and the weight stream is 16-48 k-blocks per 128-row tile)
+  if (int rc = tc_make_map_3d_bf16(&mW1, w1_split_f16, C, Hd, 2, ldw1, (int64_t)Hd * ldw1, FF_HC, 2)) return rc;
+  if (int rc = tc_make_map_3d_bf16(&mW2, w2_split_f16, Hd, C, 2, ldw2, (int64_t)C * ldw2, C, 2)) return rc;
   FfnParams p;
   p.C = C; p.Hd = Hd; p.M = M;
   p.scale1 = scale1; p.shift1 = shift1; p.unscale1 = w1_unscale;
