@@ -661,6 +661,9 @@ extern "C" int grafp_debug_tc_trace(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, grafp::g_tc_trace, sizeof(unsigned long long) * 8);
 }
 #endif
+// launches of the CTA-pair kernel so far (debug / test hook, not part of the ABI in include/grafp.h)
+static long long g_pair_launches = 0;
+extern "C" long long grafp_debug_pair_launches() { return g_pair_launches; }
 // ---- host side -------------------------------------------------------------------------
 EncodeTiledFn tc_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -934,7 +937,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   KernFn kern;
   if (f16) {
     GRAFP_REQUIRE(passes == 3 && !a.a2_gather_idx, "gemm_tc: the fp16 operand format exists as the 3-pass f16x3 engine only");
-    if (pair) kern = gemm_tc_kernel<3, 2, true, true, false, true, true>;
+    if (pair) { kern = gemm_tc_kernel<3, 2, true, true, false, true, true>; ++g_pair_launches; }
     else if (asplit) kern = cluster == 2 ? gemm_tc_kernel<3, 2, true, true, false, true> : gemm_tc_kernel<3, 1, true, true, false, true>;
     else kern = cluster == 2 ? gemm_tc_kernel<3, 2, true, false, false, true> : gemm_tc_kernel<3, 1, true, false, false, true>;
   } else if (a.a2_gather_idx)

@@ -32,6 +32,8 @@ for (M, C) in ((262144, 256), (131072, 512)):
     run("fc1 split-in gelu split-out C=%d" % C, lambda: ops.linear(xs, fc1, "gelu", 0.0, out_split=True))
     run("fc1 split-in NO act split-out C=%d" % C, lambda: ops.linear(xs, fc1, out_split=True))
     run("fc1 split-in gelu fp32-out C=%d" % C, lambda: ops.linear(xs, fc1, "gelu", 0.0))
+    run("fc1 split-in NO act fp32-out C=%d" % C, lambda: ops.linear(xs, fc1))
+    run("fc1 split-in relu split-out C=%d" % C, lambda: ops.linear(xs, fc1, "relu", 0.0, out_split=True))
     run("fc1 fp32-in gelu split-out C=%d" % C, lambda: ops.linear(x, fc1, "gelu", 0.0, out_split=True))
     run("fc2 split-in + residual C=%d" % C, lambda: ops.linear(h, fc2, residual=x))
     run("fc2 split-in no residual C=%d" % C, lambda: ops.linear(h, fc2))

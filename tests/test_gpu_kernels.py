@@ -411,6 +411,29 @@ def test_gemm_split_bf16_activations_bit_exact(M, k, hid, n, groups, engine):
     assert torch.equal(ybs.t[0], yh) and (planes == 1 or torch.equal(ybs.t[1], (y32 - yh.float()).to(dt)))
 
 
+def test_gemm_pair_mma_bit_exact(tmp_path):
+    """CTA-pair MMA (tcgen05.mma.cta_group::2, gemm_tc.cu kPair): the pre-split f16x3 GEMMs on 256-wide tiles must give the
+    same bits whether a pair of CTAs computes a 256-row tile with one MMA or each CTA its own 128 rows.  The kernel choice
+    is read from the environment once per process, so the same chain (single, split and dual output, ragged M, k from 256
+    to 1024) runs in two processes: pairs forced on every eligible shape, and pairs off."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for name, env in (("pair", {"GRAFP_TC_CLUSTER_MIN_WAVES": "0", "GRAFP_TC_PAIR_MIN_K": "32", "GRAFP_TC_PAIR": "1"}),
+                      ("solo", {"GRAFP_TC_PAIR": "0", "GRAFP_TC_CLUSTER": "1"})):
+        f = str(tmp_path / (name + ".pt"))
+        e = dict(os.environ); e.update(env)
+        r = subprocess.run([sys.executable, os.path.join(root, "tests", "pair_mma_case.py"), f], env=e, cwd=root,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs.append(torch.load(f))
+    assert outs[0].pop("pair_launches") >= 9 and outs[1].pop("pair_launches") == 0      # the pair kernel really ran / did not
+    assert outs[0].keys() == outs[1].keys() and len(outs[0]) == 12
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
 @pytest.mark.parametrize("B,N,C,k,groups", [(5, 256, 64, 3, 1), (9, 128, 128, 3, 4), (7, 64, 256, 5, 4), (11, 32, 512, 3, 4),
                                             (3, 64, 256, 9, 4)])
 @pytest.mark.parametrize("out_split", [False, True])
