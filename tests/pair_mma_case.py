@@ -19,7 +19,7 @@ def uniform(shape, lo, hi):
 
 
 out = {}
-for (M, k, hid, n) in ((128 * 9 + 37, 256, 1024, 256), (128 * 4, 512, 512, 512), (128 * 7 + 1, 64, 256, 256)):
+for (M, k, hid, n) in ((128 * 9 + 37, 256, 1024, 256), (128 * 4, 512, 512, 512), (128 * 7 + 1, 64, 256, 256), (128 * 6 + 5, 128, 512, 256)):
     a = normal((M, k)).to(dev)
     l1 = _prep.make_linear((normal((hid, k)) / float(np.sqrt(k))).to(dev),
                            uniform((hid,), 0.5, 1.5).to(dev), uniform((hid,), -0.5, 0.5).to(dev))
