@@ -56,6 +56,7 @@ struct TcParams {
   float unscale;       // multiplies the epilogue scale: undoes the host's power-of-two weight pre-scaling (f16x3)
   uint32_t tmem_cols;
   int y_split;         // 0: fp32 output; 2: bf16 [hi ; lo] planes; 1: bf16 hi plane only (1-pass engine)
+  int res_tma;         // the shortcut tile comes by TMA into the fp32 staging tile (coalesced) instead of per-thread row loads
   int y_both;          // with y_split: ALSO write the fp32 output (tmY fp32 map + tmYs split map, two staging tiles)
   int raw;             // depth of the fp32 A ring (bf16 engines with an fp32 A operand)
   // fused max-relative aggregation: the second A source is not read but computed by the transform warps,
@@ -127,7 +128,7 @@ __device__ __forceinline__ float2 unpack16(uint32_t v) {
 // their lo parts stay normal numbers.
 #ifdef TC_TRACE
 // debug build (GRAFP_NVCC_EXTRA=-DTC_TRACE): where block 0's MMA warp spends its cycles (scripts/gemm_trace.py)
-__device__ unsigned long long g_tc_trace[8];
+__device__ unsigned long long g_tc_trace[24];
 #define TC_ACC(var, stmt) do { const long long c0_ = clock64(); stmt; var += clock64() - c0_; } while (0)
 #else
 #define TC_ACC(var, stmt) do { stmt; } while (0)
@@ -137,7 +138,7 @@ template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather, boo
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
-               const __grid_constant__ CUtensorMap tmYs,
+               const __grid_constant__ CUtensorMap tmYs, const __grid_constant__ CUtensorMap tmR,
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
@@ -147,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __shared__ __align__(8) uint64_t raw_empty_bar[TC_RAW_MAX];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t res_bar[3];          // shortcut tile landed in my group's staging tile
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_scale[2][256];   // folded scale / shift of the tile's columns
   __shared__ __align__(16) float s_shift[2][256];
@@ -201,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmYs);
+    tma_prefetch_desc(&tmR);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&xf_bar[s], TC_XF_THREADS);
@@ -210,6 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       mbar_init(&raw_full_bar[r], 1);
       mbar_init(&raw_empty_bar[r], kASplit ? 1 : TC_XF_THREADS);
     }
+    for (int b = 0; b < 3; ++b) mbar_init(&res_bar[b], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], (kPair ? 2 : 1) * kEpiThreads / 32);      // one arrival per epilogue warp
@@ -539,6 +543,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       if (lane == 0) { if (kPair && crank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(bar), 0)); else mbar_arrive(bar); }
     };
     uint32_t ti = 0;
+    uint32_t res_phase = 0;                       // shortcut tiles my group has consumed
+    long long ec[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; (void)ec; const long long ec_t0 = clock64(); (void)ec_t0;
     for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
       const int nt = (int)(tile % tiles_n);
       const int64_t rest = tile / tiles_n;
@@ -561,8 +567,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       if (res_row)
         for (int c = half * 32; c < p.bn; c += 32 * kEpiGroups)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(res_row + c));
-      named_bar_sync(3, kEpiThreads);
-      mbar_wait(&tmem_full_bar[buf], tph);
+      TC_ACC(ec[0], named_bar_sync(3, kEpiThreads));
+      TC_ACC(ec[1], mbar_wait(&tmem_full_bar[buf], tph));
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(quad * 32) << 16);
       float rowsq = 0.0f;
@@ -572,16 +578,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
       for (int c = half * 32; c < p.bn; c += 32 * kEpiGroups) {
         float4 r4[8];
+        if (p.res_tma) {
+          // The shortcut tile (128 rows x 32 fp32) comes by TMA into the fp32 staging tile my group writes its result to:
+          // one coalesced request instead of 8 row-strided 16-byte loads per thread (measured: 5 000+ cycles per chunk,
+          // the longest step of the epilogue).  Every thread later reads its own row of it and overwrites the same bytes.
+          if (store_thread) {
+            bulk_wait_group_read<0>();                      // my group's previous store has read the staging tiles
+            mbar_arrive_expect_tx(&res_bar[half], TC_STORE_BYTES);
+            tma_load_2d(p.y_both ? sb32 : sb, &tmR, (int)(col0 + c), m0, &res_bar[half]);
+          }
+        } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          r4[q] = res_row ? *reinterpret_cast<const float4*>(res_row + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < 8; ++q)
+            r4[q] = res_row ? *reinterpret_cast<const float4*>(res_row + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float v[32];
-        tmem_ld16_nowait(tacc + (uint32_t)c, v);
+        TC_ACC(ec[2], { tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
-        tmem_ld_wait();
+        tmem_ld_wait(); });
+        ec[11] += 1;
         if (c + 32 * kEpiGroups >= p.bn) {        // my last read of this accumulator: hand it back
           tc_fence_before();
           tmem_release(&tmem_empty_bar[buf]);
+        }
+        if (p.res_tma) {
+          mbar_wait(&res_bar[half], res_phase & 1u);
+          ++res_phase;
+          const uint8_t* rb = (p.y_both ? sb32 : sb) + r * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r4[q] = *reinterpret_cast<const float4*>(rb + ((q ^ (r & 7)) << 4));   // 128B swizzle
         }
         switch (p.act) {        // one specialised, branch-free instance per activation
           case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, ssc + c, ssh + c, r4, p.act_param); break;
@@ -594,8 +619,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 32; ++q) rowsq = fmaf(v[q], v[q], rowsq);
         }
-        if (store_thread) bulk_wait_group_read<0>();      // my group's previous store has read `sb`
-        named_bar_sync(half < 2 ? 1 + half : 5, 128);
+        if (!p.res_tma) {       // (with a TMA shortcut tile the wait on its barrier has already ordered us after the store)
+          TC_ACC(ec[3], { if (store_thread) bulk_wait_group_read<0>(); });      // my group's previous store has read `sb`
+          TC_ACC(ec[4], named_bar_sync(half < 2 ? 1 + half : 5, 128));
+        }
+        const long long ec_c0 = clock64(); (void)ec_c0;
         if (p.y_split) {
           // bf16 [hi ; lo] planes: exactly the operand pair a consuming bf16x3 GEMM would derive from the
           // fp32 value (hi = bf16(v), lo = bf16(v - hi)); two 128 x 64 B tiles, 64B swizzle
@@ -622,8 +650,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             *reinterpret_cast<float4*>(dst + r * 128 + ((q ^ (r & 7)) << 4)) =
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
-        fence_proxy_async_smem();
-        named_bar_sync(half < 2 ? 1 + half : 5, 128);
+#ifdef TC_TRACE
+        ec[5] += clock64() - ec_c0;
+#endif
+        TC_ACC(ec[6], fence_proxy_async_smem());
+        TC_ACC(ec[7], named_bar_sync(half < 2 ? 1 + half : 5, 128));
+        const long long ec_c1 = clock64(); (void)ec_c1;
         if (store_thread) {
           if (p.y_split) {
             tma_store_3d(&tmYs, sb, (int)(col0 + c), m0, 0);      // one box: the hi tile and (3-pass engines) the lo tile
@@ -633,6 +665,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
           bulk_commit_group();
         }
+#ifdef TC_TRACE
+        ec[8] += clock64() - ec_c1;
+#endif
       }
       if (p.row_sumsq) {
         // deterministic: group 1 hands its partial to group 0 (fixed order), one atomic per row and
@@ -647,6 +682,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
     if (store_thread) bulk_wait_group_all();
+#ifdef TC_TRACE
+    if (blockIdx.x == 0 && warp == 2 && lane == 0) {
+      g_tc_trace[8] = clock64() - ec_t0;
+      for (int i = 0; i < 9; ++i) g_tc_trace[9 + i] = ec[i];
+      g_tc_trace[18] = ec[11];
+    }
+#endif
   }
   tc_fence_before();
   if (kCluster == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal my barriers
@@ -658,7 +700,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
 #ifdef TC_TRACE
 extern "C" int grafp_debug_tc_trace(unsigned long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, grafp::g_tc_trace, sizeof(unsigned long long) * 8);
+  return (int)cudaMemcpyFromSymbol(out, grafp::g_tc_trace, sizeof(unsigned long long) * 24);
 }
 #endif
 // launches of the CTA-pair kernel so far (debug / test hook, not part of the ABI in include/grafp.h)
@@ -806,7 +848,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   const bool f16 = fmt == 2;
   const int bn = pick_bn(a.n);
   const int n_total = a.groups * a.n;
-  CUtensorMap mA1, mA2, mW, mY, mYs;
+  CUtensorMap mA1, mA2, mW, mY, mYs, mR;
   TcParams p;
   p.tap3_rows = 0; p.tap3_cin = 0;
   if (a.tap3_nodes > 0) {
@@ -854,7 +896,17 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   }
   if (!a.y) mY = mYs;
   if (!a.y_split) mYs = mY;
+  // shortcut by TMA: needs the fp32 staging tile (fp32 or dual output) and a TMA-addressable residual matrix
+  static int res_tma_env = -1;
+  if (res_tma_env < 0) { const char* e = getenv("GRAFP_TC_RES_TMA"); res_tma_env = e ? atoi(e) : 1; }
+  const bool res_tma = res_tma_env != 0 && a.residual && a.y && a.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0;
+  if (res_tma) {
+    if (int rc = tc_make_map_2d(&mR, a.residual, a.m, n_total, a.ldr, TC_BM)) return rc;
+  } else {
+    mR = mY;
+  }
   p.y_both = y_both ? 1 : 0;
+  p.res_tma = res_tma ? 1 : 0;
   p.y_split = a.y_split ? (passes == 3 ? 2 : 1) : 0;     // the 1-pass engine carries the hi plane only
   p.gat_idx = a.a2_gather_idx; p.gat_x = a.a1; p.gat_ld = a.lda1; p.gat_n = a.a2_gather_nodes; p.gat_k = a.a2_gather_k;
   const bool asplit = a.a1_split != nullptr;
@@ -933,7 +985,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   int grid = sm_count() / cluster;
   if (units < grid) grid = (int)units;
   grid *= cluster;
-  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   KernFn kern;
   if (f16) {
     GRAFP_REQUIRE(passes == 3 && !a.a2_gather_idx, "gemm_tc: the fp16 operand format exists as the 3-pass f16x3 engine only");
@@ -965,7 +1017,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA1, mA2, mW, mY, mYs, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA1, mA2, mW, mY, mYs, mR, p);
   if (le != cudaSuccess) return fail("gemm_tc launch: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc");
 }

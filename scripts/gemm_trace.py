@@ -7,7 +7,7 @@ from neuralsampleid_b200 import ops, _prep
 dev = "cuda:0"
 torch.manual_seed(0)
 lib = ctypes.CDLL(os.path.join(ROOT, "neuralsampleid_b200", "libgrafp_sm100a.so"))
-buf = (ctypes.c_ulonglong * 8)()
+buf = (ctypes.c_ulonglong * 24)()
 
 def lin(n, k):
     return _prep.make_linear(torch.randn(n, k, device=dev) / k ** 0.5, torch.ones(n, device=dev), torch.zeros(n, device=dev))
@@ -18,10 +18,18 @@ def run(tag, fn):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     assert lib.grafp_debug_tc_trace(buf) == 0
-    tot, ce, cw, ca, tiles, nkb, S, RAW = [int(b) for b in buf]
+    tot, ce, cw, ca, tiles, nkb, S, RAW = [int(b) for b in buf][:8]
+    et = [int(b) for b in buf][8:19]
     kb = max(1, tiles * nkb)
     print("%-34s %7.1f us | block 0: %3d tiles x %2d k-blocks, W stages %d, A ring %d | cycles per k-block %5.0f: wait tmem_empty %4.0f, W %4.0f, A %4.0f, issue+rest %4.0f"
           % (tag, 1e3 * e0.elapsed_time(e1), tiles, nkb, S, RAW, tot / kb, ce / kb, cw / kb, ca / kb, (tot - ce - cw - ca) / kb), flush=True)
+    ch = max(1, et[10])
+    names = ["tile-start barrier", "wait tmem_full", "tmem ld", "wait store read", "barrier A", "pack + st.shared", "fence", "barrier B", "TMA store issue"]
+    per_tile = ", ".join("%s %.0f" % (n, et[1 + i] / max(1, tiles)) for i, n in enumerate(names[:2]))
+    per_chunk = ", ".join("%s %.0f" % (n, et[1 + i] / ch) for i, n in enumerate(names) if i >= 2)
+    acc = sum(et[1:10])
+    print("      epilogue warp 2: %.0f cycles per tile (%d chunks of mine per tile); per tile: %s; per chunk: %s, rest (residual loads, apply) %.0f"
+          % (et[0] / max(1, tiles), ch // max(1, tiles), per_tile, per_chunk, (et[0] - acc) / ch), flush=True)
 
 for (M, C) in ((262144, 256), (131072, 512)):
     x = torch.randn(M, C, device=dev)
