@@ -66,19 +66,34 @@ struct TcParams {
 
 // v = act(v * scale + shift) + residual over one 32-column chunk of a row; scale/shift come from
 // shared memory as 128-bit broadcast reads (every thread of the warp reads the same 32 columns), the
-// residual from registers (loaded before the TMEM wait so its latency overlaps it)
+// residual through `res(q)`: the staged TMA tile (shared memory) or the row in global memory
 template <int ACT>
-__device__ __forceinline__ void epi_apply(float (&v)[32], const float* scale, const float* shift,
-                                          const float4 (&res)[8], float act_param) {
+__device__ __forceinline__ void epi_apply(float (&v)[32], const float* scale, const float* shift, float act_param) {
 #pragma unroll
   for (int q = 0; q < 32; q += 4) {
     const float4 sc = *reinterpret_cast<const float4*>(scale + q);
     const float4 sh = *reinterpret_cast<const float4*>(shift + q);
-    const float4 r4 = res[q >> 2];
-    v[q + 0] = apply_act(fmaf(v[q + 0], sc.x, sh.x), ACT, act_param) + r4.x;
-    v[q + 1] = apply_act(fmaf(v[q + 1], sc.y, sh.y), ACT, act_param) + r4.y;
-    v[q + 2] = apply_act(fmaf(v[q + 2], sc.z, sh.z), ACT, act_param) + r4.z;
-    v[q + 3] = apply_act(fmaf(v[q + 3], sc.w, sh.w), ACT, act_param) + r4.w;
+    v[q + 0] = apply_act(fmaf(v[q + 0], sc.x, sh.x), ACT, act_param);
+    v[q + 1] = apply_act(fmaf(v[q + 1], sc.y, sh.y), ACT, act_param);
+    v[q + 2] = apply_act(fmaf(v[q + 2], sc.z, sh.z), ACT, act_param);
+    v[q + 3] = apply_act(fmaf(v[q + 3], sc.w, sh.w), ACT, act_param);
+  }
+}
+// v += shortcut row piece (32 floats: the staged TMA tile in shared memory, 128B-swizzled, or global memory)
+__device__ __forceinline__ void epi_add_smem(float (&v)[32], const uint8_t* row_base, int r) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(row_base + ((q ^ (r & 7)) << 4));
+    v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    if ((q & 3) == 3) asm volatile("" ::: "memory");      // at most four loads (16 registers) in flight
+  }
+}
+__device__ __forceinline__ void epi_add_global(float (&v)[32], const float* row) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(row + 4 * q);
+    v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    if (q & 1) asm volatile("" ::: "memory");      // two loads in flight, not eight: this rare path must not cost the common ones registers
   }
 }
 
@@ -130,12 +145,16 @@ __device__ __forceinline__ float2 unpack16(uint32_t v) {
 // debug build (GRAFP_NVCC_EXTRA=-DTC_TRACE): where block 0's MMA warp spends its cycles (scripts/gemm_trace.py)
 __device__ unsigned long long g_tc_trace[24];
 #define TC_ACC(var, stmt) do { const long long c0_ = clock64(); stmt; var += clock64() - c0_; } while (0)
+#define TC_CLK(name) const long long name = clock64()
+#define TC_SINCE(var, name) var += clock64() - name
 #else
 #define TC_ACC(var, stmt) do { stmt; } while (0)
+#define TC_CLK(name) do { } while (0)
+#define TC_SINCE(var, name) do { } while (0)
 #endif
 
 template <int kPasses, int kCluster, bool kBf16, bool kASplit, bool kGather, bool kF16 = false, bool kPair = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)      // 128 registers: 4 warps per scheduler x 32 x 128 = its 16 K registers
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmYs, const __grid_constant__ CUtensorMap tmR,
@@ -352,7 +371,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const uint32_t d_alo = kAop >> 4, d_bhi = kASplit ? 0u : (kNP * kAop) >> 4, d_blo = d_bhi + (b_bytes >> 4);
       const uint32_t d_ring0 = umma_desc_lo(smem_u32(raw0)), d_ring = (kNP * kAop) >> 4;     // kASplit: the A ring
       uint32_t s = 0, ph = 0, ti = 0, sa = 0, pha = 0;
-      long long cy_e = 0, cy_w = 0, cy_a = 0; const long long cy_t0 = clock64(); (void)cy_t0; (void)cy_e; (void)cy_w; (void)cy_a;
+#ifdef TC_TRACE
+      long long cy_e = 0, cy_w = 0, cy_a = 0; const long long cy_t0 = clock64();
+#endif
       for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
         const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
         TC_ACC(cy_e, mbar_wait(&tmem_empty_bar[buf], tph ^ 1u));          // epilogue drained this accumulator
@@ -544,7 +565,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     };
     uint32_t ti = 0;
     uint32_t res_phase = 0;                       // shortcut tiles my group has consumed
-    long long ec[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; (void)ec; const long long ec_t0 = clock64(); (void)ec_t0;
+#ifdef TC_TRACE
+    long long ec[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long ec_t0 = clock64();
+#endif
     for (int64_t tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
       const int nt = (int)(tile % tiles_n);
       const int64_t rest = tile / tiles_n;
@@ -577,7 +600,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tmem_release(&tmem_empty_bar[buf]);
       }
       for (int c = half * 32; c < p.bn; c += 32 * kEpiGroups) {
-        float4 r4[8];
         if (p.res_tma) {
           // The shortcut tile (128 rows x 32 fp32) comes by TMA into the fp32 staging tile my group writes its result to:
           // one coalesced request instead of 8 row-strided 16-byte loads per thread (measured: 5 000+ cycles per chunk,
@@ -587,16 +609,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             mbar_arrive_expect_tx(&res_bar[half], TC_STORE_BYTES);
             tma_load_2d(p.y_both ? sb32 : sb, &tmR, (int)(col0 + c), m0, &res_bar[half]);
           }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            r4[q] = res_row ? *reinterpret_cast<const float4*>(res_row + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float v[32];
         TC_ACC(ec[2], { tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
         tmem_ld_wait(); });
+#ifdef TC_TRACE
         ec[11] += 1;
+#endif
         if (c + 32 * kEpiGroups >= p.bn) {        // my last read of this accumulator: hand it back
           tc_fence_before();
           tmem_release(&tmem_empty_bar[buf]);
@@ -604,17 +624,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (p.res_tma) {
           mbar_wait(&res_bar[half], res_phase & 1u);
           ++res_phase;
-          const uint8_t* rb = (p.y_both ? sb32 : sb) + r * 128;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) r4[q] = *reinterpret_cast<const float4*>(rb + ((q ^ (r & 7)) << 4));   // 128B swizzle
         }
+
         switch (p.act) {        // one specialised, branch-free instance per activation
-          case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, ssc + c, ssh + c, r4, p.act_param); break;
-          case GRAFP_ACT_RELU:  epi_apply<GRAFP_ACT_RELU>(v, ssc + c, ssh + c, r4, p.act_param); break;
-          case GRAFP_ACT_LEAKY: epi_apply<GRAFP_ACT_LEAKY>(v, ssc + c, ssh + c, r4, p.act_param); break;
-          case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, ssc + c, ssh + c, r4, p.act_param); break;
-          default:              epi_apply<GRAFP_ACT_ELU>(v, ssc + c, ssh + c, r4, p.act_param); break;
+          case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, ssc + c, ssh + c, p.act_param); break;
+          case GRAFP_ACT_RELU:  epi_apply<GRAFP_ACT_RELU>(v, ssc + c, ssh + c, p.act_param); break;
+          case GRAFP_ACT_LEAKY: epi_apply<GRAFP_ACT_LEAKY>(v, ssc + c, ssh + c, p.act_param); break;
+          case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, ssc + c, ssh + c, p.act_param); break;
+          default:              epi_apply<GRAFP_ACT_ELU>(v, ssc + c, ssh + c, p.act_param); break;
         }
+        if (p.res_tma) epi_add_smem(v, (p.y_both ? sb32 : sb) + r * 128, r);
+        else if (res_row) epi_add_global(v, res_row + c);      // (rare: split-only output or unaligned shortcut)
         if (p.row_sumsq) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) rowsq = fmaf(v[q], v[q], rowsq);
@@ -623,7 +643,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           TC_ACC(ec[3], { if (store_thread) bulk_wait_group_read<0>(); });      // my group's previous store has read `sb`
           TC_ACC(ec[4], named_bar_sync(half < 2 ? 1 + half : 5, 128));
         }
-        const long long ec_c0 = clock64(); (void)ec_c0;
+        TC_CLK(ec_c0);
         if (p.y_split) {
           // bf16 [hi ; lo] planes: exactly the operand pair a consuming bf16x3 GEMM would derive from the
           // fp32 value (hi = bf16(v), lo = bf16(v - hi)); two 128 x 64 B tiles, 64B swizzle
@@ -650,12 +670,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             *reinterpret_cast<float4*>(dst + r * 128 + ((q ^ (r & 7)) << 4)) =
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
-#ifdef TC_TRACE
-        ec[5] += clock64() - ec_c0;
-#endif
+        TC_SINCE(ec[5], ec_c0);
         TC_ACC(ec[6], fence_proxy_async_smem());
         TC_ACC(ec[7], named_bar_sync(half < 2 ? 1 + half : 5, 128));
-        const long long ec_c1 = clock64(); (void)ec_c1;
+        TC_CLK(ec_c1);
         if (store_thread) {
           if (p.y_split) {
             tma_store_3d(&tmYs, sb, (int)(col0 + c), m0, 0);      // one box: the hi tile and (3-pass engines) the lo tile
@@ -665,9 +683,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
           bulk_commit_group();
         }
-#ifdef TC_TRACE
-        ec[8] += clock64() - ec_c1;
-#endif
+        TC_SINCE(ec[8], ec_c1);
       }
       if (p.row_sumsq) {
         // deterministic: group 1 hands its partial to group 0 (fixed order), one atomic per row and
