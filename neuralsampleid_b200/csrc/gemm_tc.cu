@@ -67,16 +67,33 @@ struct TcParams {
 // v = act(v * scale + shift) + residual over one 32-column chunk of a row; scale/shift come from
 // shared memory as 128-bit broadcast reads (every thread of the warp reads the same 32 columns), the
 // residual through `res(q)`: the staged TMA tile (shared memory) or the row in global memory
+// The first 16 columns' scale / shift (sc0, sh0) were fetched BEFORE the TMEM load: under the MMA's operand traffic a
+// shared-memory read takes > 100 cycles and the profile showed this loop waiting on the short scoreboard (the whole
+// scale / shift / activation step cost 1 300-2 000 cycles per chunk); the second half is fetched while the first computes.
 template <int ACT>
-__device__ __forceinline__ void epi_apply(float (&v)[32], const float* scale, const float* shift, float act_param) {
+__device__ __forceinline__ void epi_apply(float (&v)[32], const float4 (&sc0)[4], const float4 (&sh0)[4], const float* scale,
+                                          const float* shift, float act_param) {
+  float4 sc1[4], sh1[4];
 #pragma unroll
-  for (int q = 0; q < 32; q += 4) {
-    const float4 sc = *reinterpret_cast<const float4*>(scale + q);
-    const float4 sh = *reinterpret_cast<const float4*>(shift + q);
-    v[q + 0] = apply_act(fmaf(v[q + 0], sc.x, sh.x), ACT, act_param);
-    v[q + 1] = apply_act(fmaf(v[q + 1], sc.y, sh.y), ACT, act_param);
-    v[q + 2] = apply_act(fmaf(v[q + 2], sc.z, sh.z), ACT, act_param);
-    v[q + 3] = apply_act(fmaf(v[q + 3], sc.w, sh.w), ACT, act_param);
+  for (int i = 0; i < 4; ++i) {
+    sc1[i] = *reinterpret_cast<const float4*>(scale + 16 + 4 * i);
+    sh1[i] = *reinterpret_cast<const float4*>(shift + 16 + 4 * i);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = 4 * i;
+    v[q + 0] = apply_act(fmaf(v[q + 0], sc0[i].x, sh0[i].x), ACT, act_param);
+    v[q + 1] = apply_act(fmaf(v[q + 1], sc0[i].y, sh0[i].y), ACT, act_param);
+    v[q + 2] = apply_act(fmaf(v[q + 2], sc0[i].z, sh0[i].z), ACT, act_param);
+    v[q + 3] = apply_act(fmaf(v[q + 3], sc0[i].w, sh0[i].w), ACT, act_param);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = 16 + 4 * i;
+    v[q + 0] = apply_act(fmaf(v[q + 0], sc1[i].x, sh1[i].x), ACT, act_param);
+    v[q + 1] = apply_act(fmaf(v[q + 1], sc1[i].y, sh1[i].y), ACT, act_param);
+    v[q + 2] = apply_act(fmaf(v[q + 2], sc1[i].z, sh1[i].z), ACT, act_param);
+    v[q + 3] = apply_act(fmaf(v[q + 3], sc1[i].w, sh1[i].w), ACT, act_param);
   }
 }
 // v += shortcut row piece (32 floats: the staged TMA tile in shared memory, 128B-swizzled, or global memory)
@@ -610,6 +627,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             tma_load_2d(p.y_both ? sb32 : sb, &tmR, (int)(col0 + c), m0, &res_bar[half]);
           }
         }
+        float4 sc0[4], sh0[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          sc0[i] = *reinterpret_cast<const float4*>(ssc + c + 4 * i);
+          sh0[i] = *reinterpret_cast<const float4*>(ssh + c + 4 * i);
+        }
         float v[32];
         TC_ACC(ec[2], { tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld16_nowait(tacc + (uint32_t)c + 16u, v + 16);
@@ -627,11 +650,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
 
         switch (p.act) {        // one specialised, branch-free instance per activation
-          case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, ssc + c, ssh + c, p.act_param); break;
-          case GRAFP_ACT_RELU:  epi_apply<GRAFP_ACT_RELU>(v, ssc + c, ssh + c, p.act_param); break;
-          case GRAFP_ACT_LEAKY: epi_apply<GRAFP_ACT_LEAKY>(v, ssc + c, ssh + c, p.act_param); break;
-          case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, ssc + c, ssh + c, p.act_param); break;
-          default:              epi_apply<GRAFP_ACT_ELU>(v, ssc + c, ssh + c, p.act_param); break;
+          case GRAFP_ACT_NONE:  epi_apply<GRAFP_ACT_NONE>(v, sc0, sh0, ssc + c, ssh + c, p.act_param); break;
+          case GRAFP_ACT_RELU:  epi_apply<GRAFP_ACT_RELU>(v, sc0, sh0, ssc + c, ssh + c, p.act_param); break;
+          case GRAFP_ACT_LEAKY: epi_apply<GRAFP_ACT_LEAKY>(v, sc0, sh0, ssc + c, ssh + c, p.act_param); break;
+          case GRAFP_ACT_GELU:  epi_apply<GRAFP_ACT_GELU>(v, sc0, sh0, ssc + c, ssh + c, p.act_param); break;
+          default:              epi_apply<GRAFP_ACT_ELU>(v, sc0, sh0, ssc + c, ssh + c, p.act_param); break;
         }
         if (p.res_tma) epi_add_smem(v, (p.y_both ? sb32 : sb) + r * 128, r);
         else if (res_row) epi_add_global(v, res_row + c);      // (rare: split-only output or unaligned shortcut)
