@@ -198,6 +198,11 @@ class KernelTimer:
             info = "ffn_fused m=%d c=%d hidden=%d" % (args[2], args[3], args[4])
             name = "grafp_gemm_fwd"
             extra = 4.0 * args[2] * args[3] * args[4]
+        elif name == "grafp_mrconv_fc2_fused_fwd":
+            # MRConv's grouped conv (2 M (C/2) 2C useful flops) + fc2 (2 M 2C C): counted in the GEMM class
+            info = "mrconv_fc2_fused m=%d c=%d" % (args[4], args[5])
+            name = "grafp_gemm_fwd"
+            extra = 6.0 * args[4] * args[5] * args[5]
         elif name == "grafp_knn_fwd":
             info = "knn N=%d C=%d" % (args[2], args[3])
         elif name == "grafp_mr_aggregate_fwd":

@@ -194,12 +194,30 @@ int grafp_split_f16(const float* w, int64_t count, float prescale, void* out_f16
  * in ONE kernel: the (M, Hd) hidden tensor never reaches HBM (it is the largest tensor of the forward).  Both GEMMs run
  * on the f16x3 engine with the operand values and accumulation order of the two grafp_gemm_fwd launches they replace:
  * the result is bit-identical.  x (M, C) fp32 (also the shortcut); w1_split_f16 (2*Hd, C), w2_split_f16 (2*C, Hd): the
- * grafp_split_f16 planes of the pre-scaled weights, w*_unscale = 2^-s.  C in {64, 128}, Hd a multiple of 64. */
+ * grafp_split_f16 planes of the pre-scaled weights, w*_unscale = 2^-s.  C in {64, 128}, Hd a multiple of 64, at most 512. */
 int grafp_ffn_fused_supported(int64_t M, int C, int Hd);
 int grafp_ffn_fused_fwd(const float* x, int64_t ldx, int64_t M, int C, int Hd, const void* w1_split_f16, int64_t ldw1,
                         float w1_unscale, const float* scale1, const float* shift1, int act, float act_param,
                         const void* w2_split_f16, int64_t ldw2, float w2_unscale, const float* scale2,
                         const float* shift2, float* y, int64_t ldy, void* stream);
+
+/* ---- fused Grapher tail: MRConv2d's grouped conv -> fc2 + shortcut ---------------------------------------
+ * MRConv2d.forward (encoder/gcn_lib/torch_vertex.py:24-34: BasicConv([2C, 2C], groups = 4) over the channel-interleaved
+ * [x, m], m = grafp_mr_aggregate_fwd's max-relative features) followed by Grapher.forward's fc2 + BatchNorm + shortcut
+ * (torch_vertex.py:183-195), eval-mode BatchNorm folded:
+ *   y = res + scale2 * ( act(scale1 * ([x | m] W1^T) + shift1) W2^T ) + shift2
+ * in ONE kernel: the (M, 2C) MRConv output never reaches HBM.  f16x3 engine; operand values and accumulation order
+ * of the two grafp_gemm_fwd launches it replaces (bit-identical).  x, m, res (M, C) fp32.  w1_chunked_f16: the
+ * grafp_split_f16 planes (2, 2C, 64) of the pre-scaled grouped weight in CHUNK-LOCAL form: hidden row r, chunk
+ * j = r / 64, multiplies x[:, 32j + c] by column c and m[:, 32j + c] by column 32 + c (c < 32) -- at C = 128 that IS
+ * the de-interleaved groups = 4 weight (256, 32 + 32); at C = 64 each chunk holds two groups block-diagonally.
+ * w2_split_f16 (2, C, 2C): fc2.  C in {64, 128}. */
+int grafp_mrconv_fc2_fused_supported(int64_t M, int C);
+int grafp_mrconv_fc2_fused_fwd(const float* x, int64_t ldx, const float* m, int64_t ldm, int64_t M, int C,
+                               const void* w1_chunked_f16, int64_t ldw1, float w1_unscale, const float* scale1,
+                               const float* shift1, int act, float act_param, const void* w2_split_f16, int64_t ldw2,
+                               float w2_unscale, const float* scale2, const float* shift2, const float* res,
+                               int64_t ldr, float* y, int64_t ldy, void* stream);
 
 /* Stem: Conv2d(Cin -> Cout, 1x1, no bias) + BatchNorm2d + activation on a tiny input width
  * (encoder/graph_encoder.py:151-153, 201-202), fused with the layout change: reads the reference's

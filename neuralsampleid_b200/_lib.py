@@ -58,6 +58,9 @@ SIGNATURES = {
     "grafp_node_mean": [_P, _I, _I, _I, _P, _P],
     "grafp_ffn_fused_supported": [_L, _I, _I],
     "grafp_ffn_fused_fwd": [_P, _L, _L, _I, _I, _P, _L, _F, _P, _P, _I, _F, _P, _L, _F, _P, _P, _P, _L, _P],
+    "grafp_mrconv_fc2_fused_supported": [_L, _I],
+    "grafp_mrconv_fc2_fused_fwd": [_P, _L, _P, _L, _L, _I, _P, _L, _F, _P, _P, _I, _F, _P, _L, _F, _P, _P, _P, _L, _P,
+                                   _L, _P],
     "grafp_frame_window_fwd": [_P, _L, _P, _I, _I, _L, _P, _P],
     "grafp_power_spectrum_fwd": [_P, _L, _L, _I, _I, _P, _L, _P],
     "grafp_amplitude_to_db_fwd": [_P, _L, _F, _F, _F, _P, _P],

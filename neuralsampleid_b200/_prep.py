@@ -65,13 +65,17 @@ def tap3_weight(weight: torch.Tensor) -> torch.Tensor:
 class Linear:
     """Prepared operands of one fused GEMM layer: weight (groups*n, k), optional stacked tf32
     [hi ; lo] split for the tcgen05 3xTF32 engine, per-channel scale / shift."""
-    __slots__ = ("w", "w_split", "w_split_bf16", "w_split_f16", "f16_unscale", "scale", "shift", "groups")
+    __slots__ = ("w", "w_split", "w_split_bf16", "w_split_f16", "f16_unscale", "scale", "shift", "groups",
+                 "w_mr_chunked")
 
     def __init__(self, w, scale, shift, groups=1, w_split=None, w_split_bf16=None, w_split_f16=None,
                  f16_unscale=0.0):
         self.w, self.scale, self.shift, self.groups = w, scale, shift, groups
         self.w_split, self.w_split_bf16 = w_split, w_split_bf16
         self.w_split_f16, self.f16_unscale = w_split_f16, f16_unscale
+        # MRConv2d's grouped dual-source weight in the chunk-local form grafp_mrconv_fc2_fused_fwd reads
+        # (include/grafp.h): fp16 planes (2, 2C, 64), or None
+        self.w_mr_chunked = None
 
 
 @torch.no_grad()
@@ -84,6 +88,7 @@ def make_linear(w: torch.Tensor, scale, shift, groups: int = 1, dual: bool = Fal
     w = w.float().contiguous()
     n_total, k = w.shape
     parts = 2 if dual else 1
+    orig_groups, orig_shape = groups, (n_total, k * groups // parts)      # (2C, C) for MRConv2d's layer
     if groups > 1 and (k // parts) % 32 != 0 and ((k // parts) * groups) % 32 == 0:
         n = n_total // groups
         kp = k // parts
@@ -101,4 +106,17 @@ def make_linear(w: torch.Tensor, scale, shift, groups: int = 1, dual: bool = Fal
         lin.w_split_bf16 = ops.split_bf16(w)
         pre = ops.f16_prescale(w)
         lin.w_split_f16, lin.f16_unscale = ops.split_f16(w, pre), 1.0 / pre
+        if dual and orig_groups == 4 and orig_shape[0] == 2 * orig_shape[1]:
+            # the (2C, 2C) groups = 4 layer of MRConv2d: chunk j = rows [64 j, 64 j + 64) only reads columns
+            # [32 j, 32 j + 32) of either source (one group at C = 128, two block-diagonal groups at C = 64)
+            c = orig_shape[1]                       # C = orig k per group (both sources) * 4 / 2 = n_total / 2
+            sp = lin.w_split_f16.reshape(2, n_total, -1)
+            if groups == 4 and c == 128:
+                lin.w_mr_chunked = sp
+            elif groups == 1 and c == 64:
+                ch = torch.empty((2, n_total, 64), device=w.device, dtype=sp.dtype)
+                for j in range(n_total // 64):
+                    ch[:, 64 * j:64 * j + 64, :32] = sp[:, 64 * j:64 * j + 64, 32 * j:32 * j + 32]
+                    ch[:, 64 * j:64 * j + 64, 32:] = sp[:, 64 * j:64 * j + 64, c + 32 * j:c + 32 * j + 32]
+                lin.w_mr_chunked = ch.contiguous()
     return lin

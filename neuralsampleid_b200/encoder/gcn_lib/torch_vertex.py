@@ -238,6 +238,14 @@ class Grapher(nn.Module):
             taps["fc1"] = y
             taps["idx"] = nn_idx
         fc2 = self._folded("fc2")
+        gconv = self.graph_conv.gconv
+        if isinstance(gconv, MRConv2d) and not want_split:
+            lin, act, slope = gconv.nn.layer_params(0, interleaved_sources=True)
+            if len(gconv.nn._plan) == 1 and ops.mrconv_fc2_fused_ok(lin, fc2, y, x):
+                # C <= 128: MRConv's grouped conv and fc2 are HBM-bound on the 2C-wide tensor between them -- one
+                # kernel keeps it on chip (bit-identical to the two GEMMs)
+                m = ops.mr_aggregate(y, nn_idx, B, N)
+                return ops.mrconv_fc2_fused(y, m, lin, act, slope, fc2, x)
         # the MRConv output feeds only fc2: split-bf16 on the bf16 tensor-core engines (ops.SplitAct)
         g = self.graph_conv.forward_nodes(y, B, N, nn_idx, out_split=ops.split_ok(fc2, 2 * self.channels))
         if want_split:

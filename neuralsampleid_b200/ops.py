@@ -445,6 +445,45 @@ def ffn_fused(x: torch.Tensor, lin1, lin2, act=None, act_param: float = 0.0) -> 
     return y
 
 
+def mrconv_fc2_fused_ok(lin_mr, lin_fc2, x, residual) -> bool:
+    """True when MRConv2d's grouped conv -> fc2 (+ shortcut) can run as ONE kernel with the 2C-wide MRConv output on
+    chip (grafp_mrconv_fc2_fused_fwd): fp32 x of C in {64, 128} channels, f16x3 engine.  GRAFP_NO_MR_FUSED=1 keeps
+    the two-GEMM route."""
+    if os.environ.get("GRAFP_NO_MR_FUSED", "0") == "1" or isinstance(x, SplitAct) or residual is None:
+        return False
+    if _effective_engine() not in (_lib.ENGINE_AUTO, _lib.ENGINE_TC_F16X3):
+        return False
+    if lin_mr.w_mr_chunked is None or lin_fc2.groups != 1 or lin_fc2.w_split_f16 is None:
+        return False
+    if lin_mr.scale is None or lin_mr.shift is None or lin_fc2.scale is None or lin_fc2.shift is None:
+        return False
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+        return False
+    c = x.shape[1]
+    if lin_mr.w_mr_chunked.shape != (2, 2 * c, 64) or lin_fc2.w.shape != (c, 2 * c) or residual.shape != x.shape:
+        return False
+    return bool(_lib.load().grafp_mrconv_fc2_fused_supported(x.shape[0], c)) and x.shape[0] > 0
+
+
+def mrconv_fc2_fused(x: torch.Tensor, m: torch.Tensor, lin_mr, act, act_param: float, lin_fc2,
+                     residual: torch.Tensor) -> torch.Tensor:
+    """y = residual + scale2 * (act(scale1 * ([x | m] Wmr^T) + shift1) Wfc2^T) + shift2 in one kernel
+    (include/grafp.h: the tail of Grapher.forward, torch_vertex.py:24-34 + :183-195)."""
+    x, m, residual = _chk(x, name="x"), _chk(m, name="m"), _chk(residual, name="residual")
+    if m.shape != x.shape:
+        raise GrafpError("mrconv_fc2_fused: x and m must have the same shape")
+    M, c = x.shape
+    y = torch.empty_like(x)
+    w1, w2 = lin_mr.w_mr_chunked, lin_fc2.w_split_f16
+    with torch.cuda.device(x.device):
+        check(_lib.load().grafp_mrconv_fc2_fused_fwd(
+            _ptr(x), x.stride(0), _ptr(m), m.stride(0), M, c, _ptr(w1), w1.stride(1), float(lin_mr.f16_unscale),
+            _ptr(lin_mr.scale), _ptr(lin_mr.shift), act_code(act), act_param, _ptr(w2), w2.stride(0),
+            float(lin_fc2.f16_unscale), _ptr(lin_fc2.scale), _ptr(lin_fc2.shift), _ptr(residual), residual.stride(0),
+            _ptr(y), y.stride(0), _stream(x)), "mrconv_fc2_fused_fwd")
+    return y
+
+
 def stem_supported(cin: int, cout: int, N: int) -> bool:
     return cin in (4, 8, 16) and cout % 4 == 0 and 4 <= cout <= 1024 and 256 % (cout // 4) == 0 and \
         (cin * N + cin * cout) * 4 <= 96 * 1024

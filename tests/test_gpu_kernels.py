@@ -495,6 +495,41 @@ def test_ffn_fused_bit_exact(M, C, act):
     assert float((got.cpu().double() - ref).abs().max() / ref.abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize("act", ["relu", "gelu"])
+@pytest.mark.parametrize("M,C", [(128 * 5 + 7, 64), (4096, 64), (300, 128), (128 * 37, 128), (20000, 128), (128 * 600, 64)])
+def test_mrconv_fc2_fused_bit_exact(M, C, act):
+    """grafp_mrconv_fc2_fused_fwd (MRConv2d's groups = 4 conv over [x, m] -> activation -> fc2 -> + shortcut in one
+    kernel, the 2C-wide MRConv output on chip) is BIT-identical to the two f16x3 GEMM launches it replaces (grouped
+    dual-source GEMM at C = 128, block-diagonal densified GEMM at C = 64), ragged last tile and several tiles per
+    CTA included; and within the engine's tolerance of an fp64 restatement of the grouped conv."""
+    ops = _ops()
+    from neuralsampleid_b200 import _prep
+    x = synth.synth_normal((M, C), 50).to(DEV)
+    m = synth.synth_normal((M, C), 51).abs().to(DEV)
+    res = synth.synth_normal((M, C), 52).to(DEV)
+    kg = C // 2                                      # columns per group: C/4 of x then C/4 of m (de-interleaved)
+    w1 = (synth.synth_normal((2 * C, kg), 53) / float(np.sqrt(kg))).to(DEV)
+    w2 = (synth.synth_normal((C, 2 * C), 54) / float(np.sqrt(2 * C))).to(DEV)
+    sc1, sh1 = synth.synth_uniform((2 * C,), 55, 0.5, 1.5).to(DEV), synth.synth_uniform((2 * C,), 56, -0.5, 0.5).to(DEV)
+    sc2, sh2 = synth.synth_uniform((C,), 57, 0.5, 1.5).to(DEV), synth.synth_uniform((C,), 58, -0.5, 0.5).to(DEV)
+    l1 = _prep.make_linear(w1, sc1, sh1, 4, dual=True)
+    l2 = _prep.make_linear(w2, sc2, sh2, 1)
+    assert ops.mrconv_fc2_fused_ok(l1, l2, x, res)
+    h = ops.linear(x, l1, act, 0.0, a2=m, out_split=True)
+    want = ops.linear(h, l2, None, 0.0, res)
+    got = ops.mrconv_fc2_fused(x, m, l1, act, 0.0, l2, res)
+    assert torch.equal(got, want), float((got - want).abs().max())
+    assert torch.equal(ops.mrconv_fc2_fused(x, m, l1, act, 0.0, l2, res), got)     # deterministic
+    # fp64: group g reads x[:, g C/4 : (g+1) C/4] and m[:, the same columns]
+    xd, md, q = x.cpu().double(), m.cpu().double(), C // 4
+    hid = torch.cat([torch.cat([xd[:, g * q:(g + 1) * q], md[:, g * q:(g + 1) * q]], 1)
+                     @ w1.cpu().double()[g * (C // 2):(g + 1) * (C // 2)].T for g in range(4)], 1)
+    hid = hid * sc1.cpu().double() + sh1.cpu().double()
+    hid = torch.relu(hid) if act == "relu" else torch.nn.functional.gelu(hid)
+    ref = (hid @ w2.cpu().double().T) * sc2.cpu().double() + sh2.cpu().double() + res.cpu().double()
+    assert float((got.cpu().double() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
 def test_gemm_split_bf16_needs_bf16_engine():
     ops = _ops()
     from neuralsampleid_b200 import _lib, _prep
