@@ -376,7 +376,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int row = quad * 32 + lane;
     uint32_t c1 = 0;
     int tr_n = (warp == 12 && lane == 0) ? 0 : 1 << 20; (void)tr_n;
-    FF_DECL(cy_f = 0, cy_he = 0, cy_t0 = clock64());
+    FF_DECL(cy_f = 0, cy_he = 0, cy_ld = 0, cy_act = 0, cy_pk = 0, cy_fn = 0, cy_t0 = clock64());
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       for (int j = 0; j < nch; ++j, ++c1) {
         const uint32_t b = c1 & 1u;
@@ -388,12 +388,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         FF_T(1, 10);
         const uint32_t tacc = t_acc1 + b * FF_HC + half * 32u + ((uint32_t)(quad * 32) << 16);
         float v[32];
-        tmem_ld16_nowait(tacc, v);
+        FF_ACC(cy_ld, tmem_ld16_nowait(tacc, v);
         tmem_ld16_nowait(tacc + 16u, v + 16);
         tmem_ld_wait();
         tc_fence_before();
-        warp_arrive(&acc1_empty[b], lane);
+        warp_arrive(&acc1_empty[b], lane));
         FF_T(1, 11);
+        FF_DECL(c_a0 = clock64());
         switch (p.act) {
           case GRAFP_ACT_NONE:  ff_act32<GRAFP_ACT_NONE>(v, sc, sh, p.act_param); break;
           case GRAFP_ACT_RELU:  ff_act32<GRAFP_ACT_RELU>(v, sc, sh, p.act_param); break;
@@ -402,10 +403,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           default:              ff_act32<GRAFP_ACT_ELU>(v, sc, sh, p.act_param); break;
         }
         FF_T(1, 12);
+#ifdef FF_TRACE
+        cy_act += clock64() - c_a0;
+#endif
         FF_ACC(cy_he, FF_WAIT(&h_empty[b], ((c1 >> 1) & 1u) ^ 1u));  // GEMM 2 of chunk c1 - 2 has read this buffer
         FF_T(1, 13);
         uint8_t* hi = h_hi(b, half);
         uint8_t* lo = hi + FF_KB_BYTES;
+        FF_DECL(c_p0 = clock64());
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t hp[4], lp[4];
@@ -419,12 +424,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           *reinterpret_cast<uint4*>(hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
           *reinterpret_cast<uint4*>(lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
         }
-        fence_proxy_async_smem();
-        warp_arrive(&h_full[b], lane);
+#ifdef FF_TRACE
+        cy_pk += clock64() - c_p0;
+#endif
+        FF_ACC(cy_fn, fence_proxy_async_smem();
+        warp_arrive(&h_full[b], lane));
         FF_T(1, 14);
       }
     }
-    if (warp == 12) { FF_OUT(12, clock64() - cy_t0); FF_OUT(13, cy_f); FF_OUT(14, cy_he); }
+    if (warp == 12) {
+      FF_OUT(12, clock64() - cy_t0); FF_OUT(13, cy_f); FF_OUT(14, cy_he);
+      FF_OUT(17, cy_ld); FF_OUT(18, cy_act); FF_OUT(19, cy_pk); FF_OUT(20, cy_fn);
+    }
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue 2: output tile -> s2 / t2 + shortcut -> y =====
     // A thread's TMEM lane is one tile row, but a row-per-thread global access touches 32 lines per instruction and
@@ -435,7 +446,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint8_t* stg = stage + quad * 2048;
     const int lr = lane >> 2, lq = lane & 3;                 // coalesced form: row within a group of 8, 16 B chunk
     uint32_t ti = 0;
-    FF_DECL(cy_f2 = 0, cy_t0 = clock64());
+    FF_DECL(cy_f2 = 0, cy_tm = 0, cy_st = 0, cy_out = 0, cy_pf = 0, cy_t0 = clock64());
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
       const int64_t row0 = tile * TC_BM + quad * 32;         // first row of this warp's 32
       if (MR) {
@@ -458,12 +469,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           res[it] = rr < p.M ? __ldg(reinterpret_cast<const float4*>(p.x + rr * p.ldx + c + 4 * lq)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float v[16];
-        tmem_ld16_nowait(tacc + (uint32_t)c, v);
-        tmem_ld_wait();
+        FF_ACC(cy_tm, tmem_ld16_nowait(tacc + (uint32_t)c, v);
+        tmem_ld_wait());
         if (c + 16 >= p.C) {
           tc_fence_before();
           warp_arrive(&acc2_empty[ti & 1u], lane);
         }
+        FF_DECL(c_s0 = clock64());
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 s4 = *reinterpret_cast<const float4*>(s_sc2 + c + 4 * q);
@@ -476,6 +488,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
         }
         __syncwarp();
+#ifdef FF_TRACE
+        cy_st += clock64() - c_s0;
+        const long long c_o0 = clock64();
+#endif
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rl = it * 8 + lr;
@@ -485,9 +501,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (rr < p.M) *reinterpret_cast<float4*>(p.y + rr * p.ldy + c + 4 * lq) = o;
         }
         __syncwarp();
+#ifdef FF_TRACE
+        cy_out += clock64() - c_o0;
+#endif
       }
     }
-    if (warp == 4) { FF_OUT(15, clock64() - cy_t0); FF_OUT(16, cy_f2); }
+    if (warp == 4) { FF_OUT(15, clock64() - cy_t0); FF_OUT(16, cy_f2); FF_OUT(21, cy_tm); FF_OUT(22, cy_st); FF_OUT(23, cy_out); }
   }
   tc_fence_before();
   __syncthreads();

@@ -23,11 +23,13 @@ lib = ctypes.CDLL(os.path.join(ROOT, "neuralsampleid_b200", "libgrafp_sm100a.so"
 if hasattr(lib, "grafp_debug_ffn_trace"):
     buf = (ctypes.c_ulonglong * 3072)()
     assert lib.grafp_debug_ffn_trace(buf) == 0
-    b = [int(buf[i]) for i in range(17)]
+    b = [int(buf[i]) for i in range(24)]
     t = max(b[6], 1)
     print("tiles %d, MMA warp cycles/tile %.0f; waits: w_full %.0f h_full %.0f acc1_empty %.0f a_full %.0f acc2_empty %.0f; issue+other %.0f"
           % (t, b[0] / t, b[1] / t, b[2] / t, b[3] / t, b[4] / t, b[5] / t, (b[0] - sum(b[1:6])) / t))
     print("TMA A: %.0f/tile, waiting a_empty %.0f" % (b[8] / t, b[9] / t))
     print("transform: %.0f/tile, waiting data %.0f" % (b[10] / t, b[11] / t))
     print("epilogue 1: %.0f/tile, waiting acc1_full %.0f, h_empty %.0f" % (b[12] / t, b[13] / t, b[14] / t))
+    print("   tmem ld %.0f, act %.0f, pack+sts %.0f, fence+arrive %.0f" % (b[17] / t, b[18] / t, b[19] / t, b[20] / t))
     print("epilogue 2: %.0f/tile, waiting acc2_full %.0f" % (b[15] / t, b[16] / t))
+    print("   tmem ld %.0f, scale+sts %.0f, lds+ldg wait+stg %.0f" % (b[21] / t, b[22] / t, b[23] / t))

@@ -117,6 +117,26 @@ def test_encoder_matches_reference_golden(golden_dir, fname, k):
     assert float(_rel(got_f.cpu(), torch.from_numpy(g["emb"])).max()) < REL_TOL
 
 
+def test_encoder_fused_kernels_are_bit_identical_to_the_gemm_route(monkeypatch):
+    """The on-chip fusions of the default engine (FFN fc1 -> fc2 and MRConv -> fc2 at C <= 128) compute with the
+    operand values and accumulation order of the GEMM launches they replace: the free-running encoder output, every
+    neighbour list included, is bit-identical with them switched off."""
+    enc, _ = _encoder(3)
+    x = synth.synth_uniform((24, 8, 256), 77).to(DEV)
+    with torch.no_grad():
+        taps = []
+        got = enc(x, taps=taps)
+        monkeypatch.setenv("GRAFP_NO_MR_FUSED", "1")
+        taps_mr = []
+        no_mr = enc(x, taps=taps_mr)
+        monkeypatch.setenv("GRAFP_NO_FFN_FUSED", "1")
+        taps_off = []
+        off = enc(x, taps=taps_off)
+    assert torch.equal(got, no_mr) and torch.equal(got, off)
+    for a, b in zip(taps, taps_off):
+        assert torch.equal(a["idx"], b["idx"]) and torch.equal(a["out"], b["out"])
+
+
 @pytest.mark.parametrize("engine", ["simt", "3xtf32", "bf16x3", "f16x3"])
 def test_encoder_engines_agree(engine):
     from neuralsampleid_b200 import ops
