@@ -30,14 +30,20 @@ namespace grafp {
 #ifndef FF_WAIT
 #define FF_WAIT mbar_wait
 #endif
+// The hidden chunk (GEMM 2's A operand) lives in TMEM (tcgen05.st by epilogue 1, tcgen05.mma with A from TMEM): no
+// shared-memory round trip and 64 KB of shared memory back for the rings.  -DFF_HTMEM=0: the shared-memory form.
+#ifndef FF_HTMEM
+#define FF_HTMEM 1
+#endif
 // w0 TMA x, w1 MMA + TMEM, w2 TMA W, w4-7 epilogue 2, w8-11 transform, w12-27 epilogue 1 (the activation is the
 // instruction-heaviest stage: 16 warps = {chunk parity} x {32-column half} x {TMEM lane quarter})
 constexpr int FF_THREADS = 896;
 constexpr int FF_HC = 64;            // hidden columns per chunk
 constexpr int FF_RAW = 2;            // fp32 x k-blocks in flight
-constexpr int FF_WMAX = 6;           // weight ring slots
+constexpr int FF_WMAX = 8;           // weight ring slots
 constexpr int FF_AMAX = 6;           // A operand ring slots (MR mode)
 constexpr uint32_t FF_KB_BYTES = TC_BM * 64;          // one 128-row fp16 k-block (32 columns): 8 KB
+constexpr size_t FF_HOP_BYTES = FF_HTMEM ? 0 : 2 * 2 * 2 * FF_KB_BYTES;      // hidden operand in shared memory
 constexpr size_t FF_STAGE_BYTES = 4 * 2048;           // epilogue 2 staging: 32 rows x 16 columns fp32 per warp
 constexpr size_t FF_SMEM_BUDGET = 216 * 1024;         // dynamic shared memory (the 227 KB limit less ~6 KB static + alignment)
 
@@ -129,7 +135,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   // [ x operand: nkb1 x (hi 8 KB | lo 8 KB) ][ h operand: 2 buffers x 2 k-blocks x (hi | lo) ][ raw ring ][ W ring ]
   uint8_t* xop = smem;
   uint8_t* hop = xop + (size_t)na * 2 * FF_KB_BYTES;
-  uint8_t* rawb = hop + 2 * 2 * 2 * FF_KB_BYTES;
+  uint8_t* rawb = hop + (FF_HTMEM ? 0 : 2 * 2 * 2 * FF_KB_BYTES);
   uint8_t* wring = rawb + (MR ? 0 : FF_RAW * TC_A_BYTES);      // MR: no separate raw ring
   uint8_t* stage = wring + (size_t)p.wslots * p.wslot_bytes;   // epilogue 2: 4 warps x 2 KB
   auto x_hi = [&](int kb) { return xop + (size_t)kb * 2 * FF_KB_BYTES; };
@@ -164,6 +170,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t t_acc1 = tmem_base;                      // 2 x 64 columns
   const uint32_t t_acc2 = tmem_base + 128;                // 2 x C columns (C <= 128)
+  const uint32_t t_h = tmem_base + 384;                   // FF_HTMEM: 2 buffers x [hi 32 | lo 32] columns of packed fp16 pairs
 
   if (warp == 0) {
     // ===== TMA: x rows of my tiles, k-block by k-block, into the raw ring =====
@@ -286,7 +293,28 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           FF_ACC(cy_h, FF_WAIT(&h_full[b], (hcnt >> 1) & 1u));
           if (j == 0) FF_ACC(cy_2, FF_WAIT(&acc2_empty[ti & 1u], ((ti >> 1) & 1u) ^ 1u));
           tc_fence_after();
+#if FF_HTMEM
+          for (int kb = 0; kb < FF_HC / 32; ++kb) {
+            FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
+            tc_fence_after();
+            const uint32_t tah = t_h + b * 64u + (uint32_t)kb * 16u, tal = tah + 32u;
+            const uint32_t dbh = d_w0 + ws * d_wslot, dbl = dbh + d_w2lo;
+            if (elect_one()) {
+#pragma unroll
+              for (uint32_t k = 0; k < 2; ++k) {
+                umma_f16_ts(a2, tal + 8u * k, dbh + 2u * k, UMMA_HI_SW64, idesc2, (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                umma_f16_ts(a2, tah + 8u * k, dbl + 2u * k, UMMA_HI_SW64, idesc2, 1u);
+                umma_f16_ts(a2, tah + 8u * k, dbh + 2u * k, UMMA_HI_SW64, idesc2, 1u);
+              }
+              umma_commit(&w_empty[ws]);
+              if (kb == FF_HC / 32 - 1) umma_commit(&h_empty[b]);
+            }
+            __syncwarp();
+            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
+          }
+#else
           gemm(a2, d_h0 + b * 2 * d_kb, FF_HC / 32, d_w2lo, idesc2, j == 0, &h_empty[b]);
+#endif
           ++hcnt;
         };
         if (!MR) {
@@ -408,9 +436,32 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #endif
         FF_ACC(cy_he, FF_WAIT(&h_empty[b], ((c1 >> 1) & 1u) ^ 1u));  // GEMM 2 of chunk c1 - 2 has read this buffer
         FF_T(1, 13);
+        FF_DECL(c_p0 = clock64());
+#if FF_HTMEM
+        tc_fence_after();
+        // this warp's 32 hidden columns = 16 packed columns of the hi plane and 16 of the lo plane, rows = its TMEM lanes
+        const uint32_t th = t_h + b * 64u + half * 16u + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t hp[8], lp[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            hp[e] = ff_pack(v[16 * q + 2 * e], v[16 * q + 2 * e + 1]);
+            const float2 f = ff_unpack(hp[e]);
+            lp[e] = ff_pack(v[16 * q + 2 * e] - f.x, v[16 * q + 2 * e + 1] - f.y);
+          }
+          tmem_st8(th + 8u * q, hp);
+          tmem_st8(th + 32u + 8u * q, lp);
+        }
+#ifdef FF_TRACE
+        cy_pk += clock64() - c_p0;
+#endif
+        FF_ACC(cy_fn, tmem_st_wait();
+        tc_fence_before();
+        warp_arrive(&h_full[b], lane));
+#else
         uint8_t* hi = h_hi(b, half);
         uint8_t* lo = hi + FF_KB_BYTES;
-        FF_DECL(c_p0 = clock64());
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t hp[4], lp[4];
@@ -429,6 +480,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #endif
         FF_ACC(cy_fn, fence_proxy_async_smem();
         warp_arrive(&h_full[b], lane));
+#endif
         FF_T(1, 14);
       }
     }
@@ -555,7 +607,7 @@ extern "C" int grafp_ffn_fused_fwd(const float* x, int64_t ldx, int64_t M, int C
   p.x = x; p.ldx = ldx; p.y = y; p.ldy = ldy;
   const uint32_t w1b = 2u * FF_HC * 64u, w2b = 2u * (uint32_t)C * 64u;
   p.wslot_bytes = w1b > w2b ? w1b : w2b;
-  const size_t fixed = (size_t)(C / 32) * 2 * FF_KB_BYTES + 2 * 2 * 2 * FF_KB_BYTES + FF_RAW * TC_A_BYTES + FF_STAGE_BYTES;
+  const size_t fixed = (size_t)(C / 32) * 2 * FF_KB_BYTES + FF_HOP_BYTES + FF_RAW * TC_A_BYTES + FF_STAGE_BYTES;
   int slots = (int)((FF_SMEM_BUDGET - fixed) / p.wslot_bytes);
   if (slots > FF_WMAX) slots = FF_WMAX;
   GRAFP_REQUIRE(slots >= 2, "ffn_fused: not enough shared memory");
@@ -603,8 +655,8 @@ extern "C" int grafp_mrconv_fc2_fused_fwd(const float* x, int64_t ldx, const flo
   p.x = res; p.ldx = ldr; p.y = y; p.ldy = ldy;
   const uint32_t w1b = 2u * FF_HC * 64u, w2b = 2u * (uint32_t)C * 64u;
   p.wslot_bytes = w1b > w2b ? w1b : w2b;
-  p.aslots = 5;
-  const size_t fixed = (size_t)p.aslots * 2 * FF_KB_BYTES + 2 * 2 * 2 * FF_KB_BYTES + FF_STAGE_BYTES;
+  p.aslots = FF_HTMEM ? 6 : 5;
+  const size_t fixed = (size_t)p.aslots * 2 * FF_KB_BYTES + FF_HOP_BYTES + FF_STAGE_BYTES;
   int slots = (int)((FF_SMEM_BUDGET - fixed) / p.wslot_bytes);
   if (slots > FF_WMAX) slots = FF_WMAX;
   GRAFP_REQUIRE(slots >= 2, "mrconv_fc2_fused: not enough shared memory");
