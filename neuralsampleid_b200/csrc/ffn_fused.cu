@@ -40,7 +40,7 @@ namespace grafp {
 constexpr int FF_THREADS = 896;
 constexpr int FF_HC = 64;            // hidden columns per chunk
 constexpr int FF_RAW = 2;            // fp32 x k-blocks in flight
-constexpr int FF_WMAX = 8;           // weight ring slots
+constexpr int FF_WMAX = 16;          // weight ring slots
 constexpr int FF_AMAX = 6;           // A operand ring slots (MR mode)
 constexpr uint32_t FF_KB_BYTES = TC_BM * 64;          // one 128-row fp16 k-block (32 columns): 8 KB
 constexpr size_t FF_HOP_BYTES = FF_HTMEM ? 0 : 2 * 2 * 2 * FF_KB_BYTES;      // hidden operand in shared memory
@@ -67,6 +67,7 @@ struct FfnParams {
   int C, Hd;                 // channels, hidden width
   int64_t M;
   int wslots; uint32_t wslot_bytes;
+  int wres;                  // the weights of a whole tile fit the ring: loaded once, resident for the kernel's lifetime
   const float* scale1; const float* shift1; float unscale1;
   const float* scale2; const float* shift2; float unscale2;
   int act; float act_param;
@@ -223,6 +224,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (j >= 1) load_w2(j - 1);
         }
         load_w2(nch - 1);
+        if (p.wres) break;          // one tile's worth of k-blocks is all of W1 and W2: they stay in their slots
       }
     }
   } else if (warp == 1) {
@@ -239,7 +241,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t a2 = t_acc2 + (ti & 1u) * (uint32_t)p.C;
         auto gemm = [&](uint32_t tacc, uint32_t da0, int nkb, uint32_t d_wlo, uint32_t idesc, bool fresh, uint64_t* done) {
           for (int kb = 0; kb < nkb; ++kb) {
-            FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
+            if (!p.wres || ti == 0) FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
             tc_fence_after();
             const uint32_t dah = da0 + kb * d_kb, dal = dah + d_lo, dbh = d_w0 + ws * d_wslot, dbl = dbh + d_wlo;
             if (elect_one()) {
@@ -249,7 +251,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 umma_f16_lh(tacc, dah + k, dbl + k, UMMA_HI_SW64, idesc, 1u);
                 umma_f16_lh(tacc, dah + k, dbh + k, UMMA_HI_SW64, idesc, 1u);
               }
-              umma_commit(&w_empty[ws]);
+              if (!p.wres) umma_commit(&w_empty[ws]);
               if (kb == nkb - 1) umma_commit(done);
             }
             __syncwarp();
@@ -264,7 +266,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             // the chunk's two A k-blocks come off the ring and are released with the weight slot
             const uint32_t tacc = t_acc1 + b * FF_HC;
             for (int kb = 0; kb < 2; ++kb) {
-              FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
+              if (!p.wres || ti == 0) FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
               FF_ACC(cy_x, FF_WAIT(&a_full[as], aph));
               tc_fence_after();
               const uint32_t dah = d_x0 + as * d_kb, dal = dah + d_lo, dbh = d_w0 + ws * d_wslot, dbl = dbh + d_w1lo;
@@ -275,7 +277,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                   umma_f16_lh(tacc, dah + k, dbl + k, UMMA_HI_SW64, idesc1, 1u);
                   umma_f16_lh(tacc, dah + k, dbh + k, UMMA_HI_SW64, idesc1, 1u);
                 }
-                umma_commit(&w_empty[ws]);
+                if (!p.wres) umma_commit(&w_empty[ws]);
                 umma_commit(&a_empty[as]);
                 if (kb == 1) umma_commit(&acc1_full[b]);
               }
@@ -295,7 +297,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tc_fence_after();
 #if FF_HTMEM
           for (int kb = 0; kb < FF_HC / 32; ++kb) {
-            FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
+            if (!p.wres || ti == 0) FF_ACC(cy_w, FF_WAIT(&w_full[ws], wph));
             tc_fence_after();
             const uint32_t tah = t_h + b * 64u + (uint32_t)kb * 16u, tal = tah + 32u;
             const uint32_t dbh = d_w0 + ws * d_wslot, dbl = dbh + d_w2lo;
@@ -306,7 +308,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 umma_f16_ts(a2, tah + 8u * k, dbl + 2u * k, UMMA_HI_SW64, idesc2, 1u);
                 umma_f16_ts(a2, tah + 8u * k, dbh + 2u * k, UMMA_HI_SW64, idesc2, 1u);
               }
-              umma_commit(&w_empty[ws]);
+              if (!p.wres) umma_commit(&w_empty[ws]);
               if (kb == FF_HC / 32 - 1) umma_commit(&h_empty[b]);
             }
             __syncwarp();
@@ -520,6 +522,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int64_t rr = row0 + it * 8 + lr;
           res[it] = rr < p.M ? __ldg(reinterpret_cast<const float4*>(p.x + rr * p.ldx + c + 4 * lq)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        const float4 s4 = *reinterpret_cast<const float4*>(s_sc2 + c + 4 * lq);
+        const float4 t4 = *reinterpret_cast<const float4*>(s_sh2 + c + 4 * lq);
         float v[16];
         FF_ACC(cy_tm, tmem_ld16_nowait(tacc + (uint32_t)c, v);
         tmem_ld_wait());
@@ -528,17 +532,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           warp_arrive(&acc2_empty[ti & 1u], lane);
         }
         FF_DECL(c_s0 = clock64());
+        // raw accumulators through the staging block; scale / shift are applied after the transpose, where a thread
+        // owns 4 fixed columns (2 shared-memory loads per block instead of 8 on the TMEM-load critical path)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 s4 = *reinterpret_cast<const float4*>(s_sc2 + c + 4 * q);
-          const float4 t4 = *reinterpret_cast<const float4*>(s_sh2 + c + 4 * q);
-          float4 o;
-          o.x = fmaf(v[4 * q + 0], s4.x, t4.x);
-          o.y = fmaf(v[4 * q + 1], s4.y, t4.y);
-          o.z = fmaf(v[4 * q + 2], s4.z, t4.z);
-          o.w = fmaf(v[4 * q + 3], s4.w, t4.w);
-          *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
-        }
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+              make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
 #ifdef FF_TRACE
         cy_st += clock64() - c_s0;
@@ -549,7 +548,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int rl = it * 8 + lr;
           const int64_t rr = row0 + rl;
           float4 o = *reinterpret_cast<const float4*>(stg + rl * 64 + ((lq ^ ((rl >> 1) & 3)) << 4));
-          o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w;
+          o.x = fmaf(o.x, s4.x, t4.x) + res[it].x;
+          o.y = fmaf(o.y, s4.y, t4.y) + res[it].y;
+          o.z = fmaf(o.z, s4.z, t4.z) + res[it].z;
+          o.w = fmaf(o.w, s4.w, t4.w) + res[it].w;
           if (rr < p.M) *reinterpret_cast<float4*>(p.y + rr * p.ldy + c + 4 * lq) = o;
         }
         __syncwarp();
@@ -611,6 +613,9 @@ extern "C" int grafp_ffn_fused_fwd(const float* x, int64_t ldx, int64_t M, int C
   int slots = (int)((FF_SMEM_BUDGET - fixed) / p.wslot_bytes);
   if (slots > FF_WMAX) slots = FF_WMAX;
   GRAFP_REQUIRE(slots >= 2, "ffn_fused: not enough shared memory");
+  const int kb_per_tile = (Hd / FF_HC) * (C / 32 + FF_HC / 32);       // W1 + W2 k-blocks a tile consumes
+  p.wres = kb_per_tile <= slots;
+  if (p.wres) slots = kb_per_tile;
   p.wslots = slots;
   p.aslots = 0;
   const size_t smem = fixed + (size_t)slots * p.wslot_bytes + 1024;
@@ -660,6 +665,9 @@ extern "C" int grafp_mrconv_fc2_fused_fwd(const float* x, int64_t ldx, const flo
   int slots = (int)((FF_SMEM_BUDGET - fixed) / p.wslot_bytes);
   if (slots > FF_WMAX) slots = FF_WMAX;
   GRAFP_REQUIRE(slots >= 2, "mrconv_fc2_fused: not enough shared memory");
+  const int kb_per_tile = (Hd / FF_HC) * (2 + FF_HC / 32);
+  p.wres = kb_per_tile <= slots;
+  if (p.wres) slots = kb_per_tile;
   p.wslots = slots;
   const size_t smem = fixed + (size_t)slots * p.wslot_bytes + 1024;
   const int64_t tiles = (M + TC_BM - 1) / TC_BM;

@@ -4,21 +4,27 @@ import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from neuralsampleid_b200 import ops, _prep
-C = int(sys.argv[1]); M = int(sys.argv[2])
+C = int(sys.argv[1]); M = int(sys.argv[2]); FFN = len(sys.argv) > 3 and sys.argv[3] == "ffn"
 dev = "cuda:0"
 torch.manual_seed(0)
 x, m, res = torch.randn(M, C, device=dev), torch.randn(M, C, device=dev).abs(), torch.randn(M, C, device=dev)
 l1 = _prep.make_linear(torch.randn(2 * C, C // 2, device=dev) / (C // 2) ** 0.5, torch.ones(2 * C, device=dev),
                        torch.zeros(2 * C, device=dev), 4, dual=True)
 l2 = _prep.make_linear(torch.randn(C, 2 * C, device=dev) / (2 * C) ** 0.5, torch.ones(C, device=dev), torch.zeros(C, device=dev))
-for _ in range(3): y = ops.mrconv_fc2_fused(x, m, l1, "relu", 0.0, l2, res)
+if FFN:
+    l1 = _prep.make_linear(torch.randn(4 * C, C, device=dev) / C ** 0.5, torch.ones(4 * C, device=dev), torch.zeros(4 * C, device=dev))
+    l2 = _prep.make_linear(torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5, torch.ones(C, device=dev), torch.zeros(C, device=dev))
+    run = lambda: ops.ffn_fused(x, l1, l2, "relu")
+else:
+    run = lambda: ops.mrconv_fc2_fused(x, m, l1, "relu", 0.0, l2, res)
+for _ in range(20): y = run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(5): y = ops.mrconv_fc2_fused(x, m, l1, "relu", 0.0, l2, res)
+for _ in range(50): y = run()
 e1.record(); torch.cuda.synchronize()
-us = 200 * e0.elapsed_time(e1)
-print("C %d M %d: %.1f us, %.2f TB/s on 16 M C bytes" % (C, M, us, 16.0 * M * C / us / 1e6))
+us = 20 * e0.elapsed_time(e1)
+print("%s C %d M %d: %.1f us, %.2f TB/s on its algorithmic bytes" % ("ffn" if FFN else "mrconv_fc2", C, M, us, (8.0 if FFN else 16.0) * M * C / us / 1e6))
 lib = ctypes.CDLL(os.path.join(ROOT, "neuralsampleid_b200", "libgrafp_sm100a.so"))
 if hasattr(lib, "grafp_debug_ffn_trace"):
     buf = (ctypes.c_ulonglong * 3072)()
