@@ -448,6 +448,37 @@ def test_simclr_eval_matches_golden(golden_dir):
     assert alive_total >= 5, alive_total       # of 8 (measured on B200: see the flip-rate test below)
 
 
+def test_create_fp_db_pipeline_matches_direct_calls():
+    """db.create_fp_db (the create_ref_db / create_query_db loop of test_fp.py:92-171 as a three-stream pipeline over a
+    captured model) writes, in order, exactly the fingerprints direct ``model(x, x)`` calls give -- full and ragged
+    batches, more batches than staging buffers -- and refuses batches / outputs that do not fit."""
+    from neuralsampleid_b200.db import create_fp_db
+    from neuralsampleid_b200.encoder.graph_encoder import GraphEncoder
+    from neuralsampleid_b200.graphed import GraphedSimCLR
+    from neuralsampleid_b200.simclr.simclr import SimCLR
+    from neuralsampleid_b200._lib import GrafpError
+    sd = synth.synth_state(synth.simclr_state_spec(CFG, "t"), 1236)
+    model = SimCLR(CFG, encoder=GraphEncoder(cfg=CFG, in_channels=CFG["n_filters"], k=3))
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    sizes = [8, 8, 5, 8, 1]
+    batches = [synth.synth_normal((b, 64, 128), 300 + i).pin_memory() for i, b in enumerate(sizes)]
+    with torch.no_grad():
+        want = torch.cat([model(x.to(DEV), x.to(DEV))[2] for x in batches]).cpu()
+        gsim = GraphedSimCLR(model, 8)
+        out = torch.zeros((sum(sizes) + 3, 128)).pin_memory()
+        n = create_fp_db(gsim, iter(batches), out)
+        torch.cuda.synchronize()
+    assert n == sum(sizes)
+    assert torch.equal(out[:n], want), float((out[:n] - want).abs().max())
+    assert float(out[n:].abs().max()) == 0.0
+    with pytest.raises(GrafpError):
+        create_fp_db(gsim, [torch.zeros((9, 64, 128))], out)
+    with pytest.raises(GrafpError):
+        create_fp_db(gsim, iter(batches), torch.zeros((10, 128)))
+    torch.cuda.synchronize()
+
+
 def test_knn_flip_rate_is_reported_and_bounded():
     """How often does a neighbour list differ from the oracle's, and at which reference gap?  512 segments, k = 3, every
     block.  Teacher-forced (the oracle's graphs drive the features, this path's kNN runs on its own fc1 output) the
