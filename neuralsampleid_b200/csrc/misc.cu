@@ -185,6 +185,116 @@ __global__ void peak_extract_kernel(const float* __restrict__ spec, const float*
   }
 }
 
+
+// Fast path (pf % 4 == 0, F in {4, 8, 16}, nodes <= 1024): persistent CTAs, one THREAD per node.
+// The (t-ramp, f-ramp) part of every output is the same for every segment: its partial sum -- the first 2*pb*pf terms
+// of the reference's accumulation order -- is formed once per CTA into a table and each segment only adds the
+// pb*pf spectrogram terms, in the same order: bit-identical to peak_extract_kernel.  The spectrogram is normalised
+// once per element (the per-output form divided every element F times), a thread reads its patch with 128-bit loads
+// and writes its node's F outputs as one contiguous run.
+template <int F>
+__global__ void __launch_bounds__(256)
+peak_extract_nodes_kernel(const float* __restrict__ spec, const float* __restrict__ w, const float* __restrict__ bias,
+                          int B, int n_mels, int n_frames, int pb, int pf, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int hw = n_mels * n_frames, pp = pb * pf;
+  const int gh = n_mels / pb, gw = n_frames / pf, nodes = gh * gw;
+  float* s_spec = sm;                                   // hw
+  float* s_w = s_spec + hw;                             // F * 3 * pp
+  float* s_pre = s_w + F * 3 * pp;                      // nodes * F: ramp partial sums
+  __shared__ float s_red[64];
+  __shared__ float s_mn, s_mx;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < F * 3 * pp; i += nt) s_w[i] = w[i];
+  __syncthreads();
+  const float tstep = n_frames > 1 ? 1.0f / (float)(n_frames - 1) : 0.0f;
+  const float fstep = n_mels > 1 ? 1.0f / (float)(n_mels - 1) : 0.0f;
+  for (int o = tid; o < nodes * F; o += nt) {
+    const int node = o / F, f = o - node * F;
+    const int gy = node / gw, gx = node - gy * gw;
+    const float* wf = s_w + f * 3 * pp;
+    float acc = 0.0f;
+    for (int ch = 0; ch < 2; ++ch)
+      for (int i = 0; i < pb; ++i) {
+        const int y = gy * pb + i;
+        for (int j = 0; j < pf; ++j) {
+          const int xx = gx * pf + j;
+          float v;
+          if (ch == 0) v = (xx < n_frames / 2) ? xx * tstep : 1.0f - (n_frames - 1 - xx) * tstep;
+          else v = (y < n_mels / 2) ? y * fstep : 1.0f - (n_mels - 1 - y) * fstep;
+          acc = fmaf(v, wf[ch * pp + i * pf + j], acc);
+        }
+      }
+    s_pre[o] = acc;
+  }
+  float bs[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) bs[f] = bias[f];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float4* sp4 = reinterpret_cast<const float4*>(spec + (size_t)b * hw);
+    float mn = INFINITY, mx = -INFINITY;
+    bool has_nan = false;                               // torch.min / torch.max propagate NaN
+    __syncthreads();                                    // the previous segment's patch reads are done
+    for (int i = tid; i < hw / 4; i += nt) {
+      const float4 v = __ldg(sp4 + i);
+      reinterpret_cast<float4*>(s_spec)[i] = v;
+      mn = fminf(fminf(mn, v.x), fminf(fminf(v.y, v.z), v.w));
+      mx = fmaxf(fmaxf(mx, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+      has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+    }
+    if (has_nan) mx = INFINITY, mn = -INFINITY;         // inf - (-inf) below: every normalised value NaN
+    mn = -warp_max(-mn);
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) { s_red[tid >> 5] = mn; s_red[32 + (tid >> 5)] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+      float a = s_red[0], c = s_red[32];
+      for (int i = 1; i < (nt >> 5); ++i) { a = fminf(a, s_red[i]); c = fmaxf(c, s_red[32 + i]); }
+      s_mn = a; s_mx = c;
+    }
+    __syncthreads();
+    const float lo = s_mn, den = s_mx - s_mn;
+    for (int i = tid; i < hw / 4; i += nt) {            // each thread normalises the elements it staged
+      float4 v = reinterpret_cast<float4*>(s_spec)[i];
+      v.x = __fdiv_rn(v.x - lo, den); v.y = __fdiv_rn(v.y - lo, den);
+      v.z = __fdiv_rn(v.z - lo, den); v.w = __fdiv_rn(v.w - lo, den);
+      reinterpret_cast<float4*>(s_spec)[i] = v;
+    }
+    __syncthreads();
+    for (int node = tid; node < nodes; node += nt) {
+      const int gy = node / gw, gx = node - gy * gw;
+      float acc[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] = s_pre[node * F + f];
+      for (int i = 0; i < pb; ++i) {
+        const float* row = s_spec + (gy * pb + i) * n_frames + gx * pf;
+        for (int j = 0; j < pf; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(row + j);
+          const float* wj = s_w + 2 * pp + i * pf + j;
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wj + f * 3 * pp);      // broadcast
+            acc[f] = fmaf(v.x, w4.x, acc[f]);
+            acc[f] = fmaf(v.y, w4.y, acc[f]);
+            acc[f] = fmaf(v.z, w4.z, acc[f]);
+            acc[f] = fmaf(v.w, w4.w, acc[f]);
+          }
+        }
+      }
+      float4* o4 = reinterpret_cast<float4*>(out + ((size_t)b * nodes + node) * F);
+#pragma unroll
+      for (int f = 0; f < F; f += 4) {
+        float4 r;
+        r.x = acc[f] + bs[f];         r.x = r.x < 0.0f ? 0.0f : r.x;                    // NaN propagates
+        r.y = acc[f + 1] + bs[f + 1]; r.y = r.y < 0.0f ? 0.0f : r.y;
+        r.z = acc[f + 2] + bs[f + 2]; r.z = r.z < 0.0f ? 0.0f : r.z;
+        r.w = acc[f + 3] + bs[f + 3]; r.w = r.w < 0.0f ? 0.0f : r.w;
+        o4[f / 4] = r;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Stem: per-node linear with a tiny input width (Conv2d(Cin -> Cout, 1x1) + BN + activation,
 // graph_encoder.py:151-153) straight from the reference's (B, Cin, N) layout.  K = Cin <= 16 is
@@ -284,6 +394,29 @@ int grafp_peak_extract_fwd(const float* spec, const float* w, const float* bias,
   GRAFP_REQUIRE(pb > 0 && pf > 0 && n_mels % pb == 0 && n_frames % pf == 0,
                 "peak_extract: patch (%d,%d) must tile (%d,%d)", pb, pf, n_mels, n_frames);
   if (B == 0) return 0;
+  {
+    // fast path: one thread per node over persistent CTAs (bit-identical; GRAFP_PEAK_SIMPLE=1 keeps the simple kernel)
+    const char* env = getenv("GRAFP_PEAK_SIMPLE");
+    const bool simple = env && atoi(env) != 0;
+    const int nodes = (n_mels / pb) * (n_frames / pf), pp = pb * pf;
+    const size_t sm2 = ((size_t)n_mels * n_frames + (size_t)F * 3 * pp + (size_t)nodes * F) * sizeof(float);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(spec) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (!simple && aligned && pf % 4 == 0 && (n_mels * n_frames) % 4 == 0 && (3 * pp) % 4 == 0 && nodes <= 4096 &&
+        (F == 4 || F == 8 || F == 16) && sm2 <= 100 * 1024) {
+      int per_sm = (int)((200 * 1024) / (sm2 + 1024));
+      if (per_sm > 4) per_sm = 4;
+      int grid = sm_count() * per_sm;
+      if (grid > B) grid = B;
+      auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        kern<<<grid, 256, sm2, as_stream(stream)>>>(spec, w, bias, B, n_mels, n_frames, pb, pf, out);
+      };
+      if (F == 4) launch(peak_extract_nodes_kernel<4>);
+      else if (F == 8) launch(peak_extract_nodes_kernel<8>);
+      else launch(peak_extract_nodes_kernel<16>);
+      return check_launch("peak_extract_nodes");
+    }
+  }
   size_t smem = ((size_t)n_mels * n_frames + (size_t)F * 3 * pb * pf) * sizeof(float);
   GRAFP_REQUIRE(smem <= 200 * 1024, "peak_extract: segment too large for shared memory");
   static bool attr_set = false;

@@ -648,6 +648,27 @@ def test_peak_extractor_matches_oracle():
     assert torch.allclose(got, want_nodes, rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("B,F,shape,patch", [(5, 8, (64, 128), (4, 8)), (700, 8, (64, 128), (4, 8)),
+                                             (9, 16, (32, 64), (8, 4)), (3, 4, (64, 128), (2, 16))])
+def test_peak_extractor_node_kernel_is_bit_identical(monkeypatch, B, F, shape, patch):
+    """The one-thread-per-node peak extractor (persistent CTAs, ramp partial sums tabulated once, spectrogram normalised
+    once per element) keeps the accumulation order of the simple one-CTA-per-segment kernel: bit-identical, more
+    segments than CTAs, other patch shapes, NaN and constant segments included."""
+    ops = _ops()
+    s = synth.synth_normal((B,) + shape, 45).to(DEV)
+    s[B // 2, 3, 5] = float("nan")                       # torch.min / max propagate NaN: the whole segment is NaN
+    s[B - 1] = 0.25                                      # max == min: 0 / 0
+    w = synth.synth_normal((F, 3) + patch, 46).to(DEV)
+    b = synth.synth_normal((F,), 47).to(DEV)
+    got = ops.peak_extract(s, w, b)
+    monkeypatch.setenv("GRAFP_PEAK_SIMPLE", "1")
+    want = ops.peak_extract(s, w, b)
+    assert got.shape == want.shape
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got, nan=7.0), torch.nan_to_num(want, nan=7.0))
+    assert bool(torch.isnan(got).any()) and bool((~torch.isnan(got)).any())
+
+
 # ------------------------------------------------------------------------------------------
 # NT-Xent
 # ------------------------------------------------------------------------------------------
