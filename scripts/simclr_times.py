@@ -21,6 +21,7 @@ with torch.no_grad():
 rows = sorted(timer.summary().items(), key=lambda kv: -kv[1]["ms"])
 tot = sum(v["ms"] for _, v in rows)
 print("total %.3f ms over %d entries" % (tot, len(rows)))
+ALL = len(sys.argv) > 2
 for k, v in rows:
-    if not k.startswith(("gemm m=26", "gemm m=13", "knn", "aggregate", "ffn_fused", "mrconv", "gemm m=52", "gemm m=10")):
+    if ALL or not k.startswith(("gemm m=26", "gemm m=13", "knn", "aggregate", "ffn_fused", "mrconv", "gemm m=52", "gemm m=10")):
         print("%-50s %.3f ms (%d calls)" % (k, v["ms"], v["calls"]))
