@@ -360,6 +360,24 @@ def extra_records(args, world, rank, dev, barrier, max_over_ranks):
                 out["chunks128"] = {"ms_per_chunk": e0.elapsed_time(e1) / 50, "value": 128 * 50 / (e0.elapsed_time(e1) * 1e-3),
                                     "unit": "segments/s", "config": "generate.py:40-46 call shape: one 128-segment chunk, one "
                                                                    "view, CUDA graph replay, one GPU"}
+                # the same chunks through the product's database builder: pinned host in / out, and 1-4 captured lanes
+                # on their own streams (a 128-segment chunk leaves most SMs idle from stage 3 on)
+                lanes = [g128] + [GraphedSimCLR(model, 128) for _ in range(3)]
+                x128h = torch.randn((128, 64, 128)).pin_memory()
+                fp128 = torch.empty((200 * 128, 128), dtype=torch.float32).pin_memory()
+                piped = {}
+                for nl in (1, 2, 3, 4):
+                    create_fp_db(lanes[:nl], (x128h for _ in range(20)), fp128)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    create_fp_db(lanes[:nl], (x128h for _ in range(200)), fp128)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    piped["lanes%d" % nl] = 128 * 200 / (e0.elapsed_time(e1) * 1e-3)
+                out["chunks128"]["create_fp_db"] = dict(piped, unit="segments/s",
+                                                         config="200 chunks of 128 pinned-host segments through "
+                                                                "db.create_fp_db, H2D / D2H included, 1-4 graph lanes on their own streams")
+                del lanes
         del model
     return out
 

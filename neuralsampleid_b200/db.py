@@ -51,55 +51,65 @@ def load_fingerprints(source_dir: str, name: str) -> Tuple[np.ndarray, np.ndarra
 @torch.no_grad()
 def create_fp_db(gsim, batches, out: torch.Tensor) -> int:
     """Fingerprints of a stream of host batches into a host array: the loop of the reference's ``create_ref_db`` /
-    ``create_query_db`` (test_fp.py:92-171: ``model(x, x)`` per chunk, ``z_i`` appended) as a three-stream pipeline over
-    a captured model (``graphed.GraphedSimCLR``): the host -> device copy of batch i+1 and the device -> host copy of
-    batch i-1 overlap the kernels of batch i (double-buffered staging on both sides).
+    ``create_query_db`` (test_fp.py:92-171: ``model(x, x)`` per chunk, ``z_i`` appended) as a pipeline over a captured
+    model (``graphed.GraphedSimCLR``): the host -> device copy of batch i+1 and the device -> host copy of batch i-1
+    overlap the kernels of batch i (double-buffered staging on both sides).
 
-    ``batches``: iterable of host tensors (b, n_mels, n_frames) float32 with b <= gsim.input.shape[0] (pinned memory for
+    ``gsim``: one captured model, or a LIST of captures of the same model (each with its own buffers): batch i then runs
+    on lane i % len(gsim), every lane on its own stream.  At the reference's call shape (chunks of <= 128 segments,
+    generate.py:40-46) the kernels of one chunk leave most SMs idle from stage 3 on (64- and 32-CTA grids), so two or
+    three lanes overlap; large captures (thousands of segments) fill the machine and want one lane.
+    ``batches``: iterable of host tensors (b, n_mels, n_frames) float32 with b <= the captured batch (pinned memory for
     asynchronous copies); ``out``: host tensor (>= total, d) float32 (pinned likewise), filled in order.  Returns the
     number of fingerprints written.  Rows of a short batch beyond b are computed on stale input and dropped (segments
     are independent: SURVEY section 8e)."""
-    dev = gsim.input.device
-    cap = gsim.input.shape[0]
-    s_comp = torch.cuda.current_stream(dev)
+    lanes = list(gsim) if isinstance(gsim, (list, tuple)) else [gsim]
+    L = len(lanes)
+    dev = lanes[0].input.device
+    cap = lanes[0].input.shape[0]
+    cur = torch.cuda.current_stream(dev)
+    s_comp = [cur] + [torch.cuda.Stream(device=dev) for _ in range(L - 1)]
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    xin = [torch.empty_like(gsim.input) for _ in range(2)]
-    zout = [torch.empty_like(gsim.z) for _ in range(2)]
-    e_in = [torch.cuda.Event() for _ in range(2)]
-    e_in_free = [torch.cuda.Event() for _ in range(2)]
-    e_comp = [torch.cuda.Event() for _ in range(2)]
-    e_out_free = [torch.cuda.Event() for _ in range(2)]
-    s_in.wait_stream(s_comp)
-    s_out.wait_stream(s_comp)
+    D = 2 * L                                   # staging depth: two batches per lane
+    xin = [torch.empty_like(lanes[0].input) for _ in range(D)]
+    zout = [torch.empty_like(lanes[0].z) for _ in range(D)]
+    e_in = [torch.cuda.Event() for _ in range(D)]
+    e_in_free = [torch.cuda.Event() for _ in range(D)]
+    e_comp = [torch.cuda.Event() for _ in range(D)]
+    e_out_free = [torch.cuda.Event() for _ in range(D)]
+    for s in s_comp[1:] + [s_in, s_out]:
+        s.wait_stream(cur)
     n = 0
     for i, x in enumerate(batches):
         b = int(x.shape[0])
-        if b > cap or tuple(x.shape[1:]) != tuple(gsim.input.shape[1:]):
+        if b > cap or tuple(x.shape[1:]) != tuple(lanes[0].input.shape[1:]):
             raise GrafpError("create_fp_db: batch of shape %s does not fit the captured model %s"
-                             % (tuple(x.shape), tuple(gsim.input.shape)))
+                             % (tuple(x.shape), tuple(lanes[0].input.shape)))
         if n + b > out.shape[0]:
             raise GrafpError("create_fp_db: output holds %d rows, batch %d needs %d" % (out.shape[0], i, n + b))
-        q = i & 1
+        q, lane = i % D, i % L
+        g, sc = lanes[lane], s_comp[lane]
         with torch.cuda.stream(s_in):
-            if i >= 2:
+            if i >= D:
                 s_in.wait_event(e_in_free[q])
             xin[q][:b].copy_(x, non_blocking=True)
             e_in[q].record(s_in)
-        s_comp.wait_event(e_in[q])
-        gsim.input.copy_(xin[q], non_blocking=True)
-        e_in_free[q].record(s_comp)
-        gsim.replay()
-        if i >= 2:
-            s_comp.wait_event(e_out_free[q])
-        zout[q].copy_(gsim.z, non_blocking=True)
-        e_comp[q].record(s_comp)
+        with torch.cuda.stream(sc):
+            sc.wait_event(e_in[q])
+            g.input.copy_(xin[q], non_blocking=True)
+            e_in_free[q].record(sc)
+            g.replay()
+            if i >= D:
+                sc.wait_event(e_out_free[q])
+            zout[q].copy_(g.z, non_blocking=True)
+            e_comp[q].record(sc)
         with torch.cuda.stream(s_out):
             s_out.wait_event(e_comp[q])
             out[n:n + b].copy_(zout[q][:b], non_blocking=True)
             e_out_free[q].record(s_out)
         n += b
-    s_comp.wait_stream(s_out)
-    s_comp.wait_stream(s_in)
+    for s in s_comp[1:] + [s_in, s_out]:
+        cur.wait_stream(s)
     return n
 
 

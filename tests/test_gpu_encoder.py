@@ -464,7 +464,8 @@ def test_create_fp_db_pipeline_matches_direct_calls():
     sizes = [8, 8, 5, 8, 1]
     batches = [synth.synth_normal((b, 64, 128), 300 + i).pin_memory() for i, b in enumerate(sizes)]
     with torch.no_grad():
-        want = torch.cat([model(x.to(DEV), x.to(DEV))[2] for x in batches]).cpu()
+        want_parts = [model(x.to(DEV), x.to(DEV))[2].cpu() for x in batches]
+        want = torch.cat(want_parts)
         gsim = GraphedSimCLR(model, 8)
         out = torch.zeros((sum(sizes) + 3, 128)).pin_memory()
         n = create_fp_db(gsim, iter(batches), out)
@@ -472,6 +473,17 @@ def test_create_fp_db_pipeline_matches_direct_calls():
     assert n == sum(sizes)
     assert torch.equal(out[:n], want), float((out[:n] - want).abs().max())
     assert float(out[n:].abs().max()) == 0.0
+    # several captured lanes on their own streams (the <= 128-segment call shape): same fingerprints, same order
+    with torch.no_grad():
+        lanes = [gsim, GraphedSimCLR(model, 8), GraphedSimCLR(model, 8)]
+        many = [batches[i % len(batches)] for i in range(11)]
+        want_many = torch.cat([want_parts[i % len(batches)] for i in range(11)])
+        for nl in (2, 3):
+            out2 = torch.zeros((want_many.shape[0], 128)).pin_memory()
+            n2 = create_fp_db(lanes[:nl], iter(many), out2)
+            torch.cuda.synchronize()
+            assert n2 == want_many.shape[0]
+            assert torch.equal(out2, want_many), (nl, float((out2 - want_many).abs().max()))
     with pytest.raises(GrafpError):
         create_fp_db(gsim, [torch.zeros((9, 64, 128))], out)
     with pytest.raises(GrafpError):
