@@ -315,4 +315,5 @@ def test_bench_reference_arm_and_traffic_file():
     sys.path.insert(0, ROOT)
     import bench
     t = bench.ncu_traffic(4096)
-    assert t["gemm"] > 6e10 and t["knn"] > 3e9 and t["aggregate"] > 5e9 and "ncu" in t["note"]
+    # committed ncu capture of the final build: GEMM class 57 GB per 4096-segment step (round 1: 70 GB)
+    assert 4e10 < t["gemm"] < 6e10 and t["knn"] > 3e9 and t["aggregate"] > 5e9 and "ncu" in t["note"]
