@@ -4,14 +4,16 @@
 // The two 1x1-conv GEMMs of the FFN are HBM-bound at C <= 128 (stages 1-2 of size 't'): the 4C-wide hidden tensor
 // (1.07 GB at 4096 segments) is written by fc1 and read back by fc2.  Here a persistent CTA owns 128 rows at a time:
 //   TMA        x rows (fp32, 128B swizzle) through a small raw ring; weight k-blocks (pre-split fp16 hi/lo) through
-//              a ring, in exactly the order the MMA warp consumes them
+//              a ring, in exactly the order the MMA warp consumes them -- or, when a tile's k-blocks all fit (C = 64),
+//              loaded once and resident for the kernel's lifetime (wres)
 //   transform  x -> fp16 hi / lo operand k-blocks (the f16x3 split of gemm_tc.cu), resident for the whole tile
 //   GEMM 1     for every chunk of 64 hidden columns: acc1[j & 1] (TMEM, 64 columns) = x W1_j^T, 3 kind::f16 passes
-//   epilogue 1 TMEM -> registers -> s1 / t1 / activation -> fp16 hi / lo -> shared memory, written directly in the
-//              K-major 64B-swizzled operand layout GEMM 2 reads (the same layout the un-fused fc1 epilogue stages for
-//              its TMA store of the split activation)
-//   GEMM 2     acc2 (TMEM, C columns) += h_j W2[:, chunk j]^T
-//   epilogue 2 s2 / t2 + the shortcut x (re-read from L2) -> y
+//   epilogue 1 TMEM -> registers -> s1 / t1 / activation -> fp16 hi / lo pairs -> tcgen05.st into TMEM (lane = row,
+//              two k-elements per 32-bit column: the layout of an A operand in TMEM).  FF_HTMEM = 0: into shared memory,
+//              in the K-major 64B-swizzled operand layout instead
+//   GEMM 2     acc2 (TMEM, C columns) += h_j W2[:, chunk j]^T, A operand from TMEM
+//   epilogue 2 raw accumulators -> per-warp staging block (transpose) -> s2 / t2 + the shortcut x (L2 hit), coalesced -> y
+// TMEM: acc1 2 x 64 | acc2 2 x C | h 2 x (32 hi + 32 lo) columns = 512 at C = 128.
 // GEMM 1 of chunk j+1 is issued before GEMM 2 of chunk j, so the tensor pipe works while epilogue 1 converts.
 // The arithmetic (operand values, accumulation order over k) is that of the two gemm_tc.cu launches it replaces:
 // the result is bit-identical (tests/test_gpu_kernels.py::test_ffn_fused_bit_exact).
