@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1)
 mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int B,
                            int N, int C, int k, int stages, uint32_t stage_bytes, int idx_in_smem,
                            float* __restrict__ m, uint32_t* __restrict__ arg_out) {
+  pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[AGG_MAX_STAGES];
   const uint32_t graph_floats = (uint32_t)N * C;
@@ -58,6 +59,7 @@ mr_aggregate_staged_kernel(const float* __restrict__ x, const int32_t* __restric
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();            // nothing above reads or writes a tensor (common.cuh)
 
   auto issue = [&](int s, int g) {
     unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
@@ -464,12 +466,12 @@ int grafp_mr_aggregate_fwd(const float* x, const int32_t* idx, int B, int N, int
     const size_t smem = (size_t)stages * stage_bytes;
     if (arg_out) {
       cudaFuncSetAttribute(mr_aggregate_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      mr_aggregate_staged_kernel<true><<<grid, AGG_THREADS, smem, st>>>(
-          x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m, reinterpret_cast<uint32_t*>(arg_out));
+      launch_ex(mr_aggregate_staged_kernel<true>, dim3(grid), dim3(AGG_THREADS), smem, st, 0,
+                x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m, reinterpret_cast<uint32_t*>(arg_out));
     } else {
       cudaFuncSetAttribute(mr_aggregate_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      mr_aggregate_staged_kernel<false><<<grid, AGG_THREADS, smem, st>>>(
-          x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m, nullptr);
+      launch_ex(mr_aggregate_staged_kernel<false>, dim3(grid), dim3(AGG_THREADS), smem, st, 0,
+                x, idx, B, N, C, k, stages, (uint32_t)stage_bytes, idx_in_smem, m, (uint32_t*)nullptr);
     }
     return check_launch("mr_aggregate_staged");
   }

@@ -16,6 +16,46 @@ int check_launch(const char* what);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (GRAFP_PDL=1) -------------------------------------------------------------------
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the stream
+// is still running.  Every such kernel here (a) triggers its own dependents at its first instruction and (b) executes
+// griddepcontrol.wait -- which returns once the predecessor grid has completed and its memory is visible -- after the
+// prologue that touches no global data (barrier init, TMEM allocation, descriptor prefetch, staging of constant
+// per-channel parameters) and before ANY access to tensors another kernel writes.  What overlaps is the launch latency
+// and that prologue; the data path is ordered exactly as without the attribute.  Without the attribute both
+// instructions are no-ops.
+int pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 0) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define GRAFP_REQUIRE(cond, ...) \
   do { if (!(cond)) return ::grafp::fail(__VA_ARGS__); } while (0)
 

@@ -116,6 +116,7 @@ template <bool MR>
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t raw_full[FF_RAW], raw_empty[FF_RAW];
   __shared__ __align__(8) uint64_t xop_full, xop_free;
@@ -174,6 +175,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const uint32_t t_acc1 = tmem_base;                      // 2 x 64 columns
   const uint32_t t_acc2 = tmem_base + 128;                // 2 x C columns (C <= 128)
   const uint32_t t_h = tmem_base + 384;                   // FF_HTMEM: 2 buffers x [hi 32 | lo 32] columns of packed fp16 pairs
+  pdl_wait();            // above: barriers, TMEM, the folded (constant) scale / shift vectors -- no tensor access (common.cuh)
 
   if (warp == 0) {
     // ===== TMA: x rows of my tiles, k-block by k-block, into the raw ring =====
@@ -625,7 +627,7 @@ extern "C" int grafp_ffn_fused_fwd(const float* x, int64_t ldx, int64_t M, int C
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;
   cudaFuncSetAttribute(ffn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ffn_fused_kernel<false><<<grid, FF_THREADS, smem, as_stream(stream)>>>(mX, mX, mW1, mW2, p);
+  launch_ex(ffn_fused_kernel<false>, dim3(grid), dim3(FF_THREADS), smem, as_stream(stream), 0, mX, mX, mW1, mW2, p);
   return check_launch("ffn_fused");
 }
 
@@ -676,6 +678,6 @@ extern "C" int grafp_mrconv_fc2_fused_fwd(const float* x, int64_t ldx, const flo
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;
   cudaFuncSetAttribute(ffn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ffn_fused_kernel<true><<<grid, FF_THREADS, smem, as_stream(stream)>>>(mX, mM, mW1, mW2, p);
+  launch_ex(ffn_fused_kernel<true>, dim3(grid), dim3(FF_THREADS), smem, as_stream(stream), 0, mX, mM, mW1, mW2, p);
   return check_launch("mrconv_fc2_fused");
 }

@@ -176,6 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmYs, const __grid_constant__ CUtensorMap tmR,
                const TcParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t xf_bar[TC_MAX_STAGES];
@@ -261,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (kCluster == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();            // nothing above reads or writes a tensor (common.cuh)
 
   if (warp == 0 || warp == 14) {
     // ===== TMA producers =====
@@ -1044,19 +1046,7 @@ int gemm_tc_launch(const grafp_gemm_args& a, int passes, int fmt, cudaStream_t s
     kern = passes == 3 ? (cluster == 2 ? gemm_tc_kernel<3, 2, false, false, false> : gemm_tc_kernel<3, 1, false, false, false>)
                        : (cluster == 2 ? gemm_tc_kernel<1, 2, false, false, false> : gemm_tc_kernel<1, 1, false, false, false>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA1, mA2, mW, mY, mYs, mR, p);
+  cudaError_t le = launch_ex(kern, dim3(grid), dim3(TC_THREADS), smem, st, cluster, mA1, mA2, mW, mY, mYs, mR, p);
   if (le != cudaSuccess) return fail("gemm_tc launch: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc");
 }

@@ -89,6 +89,7 @@ knn_rownorm_kernel(const float* __restrict__ x, int64_t M, int C, int normalize,
 template <int KMAX>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[KT_MAX_STAGES];
   __shared__ __align__(8) uint64_t xf_bar[KT_MAX_STAGES];
@@ -132,6 +133,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmCols, const KnnTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();            // nothing above reads or writes a tensor (common.cuh)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -479,7 +481,7 @@ static int knn_tc_launch_t(const CUtensorMap& mc, KnnTcParams p, int grid, cudaS
   p.stages = stages;
   const size_t smem = stage_bytes * stages + list_bytes + 1024;
   cudaFuncSetAttribute(knn_tc_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  knn_tc_kernel<KMAX><<<grid, KT_THREADS, smem, st>>>(mc, p);
+  launch_ex(knn_tc_kernel<KMAX>, dim3(grid), dim3(KT_THREADS), smem, st, 0, mc, p);
   return check_launch("knn_tc");
 }
 

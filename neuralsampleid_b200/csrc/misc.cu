@@ -22,6 +22,12 @@ int check_launch(const char* what) {
   return 0;
 }
 
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GRAFP_PDL"); v = e ? (atoi(e) != 0) : 0; }
+  return v;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
